@@ -1,0 +1,217 @@
+/*
+ * vqs_b200.h -- C ABI of libvqs_b200.so: hand-written sm_100a CUDA kernels for the VQ-VAE-Speech
+ * training hot path (VQ bottleneck + Conv1d encoder / residual stack / jitter / deconvolutional decoder
+ * + MSE + AMSGrad).  This is the drop-in boundary: everything above it is host code mirroring the
+ * reference's torch.nn.Module interface; everything below it is CUDA.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, non-zero on error (a cudaError_t or a VQS_ERR_* code);
+ *     vqs_last_error() returns a thread-local message.  No exceptions cross the ABI.
+ *   - all tensor pointers are DEVICE pointers owned by the caller (the PyTorch caching allocator in the
+ *     Python host); the library allocates nothing persistent and never synchronises the device, so every
+ *     call is stream-ordered on `stream` and CUDA-graph capturable.
+ *   - all floating-point tensors are fp32, indices are int64 (the reference's torch.argmin dtype).
+ *   - "NCL" = contiguous (batch, channels, length) as torch.nn.Conv1d uses.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   src/models/vector_quantizer_ema.py:83-183   VectorQuantizerEMA.forward   -> vqs_vq_assign, vqs_vq_ema_update,
+ *                                                                              vqs_vq_quantize, vqs_vq_backward
+ *   src/models/vector_quantizer.py:70-156       VectorQuantizer.forward      -> same + vqs_vq_grad_codebook
+ *   src/modules/conv1d_builder.py:33-44 / conv_transpose1d_builder.py:33-44 (nn.Conv1d / nn.ConvTranspose1d
+ *   forward and the autograd backward)                                       -> vqs_conv_gemm, vqs_wgrad_gemm,
+ *                                                                              vqs_bias_grad, vqs_permute_weight
+ *   src/modules/residual.py:31-70, residual_stack.py:34-46 (ReLU / skip adds) -> epilogue flags of vqs_conv_gemm
+ *   src/modules/jitter.py:47-70                  Jitter.forward               -> vqs_jitter_fwd / vqs_jitter_bwd
+ *   src/models/deconvolutional_decoder.py:66,117 nn.Upsample(scale_factor=2)  -> vqs_upsample2_fwd / _bwd
+ *   src/experiments/convolutional_trainer.py:40,54 nn.MSELoss                 -> vqs_mse_fwd_bwd
+ *   src/experiments/convolutional_trainer.py:41-42,68 optim.Adam(amsgrad=True) -> vqs_amsgrad_step
+ */
+#ifndef VQS_B200_H
+#define VQS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vqs_stream_t; /* a cudaStream_t */
+
+#define VQS_ERR_ARG 10001        /* invalid argument (shape, NULL pointer, unsupported size) */
+#define VQS_ERR_WORKSPACE 10002  /* workspace too small */
+
+/* ------------------------------------------------------------------------------------------------ */
+/* library                                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+int vqs_version(void);
+const char* vqs_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
+long long vqs_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* VQ bottleneck                                                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+/* Row layouts.  FLAT_ND: z is a contiguous (N, D) matrix, N = B*T.
+ * BDT_AS_DTB: z is a contiguous (B, D, T) tensor and rows are formed exactly as the reference does,
+ * `inputs.permute(1, 2, 0).contiguous().view(-1, D)` (vector_quantizer_ema.py:101-106): row r holds flat
+ * elements [r*D, (r+1)*D) of the (D, T, B) ordering, flat element f = d*T*B + t*B + b <- z[b, d, t]. */
+#define VQS_LAYOUT_FLAT_ND 0
+#define VQS_LAYOUT_BDT_AS_DTB 1
+
+/* bytes of scratch the VQ entry points need for (K, D); pass at least this much as `workspace`. */
+size_t vqs_vq_workspace_bytes(int K, int D);
+
+/* Nearest-code search (vector_quantizer_ema.py:109-117): d[n,k] = (sum_j x_nj^2 + sum_j e_kj^2) - 2 sum_j x_nj e_kj
+ * in fp32, idx[n] = first minimum over k.  Also accumulates the per-code statistics the EMA update and the
+ * codebook gradient need: stats = [counts (K) | dw (K*D)], counts[k] = #rows assigned to k, dw[k] = sum of those rows
+ * (`torch.sum(encodings, 0)`, `encodings.t() @ flat_input`, :145,:153) -- deterministic two-stage reduction.
+ * Optional outputs (NULL to skip): dmin2 (N, 2) = best and second-best distance per row (near-tie report),
+ * distances (N, K). */
+int vqs_vq_assign(const float* z, int layout, int B, int D, int T, const float* codebook, int K,
+                  int64_t* idx, float* stats, float* dmin2, float* distances,
+                  void* workspace, size_t workspace_bytes, vqs_stream_t stream);
+
+/* encodings = zeros(N, K).scatter_(1, idx, 1)  (vector_quantizer_ema.py:118-119). */
+int vqs_vq_one_hot(const int64_t* idx, long long N, int K, float* encodings, vqs_stream_t stream);
+
+/* EMA codebook update with Laplace smoothing, in place (vector_quantizer_ema.py:143-156):
+ *   cs <- cs*decay + (1-decay)*counts ; n = sum(cs) ; cs <- (cs + eps) / (n + K*eps) * n
+ *   ema_w <- ema_w*decay + (1-decay)*dw ; embedding <- ema_w / cs[:, None]
+ * `stats` is the [counts | dw] vector of vqs_vq_assign (allreduced over ranks under data parallelism). */
+int vqs_vq_ema_update(float* cluster_size, float* ema_w, float* embedding, const float* stats,
+                      float decay, float one_minus_decay, float eps, float k_eps, int K, int D, vqs_stream_t stream);
+
+/* Quantise + straight-through + loss terms (vector_quantizer_ema.py:159-176):
+ *   q = codebook[idx] ; out = x + (q - x) (same layout as z) ; sse = sum (q - x)^2
+ *   scalars[0] = sse, [1] = e_latent = sse / (N*D), [2] = perplexity = exp(-sum p log(p + 1e-10)), p = counts / n_rows_total,
+ *   [3] = beta * e_latent (VectorQuantizerEMA's vq_loss), [4] = e_latent + beta * e_latent (VectorQuantizer's vq_loss)
+ * `counts` (K) are the (global) counts; n_rows_total is the number of rows they were taken over.
+ * q_rows: optional (N, D) `concatenated_quantized` (:162), NULL to skip. */
+int vqs_vq_quantize(const float* z, int layout, int B, int D, int T, const int64_t* idx, const float* codebook, int K,
+                    float* out, float* q_rows, const float* counts, double n_rows_total, float beta, float* scalars,
+                    void* workspace, size_t workspace_bytes, vqs_stream_t stream);
+
+/* Backward of the bottleneck w.r.t. its input (autograd of :165-169):
+ *   grad_z = g_out + g_loss[0] * coef * (x - q),  coef = 2*beta/(N*D) supplied by the caller; g_loss is a device scalar. */
+int vqs_vq_backward(const float* g_out, const float* g_loss, float coef, const float* z, int layout, int B, int D, int T,
+                    const int64_t* idx, const float* codebook, int K, float* grad_z, vqs_stream_t stream);
+
+/* Codebook gradient of the non-EMA VectorQuantizer (autograd of vector_quantizer.py:136-139):
+ *   grad_E[k] (+)= g_loss[0] * coef * (counts[k] * E[k] - dw[k]),  coef = 2/(N*D). */
+int vqs_vq_grad_codebook(const float* stats, const float* codebook, const float* g_loss, float coef, int K, int D,
+                         float* grad_E, int accumulate, vqs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Conv1d / ConvTranspose1d as implicit GEMM                                                        */
+/* ------------------------------------------------------------------------------------------------ */
+/* One descriptor covers nn.Conv1d forward, its dgrad, nn.ConvTranspose1d (stride 1) forward and its dgrad:
+ *
+ *   acc[b, m, l] = sum_{c < Cred, j < ksz} A[m, c*ksz + j] * X'[b, c, p(l, j)]
+ *   p(l, j): pn = l*l_mul + j*j_mul + off ; valid iff pn % l_div == 0 and 0 <= pn/l_div < Lin ; X' = 0 when invalid
+ *   X'[b, c, p] = X[b*x_sb + c*x_sc + p*x_sl]  (relu'd first when x_relu)
+ *
+ * A is a row-major (M, Cred*ksz) matrix: the nn.Conv1d weight (Cout, Cin, k) as is for a forward conv and
+ * the nn.ConvTranspose1d weight (Cin, Cout, k) as is for its dgrad; vqs_permute_weight produces the
+ * (d1, d0, k) arrangement the other two cases need.
+ *
+ * Epilogue, per output element (b, m, l), out tensors are NCL (B, M, Lout):
+ *   v = acc + bias[m]                       (bias may be NULL)
+ *   v += add_pre  (relu(add_pre) when add_pre_relu)
+ *   if relu: v = max(v, 0)
+ *   if mask_out: mask_out = (v > 0)
+ *   if mask: v = mask_on ? v : 0            (mask_kind 1: float tensor > 0; 2: uint8 tensor != 0)
+ *   v += add_post
+ *   out = v ;  if out2: out2 = (mask2 on) ? v : 0
+ */
+typedef struct vqs_conv_gemm_desc {
+  const float* A;
+  const float* X;
+  int M, Cred, ksz;
+  int B, Lin, Lout;
+  long long x_sb, x_sc, x_sl;
+  int l_mul, j_mul, off, l_div;
+  int x_relu;
+  const float* bias;
+  const float* add_pre;
+  int add_pre_relu;
+  int relu;
+  unsigned char* mask_out;
+  const void* mask;
+  int mask_kind;
+  const float* add_post;
+  float* out;
+  float* out2;
+  const void* mask2;
+  int mask2_kind;
+} vqs_conv_gemm_desc;
+
+int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream);
+
+/* Weight gradient of nn.Conv1d / nn.ConvTranspose1d (autograd of the above):
+ *
+ *   dW[m, c*ksz + j] (+)= sum_{b, l < La} Aact[b, m, l] * X'[b, c, l*l_mul + j*j_mul + off]   (0 outside [0, Lx))
+ *
+ * Aact is NCL (B, M, La), X is NCL (B, Cred, Lx) (relu'd on load when x_relu).  Conv1d: Aact = dy, X = x, l_mul = stride,
+ * j_mul = 1, off = -pad, dW is (Cout, Cin, k).  ConvTranspose1d: Aact = x, X = dy, l_mul = 1, j_mul = 1, off = -pad,
+ * dW is (Cin, Cout, k).  The (b, l) reduction is split over `workspace` partials and reduced in a fixed order. */
+typedef struct vqs_wgrad_desc {
+  const float* Aact;
+  const float* X;
+  int M, Cred, ksz;
+  int B, La, Lx;
+  int l_mul, j_mul, off;
+  int x_relu;
+  float* dW;
+  int accumulate;
+} vqs_wgrad_desc;
+
+size_t vqs_wgrad_workspace_bytes(int M, int Cred, int ksz, int B, int La);
+int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t workspace_bytes, vqs_stream_t stream);
+
+/* db[m] (+)= sum_{b, l} g[b, m, l]   (g NCL (B, M, L)). */
+int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int accumulate, vqs_stream_t stream);
+
+/* out[d1][d0][k] = w[d0][d1][k]  (swap the two channel dims of a conv weight). */
+int vqs_permute_weight(const float* w, int d0, int d1, int k, float* out, vqs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* element-wise pieces of the path                                                                  */
+/* ------------------------------------------------------------------------------------------------ */
+/* nn.Upsample(scale_factor=2), nearest: out[b,c,i] = in[b,c,i>>1]; backward: gin[b,c,l] = g[b,c,2l] + g[b,c,2l+1].
+ * `rows` = B*C, L = input length. */
+int vqs_upsample2_fwd(const float* in, long long rows, int L, float* out, vqs_stream_t stream);
+int vqs_upsample2_bwd(const float* g, long long rows, int L, float* gin, vqs_stream_t stream);
+
+/* Jitter (jitter.py:47-70) with a host-drawn plan src[t] (int32, device): out[b,c,t] = in[b,c,src[t]];
+ * backward: gin[b,c,t] = (src[t] == t) ? g[b,c,t] : 0 (replaced columns were overwritten in place from a detached
+ * clone, so they pass no gradient and the source columns receive none). */
+int vqs_jitter_fwd(const float* in, long long rows, int L, const int* src, float* out, vqs_stream_t stream);
+int vqs_jitter_bwd(const float* g, long long rows, int L, const int* src, float* gin, vqs_stream_t stream);
+
+/* nn.MSELoss(recon, target) forward + backward in one pass.  recon is NCL (B, C, L); target element (b,c,l) is
+ * target[b*t_sb + c*t_sc + l*t_sl] (lets the (B, T, F) feature batch be read without a permute copy).
+ * loss[0] = mean((recon - target)^2) ; grad = g_scale * 2 (recon - target) / (B*C*L)  (grad may be NULL). */
+int vqs_mse_fwd_bwd(const float* recon, const float* target, int B, int C, int L, long long t_sb, long long t_sc,
+                    long long t_sl, float g_scale, float* loss, float* grad, void* workspace, size_t workspace_bytes,
+                    vqs_stream_t stream);
+
+/* out = relu(in) ; out = a + b ; gin = (act > 0) ? g : 0  -- used by the module-level (autograd) path only. */
+int vqs_relu_fwd(const float* in, long long n, float* out, vqs_stream_t stream);
+int vqs_relu_bwd(const float* g, const float* act, long long n, float* gin, vqs_stream_t stream);
+int vqs_add(const float* a, const float* b, long long n, float* out, vqs_stream_t stream);
+/* strided (B, L, C) -> NCL (B, C, L) copy: the `.permute(0, 2, 1).contiguous().float()` of convolutional_vq_vae.py:118. */
+int vqs_blc_to_ncl(const float* in, int B, int L, int C, float* out, vqs_stream_t stream);
+
+/* torch.optim.Adam(amsgrad=True, weight_decay=0) over one flat fp32 buffer, one launch:
+ *   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; vmax <- max(vmax, v)
+ *   p <- p - (lr / bc1) * m / (sqrt(vmax) / sqrt(bc2) + eps),  bc1 = 1 - b1^step, bc2 = 1 - b2^step
+ * `step` is read from a device int64 (incremented by the kernel launch BEFORE use when inc_step != 0) so that the call
+ * is CUDA-graph replayable.  g_scale multiplies the gradient first (1/world_size after a sum-allreduce). */
+int vqs_amsgrad_step(float* p, const float* g, float* m, float* v, float* vmax, long long n, long long* step,
+                     int inc_step, float lr, float beta1, float beta2, float eps, float g_scale, vqs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQS_B200_H */

@@ -1,0 +1,263 @@
+"""GPU parity tests of the VQ bottleneck: CUDA path (through the C ABI) vs the CPU oracle and the golden vectors that the
+unmodified reference produced (tests/golden/make_golden.py).  Run with `-m gpu` on a B200."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, rel_err
+from oracle import vq_oracle as vqo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # north_star: losses, quantized outputs and gradients within 1e-5 relative (fp32)
+
+VQ_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, 'vq_*.npz')))
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    return torch.device('cuda:0')
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _make_module(g, dev):
+    from vq_vae_speech_b200.vector_quantizer import VectorQuantizer, VectorQuantizerEMA
+    K, D = int(g['K']), int(g['D'])
+    if bool(g['ema']):
+        vq = VectorQuantizerEMA(K, D, float(g['commitment_cost']), float(g['decay']), dev, float(g['epsilon']))
+    else:
+        vq = VectorQuantizer(K, D, float(g['commitment_cost']), dev)
+    vq = vq.to(dev)
+    with torch.no_grad():
+        vq._embedding.weight.copy_(_t(g['W0'], dev))
+        if bool(g['ema']):
+            vq._ema_w.copy_(_t(g['ema_w0'], dev))
+            vq._ema_cluster_size.copy_(_t(g['cs0'], dev))
+    return vq
+
+
+@pytest.mark.parametrize('case', VQ_CASES)
+def test_vq_module_matches_reference_golden(case):
+    """Same inputs, same initial state -> the drop-in module reproduces what the reference module returned."""
+    dev = _dev()
+    g = load_golden(case)
+    K, D, B, T = int(g['K']), int(g['D']), int(g['B']), int(g['T'])
+    is_ema = bool(g['ema'])
+    beta = float(g['commitment_cost'])
+    vq = _make_module(g, dev).train()
+    vq.record_near_ties = True
+    W = g['W0']
+    n_excluded = 0
+    for s in range(int(g['steps'])):
+        z = _t(g[f'z{s}'], dev).requires_grad_(True)
+        gq = _t(g[f'g{s}'], dev)
+        W_before = vq._embedding.weight.detach().cpu().numpy().copy()
+        outs = vq(z, record_codebook_stats=True)
+        vq_loss, quantized, perplexity, encodings, distances, idx, losses = outs[:7]
+        assert len(outs) == 11 and outs[7] is None and outs[8] is None and outs[9] is None
+        (vq_loss * float(g['g_loss']) + (quantized * gq).sum()).backward()
+        # which rows may legitimately differ: fp64 top-2 gap below 1e-6 relative (reported, not compared)
+        flat = vqo.rows_from_bdt(g[f'z{s}'])
+        _, near, _ = vqo.assign(flat, W_before)
+        ref_idx = g[f'idx{s}'].reshape(-1)
+        got_idx = idx.cpu().numpy().reshape(-1)
+        assert idx.dtype == torch.int64 and tuple(idx.shape) == (B * T, 1)
+        mism = got_idx != ref_idx
+        assert not np.any(mism & ~near), 'index mismatch outside near-tie rows'
+        n_excluded += int(near.sum())
+        if mism.any():      # a near-tie row flipped: every downstream quantity differs legitimately
+            pytest.skip('near-tie rows flipped (%d); reported, not compared' % int(mism.sum()))
+        ste_scale = max(np.abs(g[f'z{s}']).max(), np.abs(g[f'quantized{s}']).max())
+        assert rel_err(quantized.detach().cpu().numpy(), g[f'quantized{s}'], ste_scale) < TOL
+        assert rel_err(vq_loss.item(), g[f'vq_loss{s}']) < TOL
+        assert abs(losses['vq_loss'] - float(g[f'vq_loss{s}'])) <= TOL * abs(float(g[f'vq_loss{s}']))
+        assert rel_err(perplexity.item(), g[f'perplexity{s}']) < TOL
+        assert rel_err(outs[10].cpu().numpy(), g[f'concat{s}']) < TOL
+        assert rel_err(z.grad.cpu().numpy(), g[f'grad_z{s}']) < TOL
+        if s == 0:
+            assert np.array_equal(encodings.cpu().numpy(), g['encodings0'])
+            assert tuple(encodings.shape) == (B, T, K) and tuple(distances.shape) == (B, T, K)
+            d_scale = float(np.max(np.sum(flat.astype(np.float64) ** 2, 1)) + np.max(np.sum(W_before.astype(np.float64) ** 2, 1)))
+            assert rel_err(distances.cpu().numpy(), g['distances0'], d_scale) < TOL   # error scales with |x|^2 + |e|^2
+            # the returned distances are the ones the indices were taken from
+            assert np.array_equal(distances.view(-1, K).argmin(1).cpu().numpy(), got_idx)
+        if is_ema:
+            assert rel_err(vq._ema_cluster_size.cpu().numpy(), g[f'cs{s + 1}']) < TOL
+            assert rel_err(vq._ema_w.detach().cpu().numpy(), g[f'ema_w{s + 1}']) < TOL
+            assert rel_err(vq._embedding.weight.detach().cpu().numpy(), g[f'W{s + 1}']) < TOL
+            assert vq._embedding.weight.grad is None and vq._ema_w.grad is None
+        else:
+            gE = vq._embedding.weight.grad.cpu().numpy()
+            assert rel_err(gE, g[f'grad_E{s}']) < TOL
+            vq._embedding.weight.grad = None
+            with torch.no_grad():   # the golden run moved the codebook with plain SGD between steps
+                vq._embedding.weight -= 0.1 * _t(g[f'grad_E{s}'], dev)
+            assert rel_err(vq._embedding.weight.detach().cpu().numpy(), g[f'W{s + 1}']) < TOL
+    vq.eval()
+    with torch.no_grad():
+        if is_ema:
+            vq._embedding.weight.copy_(_t(g[f'W{int(g["steps"])}'], dev))
+        outs = vq(_t(g['z_eval'], dev), compute_distances_if_possible=False)
+    assert np.array_equal(outs[5].cpu().numpy().reshape(-1), g['eval_idx'].reshape(-1))
+    assert rel_err(outs[0].item(), g['eval_vq_loss']) < TOL
+    assert rel_err(outs[2].item(), g['eval_perplexity']) < TOL
+    assert rel_err(outs[10].cpu().numpy(), g['eval_concat']) < TOL
+    sc = max(np.abs(g['z_eval']).max(), np.abs(g['eval_quantized']).max())
+    assert rel_err(outs[1].cpu().numpy(), g['eval_quantized'], sc) < TOL
+
+
+def test_true_ties_resolve_to_lowest_index():
+    dev = _dev()
+    g = load_golden('vq_ema_k44_d64_b2_t24_dup')
+    from vq_vae_speech_b200 import ops, LAYOUT_BDT_AS_DTB
+    W = _t(g['W0'], dev)
+    z = _t(g['z0'], dev)
+    ws = ops.vq_workspace(44, 64, dev)
+    idx, stats = ops.vq_assign(z, W, LAYOUT_BDT_AS_DTB, ws)
+    idx = idx.cpu().numpy()
+    assert np.array_equal(idx, g['idx0'].reshape(-1))
+    assert not np.any(idx == 22) and not np.any(idx == 43)   # duplicates of code 1 never win
+
+
+SWEEP = [  # (K, D, B, T, layout-name)  sizes the oracle finishes in seconds
+    (44, 64, 2, 24, 'bdt'), (44, 64, 16, 96, 'bdt'), (44, 64, 256, 96, 'bdt'), (29, 64, 7, 33, 'bdt'),
+    (10, 2, 2, 24, 'bdt'), (10, 2, 64, 96, 'bdt'), (100, 64, 5, 24, 'bdt'), (512, 64, 32, 96, 'bdt'),
+    (1000, 64, 8, 24, 'bdt'), (4096, 64, 4, 96, 'bdt'), (44, 64, 1, 1000, 'flat'), (44, 48, 3, 50, 'bdt'),
+    (7, 5, 3, 11, 'bdt'), (1, 64, 2, 24, 'bdt'), (44, 64, 1, 1, 'bdt'), (64, 128, 4, 24, 'bdt'),
+]
+
+
+@pytest.mark.parametrize('K,D,B,T,lay', SWEEP)
+@pytest.mark.parametrize('ema', [True, False])
+def test_vq_ops_match_oracle(K, D, B, T, lay, ema):
+    """C-ABI calls vs the numpy oracle on seeded inputs: indices bit-exact outside near-ties, statistics, EMA state,
+    quantised output, loss, perplexity and gradients within 1e-5."""
+    dev = _dev()
+    from vq_vae_speech_b200 import ops, LAYOUT_BDT_AS_DTB, LAYOUT_FLAT_ND
+    rng = np.random.RandomState(K * 1000 + D * 10 + B)
+    W = rng.randn(K, D).astype(np.float32) if ema else rng.uniform(-1 / K, 1 / K, (K, D)).astype(np.float32)
+    trained = (K * D + B) % 2 == 0
+    if lay == 'flat':
+        N = B * T
+        rows = (W[rng.randint(0, K, N)] + 0.1 * rng.randn(N, D)).astype(np.float32) if trained \
+            else rng.randn(N, D).astype(np.float32)
+        z_dev = _t(rows, dev)
+        layout = LAYOUT_FLAT_ND
+    else:
+        N = B * T
+        if trained:
+            rows = (W[rng.randint(0, K, N)] + 0.1 * rng.randn(N, D)).astype(np.float32)
+            z = vqo.bdt_from_rows(rows, B, D, T)
+        else:
+            z = rng.randn(B, D, T).astype(np.float32)
+        z_dev = _t(z, dev)
+        layout = LAYOUT_BDT_AS_DTB
+        rows = vqo.rows_from_bdt(z)
+    beta, decay, eps = 0.25, 0.99, 1e-5
+    cs0 = rng.rand(K).astype(np.float32) * 3
+    ew0 = rng.randn(K, D).astype(np.float32)
+    # ---- oracle (fp64 truth; index search fp32) ----
+    idx_o, near, _ = vqo.assign(rows, W)
+    counts_o, dw_o = vqo.code_stats(rows.astype(np.float64), idx_o, K)
+    # ---- CUDA ----
+    Wd = _t(W, dev)
+    ws = ops.vq_workspace(K, D, dev)
+    dmin2 = torch.empty(N, 2, device=dev)
+    dist = torch.empty(N, K, device=dev)
+    idx, stats = ops.vq_assign(z_dev, Wd, layout, ws, dmin2=dmin2, distances=dist)
+    got = idx.cpu().numpy()
+    mism = got != idx_o
+    assert not np.any(mism & ~near), '%d index mismatches outside near-ties' % int((mism & ~near).sum())
+    # d = (|x|^2 + |e|^2) - 2 x.e cancels when x is close to a code: its fp32 rounding error scales with the operands
+    # (|x|^2 + |e|^2), not with d itself -- the reference's own fp32 distances carry the same error
+    d_scale = float(np.max(np.sum(rows.astype(np.float64) ** 2, 1)) + np.max(np.sum(W.astype(np.float64) ** 2, 1)))
+    assert rel_err(dist.cpu().numpy(), vqo.distances_fp64(rows, W), d_scale) < TOL
+    d2 = dmin2.cpu().numpy()
+    assert np.all(d2[:, 0] <= d2[:, 1])
+    assert np.allclose(d2[:, 0], dist.min(1).values.cpu().numpy(), rtol=0, atol=0)
+    if mism.any():
+        pytest.skip('near-tie rows flipped (%d of %d); reported, not compared' % (int(mism.sum()), N))
+    st = stats.cpu().numpy()
+    assert np.array_equal(st[:K], counts_o.astype(np.float32))          # cluster counts bit-exact
+    assert rel_err(st[K:].reshape(K, D), dw_o) < TOL
+    Wq = W.astype(np.float64)
+    if ema:
+        csd, ewd = _t(cs0, dev), _t(ew0, dev)
+        ops.vq_ema_update(csd, ewd, Wd, stats, decay, eps)
+        cs_o, ew_o, Wq = vqo.ema_update(cs0, ew0, counts_o, dw_o, decay, eps, np.float64)
+        assert rel_err(csd.cpu().numpy(), cs_o) < TOL
+        assert rel_err(ewd.cpu().numpy(), ew_o) < TOL
+        assert rel_err(Wd.cpu().numpy(), Wq) < TOL
+    q_rows = torch.empty(N, D, device=dev)
+    out, sc = ops.vq_quantize(z_dev, idx, Wd, layout, ws, stats[:K], N, beta, q_rows=q_rows)
+    q_o = Wq[idx_o]
+    diff = q_o - rows
+    e_latent = np.mean(diff * diff)
+    sc = sc.cpu().numpy()
+    assert rel_err(sc[1], e_latent) < TOL
+    assert rel_err(sc[3], beta * e_latent) < TOL and rel_err(sc[4], (1 + beta) * e_latent) < TOL
+    assert rel_err(sc[2], vqo.perplexity(counts_o, N)) < TOL
+    assert rel_err(q_rows.cpu().numpy(), q_o) < TOL
+    ste_o = rows + (q_o - rows)
+    out_rows = out.cpu().numpy() if lay == 'flat' else vqo.rows_from_bdt(out.cpu().numpy())
+    assert rel_err(out_rows, ste_o, max(np.abs(rows).max(), np.abs(q_o).max())) < TOL
+    # ---- backward ----
+    g_np = rng.randn(*z_dev.shape).astype(np.float32)
+    gl = torch.tensor([1.5], device=dev)
+    gz = ops.vq_backward(_t(g_np, dev), gl, 2.0 * beta / (N * D), z_dev, idx, Wd, layout).cpu().numpy()
+    g_rows = g_np if lay == 'flat' else vqo.rows_from_bdt(g_np)
+    gz_rows = gz if lay == 'flat' else vqo.rows_from_bdt(gz)
+    gz_o = g_rows + 1.5 * beta * 2.0 * (rows - q_o) / (N * D)
+    assert rel_err(gz_rows, gz_o) < TOL
+    if not ema:
+        gE = ops.vq_grad_codebook(stats, Wd, gl, 2.0 / (N * D)).cpu().numpy()
+        gE_o = 1.5 * (2.0 / (N * D)) * (counts_o[:, None] * Wq - dw_o)
+        assert rel_err(gE, gE_o) < TOL
+
+
+def test_vq_full_size_properties():
+    """BASELINE sizes (N = 2^20 rows, too big for the oracle): size-independent properties."""
+    dev = _dev()
+    from vq_vae_speech_b200 import ops, LAYOUT_BDT_AS_DTB
+    K, D, B, T = 44, 64, 8192, 128
+    N = B * T
+    gen = torch.Generator(device=dev).manual_seed(1)
+    W = torch.randn(K, D, device=dev, generator=gen)
+    z = torch.randn(B, D, T, device=dev, generator=gen)
+    ws = ops.vq_workspace(K, D, dev)
+    idx, stats = ops.vq_assign(z, W, LAYOUT_BDT_AS_DTB, ws)
+    assert int(idx.min()) >= 0 and int(idx.max()) < K
+    counts = stats[:K]
+    assert float(counts.sum()) == N                                             # every row counted exactly once
+    assert torch.equal(counts, torch.bincount(idx, minlength=K).float())        # counts bit-exact vs the indices
+    rows = z.permute(1, 2, 0).contiguous().view(-1, D)                           # checker only (torch reference layout)
+    # linearity: sum_k dw_k == sum of all rows; a zero-mean sum cancels, so the fp32 error is relative to sum |x|
+    l1 = float(rows.double().abs().sum(0).max())
+    assert rel_err(stats[K:].view(K, D).double().sum(0).cpu().numpy(), rows.double().sum(0).cpu().numpy(), l1) < 1e-6
+    out, sc = ops.vq_quantize(z, idx, W, LAYOUT_BDT_AS_DTB, ws, counts, N, 0.25)
+    q = W[idx]
+    out_rows = out.permute(1, 2, 0).contiguous().view(-1, D)
+    assert float((out_rows - q).abs().max()) < 1e-5 * float(q.abs().max()) * 4
+    # idempotence: quantised rows map to the same codes, with zero loss
+    idx2, _ = ops.vq_assign(q.view(D, T, B).permute(2, 0, 1).contiguous(), W, LAYOUT_BDT_AS_DTB, ws)
+    assert torch.equal(idx2, idx)
+    # distances really are minimal: compare against a blockwise fp64 check on a sample
+    sel = torch.randint(0, N, (4096,), device=dev)
+    d = torch.cdist(rows[sel].double(), W.double()) ** 2
+    best = d.min(1).values
+    chosen = d.gather(1, idx[sel].view(-1, 1)).view(-1)
+    assert float(((chosen - best) / best).max()) < 1e-5
+
+
+def test_cpu_tensor_raises():
+    _dev()
+    from vq_vae_speech_b200.vector_quantizer import VectorQuantizerEMA
+    vq = VectorQuantizerEMA(44, 64, 0.25, 0.99, 'cpu')
+    with pytest.raises(RuntimeError):
+        vq(torch.randn(2, 64, 24))

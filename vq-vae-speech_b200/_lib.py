@@ -1,0 +1,106 @@
+"""ctypes binding of libvqs_b200.so (the C ABI declared in include/vqs_b200.h).
+
+The product path has NO fallback: if the shared library is missing and cannot be built, importing an op raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'csrc', 'libvqs_b200.so')
+
+LAYOUT_FLAT_ND = 0
+LAYOUT_BDT_AS_DTB = 1
+
+
+class ConvGemmDesc(Structure):
+    """struct vqs_conv_gemm_desc (include/vqs_b200.h)."""
+    _fields_ = [
+        ('A', c_void_p), ('X', c_void_p),
+        ('M', c_int), ('Cred', c_int), ('ksz', c_int),
+        ('B', c_int), ('Lin', c_int), ('Lout', c_int),
+        ('x_sb', c_longlong), ('x_sc', c_longlong), ('x_sl', c_longlong),
+        ('l_mul', c_int), ('j_mul', c_int), ('off', c_int), ('l_div', c_int),
+        ('x_relu', c_int),
+        ('bias', c_void_p), ('add_pre', c_void_p), ('add_pre_relu', c_int), ('relu', c_int),
+        ('mask_out', c_void_p), ('mask', c_void_p), ('mask_kind', c_int),
+        ('add_post', c_void_p), ('out', c_void_p), ('out2', c_void_p), ('mask2', c_void_p), ('mask2_kind', c_int),
+    ]
+
+
+class WgradDesc(Structure):
+    """struct vqs_wgrad_desc (include/vqs_b200.h)."""
+    _fields_ = [
+        ('Aact', c_void_p), ('X', c_void_p),
+        ('M', c_int), ('Cred', c_int), ('ksz', c_int),
+        ('B', c_int), ('La', c_int), ('Lx', c_int),
+        ('l_mul', c_int), ('j_mul', c_int), ('off', c_int),
+        ('x_relu', c_int),
+        ('dW', c_void_p), ('accumulate', c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/vqs_b200.h declares
+PROTOTYPES = {
+    'vqs_version': (c_int, []),
+    'vqs_last_error': (c_char_p, []),
+    'vqs_launch_count': (c_longlong, []),
+    'vqs_vq_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'vqs_vq_assign': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_size_t, c_void_p]),
+    'vqs_vq_one_hot': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    'vqs_vq_ema_update': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int,
+                                  c_int, c_void_p]),
+    'vqs_vq_quantize': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                c_void_p, c_double, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'vqs_vq_backward': (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                c_int, c_void_p, c_void_p]),
+    'vqs_vq_grad_codebook': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'vqs_conv_gemm': (c_int, [POINTER(ConvGemmDesc), c_void_p]),
+    'vqs_wgrad_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    'vqs_wgrad_gemm': (c_int, [POINTER(WgradDesc), c_void_p, c_size_t, c_void_p]),
+    'vqs_bias_grad': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'vqs_permute_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'vqs_upsample2_fwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    'vqs_upsample2_bwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    'vqs_jitter_fwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
+    'vqs_jitter_bwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
+    'vqs_mse_fwd_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_longlong, c_longlong, c_float,
+                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'vqs_relu_fwd': (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
+    'vqs_relu_bwd': (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
+    'vqs_add': (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
+    'vqs_blc_to_ncl': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'vqs_amsgrad_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int,
+                                 c_float, c_float, c_float, c_float, c_float, c_void_p]),
+}
+
+_LIB = None
+
+
+def load():
+    """Loads (building first if the sources changed and nvcc is present) libvqs_b200.so.  Raises when unavailable."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    from . import build as _build
+    path = _build.build()
+    if not os.path.exists(path):
+        raise RuntimeError('libvqs_b200.so is missing (%s); run `python vq-vae-speech_b200/build.py`' % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        msg = load().vqs_last_error()
+        raise RuntimeError('libvqs_b200 error %d: %s' % (code, msg.decode() if msg else '?'))
+
+
+def launch_count():
+    return int(load().vqs_launch_count())

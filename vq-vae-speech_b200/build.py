@@ -1,0 +1,69 @@
+"""Builds libvqs_b200.so (sm_100a only) in-tree with nvcc.  No torch involved: the library is a plain C-ABI shared object.
+
+    python vq-vae-speech_b200/build.py [--force] [--verbose]
+"""
+import glob
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(CSRC, 'libvqs_b200.so')
+STAMP = os.path.join(CSRC, '.libvqs_b200.stamp')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+FLAGS = ['-O3', '-std=c++17', '-lineinfo', '--use_fast_math=false'] if False else ['-O3', '-std=c++17', '-lineinfo']
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
+
+
+def _digest():
+    h = hashlib.sha256()
+    for p in sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + sorted(glob.glob(os.path.join(ROOT, 'include', '*.h'))):
+        h.update(p.encode())
+        with open(p, 'rb') as f:
+            h.update(f.read())
+    h.update(' '.join(ARCH + FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ for sm_100a and link libvqs_b200.so.  Returns the library path."""
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    if not os.path.exists(NVCC):
+        if os.path.exists(LIB):      # GPU box without a toolkit: use the prebuilt library that travelled with the snapshot
+            return LIB
+        raise RuntimeError('nvcc not found at %s and no prebuilt %s' % (NVCC, LIB))
+    objs = []
+    procs = []
+    for src in sources():
+        obj = src[:-3] + '.o'
+        cmd = [NVCC] + ARCH + FLAGS + ['-Xcompiler', '-fPIC', '-c', src, '-o', obj]
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError('nvcc failed on %s:\n%s' % (src, out))
+        if verbose or out.strip():
+            sys.stderr.write(out)
+    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs + ['-lcuda']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n' + r.stdout)
+    with open(STAMP, 'w') as f:
+        f.write(dig)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

@@ -1,0 +1,477 @@
+// Conv1d / ConvTranspose1d forward, dgrad and wgrad as implicit GEMMs with fused epilogues -- exact-fp32 CUDA-core path.
+// Replaces the ATen/cuDNN calls behind nn.Conv1d / nn.ConvTranspose1d / F.relu / residual adds of
+//   /root/reference/src/models/convolutional_encoder.py:118-146, deconvolutional_decoder.py:100-137,
+//   /root/reference/src/modules/residual.py:69-70, residual_stack.py:43-46  and their autograd backward.
+//
+// GEMM view (see include/vqs_b200.h): rows m = output channels, columns n = (batch, position), reduction over
+// kk = (input channel, tap).  Operand A is a dense row-major weight matrix; operand B is gathered on the fly from the NCL
+// activation tensor (padding, stride, transposed-conv tap flip, nearest-neighbour index and input ReLU are all index
+// arithmetic in the loader), so no im2col buffer ever exists in HBM.
+#include "vqs_common.cuh"
+
+namespace vqs {
+namespace {
+
+constexpr int BK = 16;
+constexpr int NTHREADS = 256;
+
+template <int BM, int BN>
+struct TileCfg {
+  static constexpr int GM = BM / 64, GN = BN / 64;  // groups of 4 rows / 4 columns per thread
+  static constexpr int TM = 4 * GM, TN = 4 * GN;
+  static constexpr int LDA = BM + 4, LDB = BN + 4;
+  static_assert(BM % 64 == 0 && BN % 64 == 0, "tile must be a multiple of 64");
+};
+
+template <int BM, int BN>
+__device__ __forceinline__ void compute_tile(const float* __restrict__ As, const float* __restrict__ Bs,
+                                             float (&acc)[TileCfg<BM, BN>::TM][TileCfg<BM, BN>::TN], int ty, int tx) {
+  using C = TileCfg<BM, BN>;
+#pragma unroll
+  for (int k = 0; k < BK; ++k) {
+    float a[C::TM], b[C::TN];
+#pragma unroll
+    for (int g = 0; g < C::GM; ++g) {
+      float4 v = *reinterpret_cast<const float4*>(&As[k * C::LDA + g * 64 + ty * 4]);
+      a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+    }
+#pragma unroll
+    for (int g = 0; g < C::GN; ++g) {
+      float4 v = *reinterpret_cast<const float4*>(&Bs[k * C::LDB + g * 64 + tx * 4]);
+      b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < C::TM; ++i)
+#pragma unroll
+      for (int j = 0; j < C::TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv-like GEMM (forward conv, dgrad, transposed conv forward, transposed conv dgrad)
+// ------------------------------------------------------------------------------------------------
+struct ConvParams {
+  vqs_conv_gemm_desc d;
+  int Ktot, Ntot;
+  int a_vec;  // A rows are 16-byte aligned and Ktot % 4 == 0
+  FastDiv divL;
+};
+
+__device__ __forceinline__ bool mask_on(const void* m, int kind, size_t i) {
+  if (kind == 1) return reinterpret_cast<const float*>(m)[i] > 0.f;
+  return reinterpret_cast<const unsigned char*>(m)[i] != 0;
+}
+
+template <int BM, int BN, int KSZ>
+__global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const ConvParams p) {
+  using C = TileCfg<BM, BN>;
+  __shared__ __align__(16) float As[2][BK * C::LDA];
+  __shared__ __align__(16) float Bs[2][BK * C::LDB];
+  const vqs_conv_gemm_desc& d = p.d;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int Ktot = p.Ktot;
+  const int ktiles = (Ktot + BK - 1) / BK;
+
+  // ---- A loader: float4 f = tid + 256*i -> row f/4, k (f%4)*4 ----
+  constexpr int A_LD = BM / 64;
+  // ---- B loader: one column per thread, B_LD k-rows spaced B_STEP apart ----
+  constexpr int B_LD = BN / 16;
+  constexpr int B_STEP = NTHREADS / BN;
+  const int bcol = tid % BN;
+  const int brow0 = tid / BN;
+  const int n_ld = n0 + bcol;
+  const bool n_ok = n_ld < p.Ntot;
+  uint32_t bb = 0, ll = 0;
+  if (n_ok) p.divL.divmod((uint32_t)n_ld, bb, ll);
+  const float* xb = d.X + (long long)bb * d.x_sb;
+  const int lbase = (int)ll * d.l_mul + d.off;
+
+  float4 areg[A_LD];
+  float breg[B_LD];
+
+  auto load_global = [&](int kt) {
+    const int k0 = kt * BK;
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int f = tid + NTHREADS * i;
+      int row = f >> 2, kq = (f & 3) << 2;
+      int m = m0 + row, k = k0 + kq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < d.M) {
+        const float* src = d.A + (size_t)m * Ktot + k;
+        if (p.a_vec) {
+          if (k < Ktot) v = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          if (k + 0 < Ktot) v.x = __ldg(src + 0);
+          if (k + 1 < Ktot) v.y = __ldg(src + 1);
+          if (k + 2 < Ktot) v.z = __ldg(src + 2);
+          if (k + 3 < Ktot) v.w = __ldg(src + 3);
+        }
+      }
+      areg[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      int kk = k0 + brow0 + B_STEP * i;
+      int c = kk / KSZ, j = kk - c * KSZ;
+      int pn = lbase + j * d.j_mul;
+      bool ok = n_ok && kk < Ktot && pn >= 0;
+      if (d.l_div == 2) {
+        ok = ok && ((pn & 1) == 0);
+        pn >>= 1;
+      }
+      ok = ok && pn < d.Lin;
+      float v = 0.f;
+      if (ok) {
+        v = __ldg(xb + (long long)c * d.x_sc + (long long)pn * d.x_sl);
+        if (d.x_relu) v = fmaxf(v, 0.f);
+      }
+      breg[i] = v;
+    }
+  };
+  auto store_smem = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int f = tid + NTHREADS * i;
+      int row = f >> 2, kq = (f & 3) << 2;
+      float* a = &As[buf][kq * C::LDA + row];
+      a[0 * C::LDA] = areg[i].x;
+      a[1 * C::LDA] = areg[i].y;
+      a[2 * C::LDA] = areg[i].z;
+      a[3 * C::LDA] = areg[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) Bs[buf][(brow0 + B_STEP * i) * C::LDB + bcol] = breg[i];
+  };
+
+  float acc[C::TM][C::TN];
+#pragma unroll
+  for (int i = 0; i < C::TM; ++i)
+#pragma unroll
+    for (int j = 0; j < C::TN; ++j) acc[i][j] = 0.f;
+
+  load_global(0);
+  store_smem(0);
+  __syncthreads();
+  for (int kt = 0; kt < ktiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < ktiles) load_global(kt + 1);
+    compute_tile<BM, BN>(As[buf], Bs[buf], acc, ty, tx);
+    if (kt + 1 < ktiles) store_smem(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+#pragma unroll
+  for (int gj = 0; gj < C::GN; ++gj) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int n = n0 + gj * 64 + tx * 4 + jj;
+      if (n >= p.Ntot) continue;
+      uint32_t b, l;
+      p.divL.divmod((uint32_t)n, b, l);
+      const size_t col_off = (size_t)b * d.M * d.Lout + l;
+#pragma unroll
+      for (int gi = 0; gi < C::GM; ++gi) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int m = m0 + gi * 64 + ty * 4 + ii;
+          if (m >= d.M) continue;
+          const size_t o = col_off + (size_t)m * d.Lout;
+          float v = acc[gi * 4 + ii][gj * 4 + jj];
+          if (d.bias) v += __ldg(d.bias + m);
+          if (d.add_pre) {
+            float r = d.add_pre[o];
+            v += d.add_pre_relu ? fmaxf(r, 0.f) : r;
+          }
+          if (d.relu) v = fmaxf(v, 0.f);
+          if (d.mask_out) d.mask_out[o] = v > 0.f ? 1 : 0;
+          if (d.mask_kind && !mask_on(d.mask, d.mask_kind, o)) v = 0.f;
+          if (d.add_post) v += d.add_post[o];
+          d.out[o] = v;
+          if (d.out2) d.out2[o] = (d.mask2_kind == 0 || mask_on(d.mask2, d.mask2_kind, o)) ? v : 0.f;
+        }
+      }
+    }
+  }
+}
+
+template <int BM, int BN>
+int launch_conv(const ConvParams& p, cudaStream_t st) {
+  dim3 grid((p.Ntot + BN - 1) / BN, (p.d.M + BM - 1) / BM, 1);
+  switch (p.d.ksz) {
+    case 1: conv_gemm_kernel<BM, BN, 1><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 2: conv_gemm_kernel<BM, BN, 2><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 3: conv_gemm_kernel<BM, BN, 3><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 4: conv_gemm_kernel<BM, BN, 4><<<grid, NTHREADS, 0, st>>>(p); break;
+    default: set_error("vqs_conv_gemm: kernel size %d not supported (1..4)", p.d.ksz); return VQS_ERR_ARG;
+  }
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad GEMM: dW[m, (c, j)] = sum_{(b, l)} Aact[b, m, l] * X'[b, c, l*l_mul + j*j_mul + off]
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  vqs_wgrad_desc d;
+  int Nw, Kred, splits, kt_per_split;
+  float* partial;  // [splits][M*Nw] or NULL (direct)
+  FastDiv divLa;
+};
+
+template <int BM, int BN, int KSZ>
+__global__ void __launch_bounds__(NTHREADS) wgrad_gemm_kernel(const WgradParams p) {
+  using C = TileCfg<BM, BN>;
+  __shared__ __align__(16) float As[2][BK * C::LDA];
+  __shared__ __align__(16) float Bs[2][BK * C::LDB];
+  const vqs_wgrad_desc& d = p.d;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int ktiles = (p.Kred + BK - 1) / BK;
+  const int kt_begin = blockIdx.z * p.kt_per_split;
+  int kt_end = kt_begin + p.kt_per_split;
+  if (kt_end > ktiles) kt_end = ktiles;
+
+  constexpr int A_LD = BM / 16, B_LD = BN / 16;
+  const int kl = tid & 15, r = tid >> 4;
+  int boff[B_LD], bjo[B_LD];
+#pragma unroll
+  for (int i = 0; i < B_LD; ++i) {
+    int n = n0 + r + 16 * i;
+    int c = n / KSZ, j = n - c * KSZ;
+    bjo[i] = (n < p.Nw) ? j * d.j_mul + d.off : (-(1 << 29));  // forces pn < 0 -> zero
+    boff[i] = c * d.Lx;
+  }
+  float areg[A_LD], breg[B_LD];
+
+  auto load_global = [&](int kt) {
+    const int kk = kt * BK + kl;
+    const bool k_ok = kk < p.Kred;
+    uint32_t b = 0, l = 0;
+    if (k_ok) p.divLa.divmod((uint32_t)kk, b, l);
+    const float* ab = d.Aact + ((size_t)b * d.M) * d.La + l;
+    const float* xb = d.X + ((size_t)b * d.Cred) * d.Lx;
+    const int lp = (int)l * d.l_mul;
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int m = m0 + r + 16 * i;
+      areg[i] = (k_ok && m < d.M) ? __ldg(ab + (size_t)m * d.La) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      int pn = lp + bjo[i];
+      float v = 0.f;
+      if (k_ok && pn >= 0 && pn < d.Lx) {
+        v = __ldg(xb + boff[i] + pn);
+        if (d.x_relu) v = fmaxf(v, 0.f);
+      }
+      breg[i] = v;
+    }
+  };
+  auto store_smem = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) As[buf][kl * C::LDA + r + 16 * i] = areg[i];
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) Bs[buf][kl * C::LDB + r + 16 * i] = breg[i];
+  };
+
+  float acc[C::TM][C::TN];
+#pragma unroll
+  for (int i = 0; i < C::TM; ++i)
+#pragma unroll
+    for (int j = 0; j < C::TN; ++j) acc[i][j] = 0.f;
+
+  if (kt_begin < kt_end) {
+    load_global(kt_begin);
+    store_smem(0);
+    __syncthreads();
+    for (int kt = kt_begin; kt < kt_end; ++kt) {
+      const int buf = (kt - kt_begin) & 1;
+      if (kt + 1 < kt_end) load_global(kt + 1);
+      compute_tile<BM, BN>(As[buf], Bs[buf], acc, ty, tx);
+      if (kt + 1 < kt_end) store_smem(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  float* out = p.partial ? p.partial + (size_t)blockIdx.z * d.M * p.Nw : d.dW;
+  const bool accum = (p.partial == nullptr) && d.accumulate;
+#pragma unroll
+  for (int gi = 0; gi < C::GM; ++gi)
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int m = m0 + gi * 64 + ty * 4 + ii;
+      if (m >= d.M) continue;
+#pragma unroll
+      for (int gj = 0; gj < C::GN; ++gj)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int n = n0 + gj * 64 + tx * 4 + jj;
+          if (n >= p.Nw) continue;
+          const size_t o = (size_t)m * p.Nw + n;
+          float v = acc[gi * 4 + ii][gj * 4 + jj];
+          out[o] = accum ? out[o] + v : v;
+        }
+    }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, long long n, float* __restrict__ out,
+                                     int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a = accumulate ? out[i] : 0.f;
+    for (int s = 0; s < S; ++s) a += partial[(size_t)s * n + i];
+    out[i] = a;
+  }
+}
+
+template <int BM, int BN>
+int launch_wgrad(const WgradParams& p, cudaStream_t st) {
+  dim3 grid((p.Nw + BN - 1) / BN, (p.d.M + BM - 1) / BM, p.splits);
+  switch (p.d.ksz) {
+    case 1: wgrad_gemm_kernel<BM, BN, 1><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 2: wgrad_gemm_kernel<BM, BN, 2><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 3: wgrad_gemm_kernel<BM, BN, 3><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 4: wgrad_gemm_kernel<BM, BN, 4><<<grid, NTHREADS, 0, st>>>(p); break;
+    default: set_error("vqs_wgrad_gemm: kernel size %d not supported (1..4)", p.d.ksz); return VQS_ERR_ARG;
+  }
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+struct WgradPlan {
+  int bm, bn, splits, kt_per_split;
+};
+WgradPlan plan_wgrad(int M, int Nw, int Kred) {
+  WgradPlan pl;
+  pl.bm = (M > 64) ? 128 : 64;
+  pl.bn = (Nw > 64) ? 128 : 64;
+  long long tiles = (long long)((M + pl.bm - 1) / pl.bm) * ((Nw + pl.bn - 1) / pl.bn);
+  int ktiles = (Kred + BK - 1) / BK;
+  long long want = (2ll * num_sms() + tiles - 1) / tiles;
+  int max_s = ktiles / 4 > 0 ? ktiles / 4 : 1;
+  int s = (int)(want < 1 ? 1 : want);
+  if (s > max_s) s = max_s;
+  if (s > 64) s = 64;
+  pl.kt_per_split = (ktiles + s - 1) / s;
+  pl.splits = (ktiles + pl.kt_per_split - 1) / pl.kt_per_split;
+  return pl;
+}
+
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ g, int B, int M, int L,
+                                                        float* __restrict__ db, int accumulate) {
+  // one block per channel m; fixed-order tree reduction -> deterministic
+  __shared__ float red[256];
+  const int m = blockIdx.x;
+  float s = 0.f;
+  const int per = B * L;
+  for (int i = threadIdx.x; i < per; i += 256) {
+    int b = i / L, l = i - b * L;
+    s += g[((size_t)b * M + m) * L + l];
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) db[m] = accumulate ? db[m] + red[0] : red[0];
+}
+
+__global__ void permute_weight_kernel(const float* __restrict__ w, int d0, int d1, int k, float* __restrict__ out) {
+  const long long n = (long long)d0 * d1 * k;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes out[b][a][j]
+    int j = (int)(i % k);
+    long long t = i / k;
+    int a = (int)(t % d0);
+    int b = (int)(t / d0);
+    out[i] = w[((size_t)a * d1 + b) * k + j];
+  }
+}
+
+}  // namespace
+}  // namespace vqs
+
+using namespace vqs;
+
+extern "C" int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream) {
+  VQS_CHECK_ARG(d != nullptr, "vqs_conv_gemm: NULL descriptor");
+  VQS_CHECK_ARG(d->A && d->X && d->out, "vqs_conv_gemm: NULL tensor");
+  VQS_CHECK_ARG(d->M > 0 && d->Cred > 0 && d->B > 0 && d->Lin > 0 && d->Lout > 0, "vqs_conv_gemm: bad shape");
+  VQS_CHECK_ARG(d->l_div == 1 || d->l_div == 2, "vqs_conv_gemm: l_div must be 1 or 2");
+  VQS_CHECK_ARG((long long)d->B * d->Lout < (1ll << 31) && (long long)d->B * d->M * d->Lout < (1ll << 40),
+                "vqs_conv_gemm: problem too large");
+  VQS_CHECK_ARG(!(d->mask_kind && !d->mask) && !(d->mask2_kind && !d->mask2), "vqs_conv_gemm: mask kind without mask");
+  ConvParams p;
+  p.d = *d;
+  p.Ktot = d->Cred * d->ksz;
+  p.Ntot = d->B * d->Lout;
+  p.a_vec = (p.Ktot % 4 == 0) && ((reinterpret_cast<uintptr_t>(d->A) & 15) == 0);
+  p.divL = FastDiv((uint32_t)d->Lout);
+  cudaStream_t st = (cudaStream_t)stream;
+  // tile choice: big tiles once they fill the machine, small tiles otherwise
+  long long big = (long long)((d->M + 127) / 128) * ((p.Ntot + 127) / 128);
+  if (d->M > 64 && p.Ntot > 64 && big >= num_sms()) return launch_conv<128, 128>(p, st);
+  if (d->M > 64 && p.Ntot > 64 && big * 2 >= num_sms()) return launch_conv<128, 64>(p, st);
+  return launch_conv<64, 64>(p, st);
+}
+
+extern "C" size_t vqs_wgrad_workspace_bytes(int M, int Cred, int ksz, int B, int La) {
+  if (M <= 0 || Cred <= 0 || ksz <= 0 || B <= 0 || La <= 0) return 0;
+  WgradPlan pl = plan_wgrad(M, Cred * ksz, B * La);
+  return pl.splits > 1 ? (size_t)pl.splits * M * Cred * ksz * sizeof(float) : 0;
+}
+
+extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t workspace_bytes, vqs_stream_t stream) {
+  VQS_CHECK_ARG(d != nullptr, "vqs_wgrad_gemm: NULL descriptor");
+  VQS_CHECK_ARG(d->Aact && d->X && d->dW, "vqs_wgrad_gemm: NULL tensor");
+  VQS_CHECK_ARG(d->M > 0 && d->Cred > 0 && d->B > 0 && d->La > 0 && d->Lx > 0, "vqs_wgrad_gemm: bad shape");
+  VQS_CHECK_ARG((long long)d->B * d->La < (1ll << 31), "vqs_wgrad_gemm: problem too large");
+  WgradParams p;
+  p.d = *d;
+  p.Nw = d->Cred * d->ksz;
+  p.Kred = d->B * d->La;
+  WgradPlan pl = plan_wgrad(d->M, p.Nw, p.Kred);
+  p.splits = pl.splits;
+  p.kt_per_split = pl.kt_per_split;
+  p.divLa = FastDiv((uint32_t)d->La);
+  size_t need = pl.splits > 1 ? (size_t)pl.splits * d->M * p.Nw * sizeof(float) : 0;
+  if (need > workspace_bytes || (need && !workspace)) {
+    set_error("vqs_wgrad_gemm: workspace %zu < %zu", workspace_bytes, need);
+    return VQS_ERR_WORKSPACE;
+  }
+  p.partial = pl.splits > 1 ? (float*)workspace : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  int e;
+  if (pl.bm == 128 && pl.bn == 128) e = launch_wgrad<128, 128>(p, st);
+  else if (pl.bm == 128) e = launch_wgrad<128, 64>(p, st);
+  else if (pl.bn == 128) e = launch_wgrad<64, 128>(p, st);
+  else e = launch_wgrad<64, 64>(p, st);
+  if (e) return e;
+  if (pl.splits > 1) {
+    long long n = (long long)d->M * p.Nw;
+    long long blocks = (n + 255) / 256;
+    splitk_reduce_kernel<<<(int)(blocks < 8 * num_sms() ? blocks : 8 * num_sms()), 256, 0, st>>>(
+        p.partial, pl.splits, n, d->dW, d->accumulate);
+    VQS_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int accumulate, vqs_stream_t stream) {
+  VQS_CHECK_ARG(g && db && B > 0 && M > 0 && L > 0, "vqs_bias_grad: bad arguments");
+  bias_grad_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(g, B, M, L, db, accumulate);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vqs_permute_weight(const float* w, int d0, int d1, int k, float* out, vqs_stream_t stream) {
+  VQS_CHECK_ARG(w && out && d0 > 0 && d1 > 0 && k > 0, "vqs_permute_weight: bad arguments");
+  long long n = (long long)d0 * d1 * k;
+  long long blocks = (n + 255) / 256;
+  permute_weight_kernel<<<(int)(blocks < 8 * num_sms() ? blocks : 8 * num_sms()), 256, 0, (cudaStream_t)stream>>>(
+      w, d0, d1, k, out);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}

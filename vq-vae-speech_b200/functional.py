@@ -1,0 +1,293 @@
+"""Conv / VQ building blocks on top of ops.py: the six conv-like GEMM mappings and the torch.autograd.Functions that give
+the drop-in nn.Modules (modules.py, vector_quantizer.py, convolutional_vq_vae.py) a backward.  Forward and backward both
+run hand-written kernels only."""
+import torch
+from torch.autograd import Function
+
+from . import ops
+from ._lib import LAYOUT_BDT_AS_DTB, LAYOUT_FLAT_ND
+from .ops import MASK_FLOAT, MASK_NONE, MASK_U8
+
+
+# ------------------------------------------------------------------------------------------------
+# conv-like GEMM mappings (see include/vqs_b200.h for the index convention)
+# ------------------------------------------------------------------------------------------------
+def conv_out_len(Lin, k, stride, pad):
+    return (Lin + 2 * pad - k) // stride + 1
+
+
+def convT_out_len(Lin, k, pad):
+    return Lin - 1 + k - 2 * pad
+
+
+def conv1d_forward(x, w, b, stride, pad, out=None, x_strides=None, x_shape=None, **epi):
+    """nn.Conv1d forward: y[b,o,l] = bias[o] + sum_{c,j} w[o,c,j] x[b,c,l*stride + j - pad]."""
+    Cout, Cin, k = w.shape
+    B, _, Lin = x_shape if x_shape is not None else x.shape
+    Lout = conv_out_len(Lin, k, stride, pad)
+    if out is None:
+        out = torch.empty(B, Cout, Lout, dtype=torch.float32, device=w.device)
+    return ops.conv_gemm(w, x, out, Cout, Cin, k, B, Lin, Lout, stride, 1, -pad, 1, x_strides=x_strides, bias=b, **epi)
+
+
+def conv1d_dgrad(gy, w_perm, Lx, stride, pad, out=None, **epi):
+    """dx[b,c,i] = sum_{o,j} w[o,c,j] gy[b,o,(i + pad - j)/stride];  w_perm = permute_weight(w) = (Cin, Cout, k)."""
+    Cin, Cout, k = w_perm.shape
+    B, _, Ly = gy.shape
+    if out is None:
+        out = torch.empty(B, Cin, Lx, dtype=torch.float32, device=gy.device)
+    return ops.conv_gemm(w_perm, gy, out, Cin, Cout, k, B, Ly, Lx, 1, -1, pad, stride, **epi)
+
+
+def conv1d_wgrad(gy, x, dW, stride, pad, ws, x_relu=False, accumulate=False):
+    """dW[o,c,j] (+)= sum_{b,l} gy[b,o,l] x[b,c,l*stride + j - pad]."""
+    Cout, Cin, k = dW.shape
+    B, _, Ly = gy.shape
+    return ops.wgrad_gemm(gy, x, dW, Cout, Cin, k, B, Ly, x.shape[2], stride, 1, -pad, ws, x_relu=x_relu,
+                          accumulate=accumulate)
+
+
+def convT1d_forward(x, w_perm, b, pad, out_len=None, out=None, **epi):
+    """nn.ConvTranspose1d (stride 1) forward: y[b,o,i] = bias[o] + sum_{c,j} x[b,c,i - j + pad] w[c,o,j];
+    w_perm = permute_weight(w) = (Cout, Cin, k).  out_len < full length computes only the first out_len positions."""
+    Cout, Cin, k = w_perm.shape
+    B, _, Lin = x.shape
+    Lout = convT_out_len(Lin, k, pad) if out_len is None else out_len
+    if out is None:
+        out = torch.empty(B, Cout, Lout, dtype=torch.float32, device=x.device)
+    return ops.conv_gemm(w_perm, x, out, Cout, Cin, k, B, Lin, Lout, 1, -1, pad, 1, bias=b, **epi)
+
+
+def convT1d_dgrad(gy, w, Lx, pad, out=None, **epi):
+    """dx[b,c,l] = sum_{o,j} gy[b,o,l + j - pad] w[c,o,j]  (gy may be the trimmed tensor: positions beyond it are 0)."""
+    Cin, Cout, k = w.shape
+    B, _, Ly = gy.shape
+    if out is None:
+        out = torch.empty(B, Cin, Lx, dtype=torch.float32, device=gy.device)
+    return ops.conv_gemm(w, gy, out, Cin, Cout, k, B, Ly, Lx, 1, 1, -pad, 1, **epi)
+
+
+def convT1d_wgrad(gy, x, dW, pad, ws, accumulate=False):
+    """dW[c,o,j] (+)= sum_{b,l} x[b,c,l] gy[b,o,l + j - pad]."""
+    Cin, Cout, k = dW.shape
+    B, _, Lx = x.shape
+    return ops.wgrad_gemm(x, gy, dW, Cin, Cout, k, B, Lx, gy.shape[2], 1, 1, -pad, ws, accumulate=accumulate)
+
+
+def _wgrad_ws(M, Cred, k, B, La, device):
+    n = ops.wgrad_workspace_bytes(M, Cred, k, B, La)
+    return torch.empty(max(n, 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions (module-level path)
+# ------------------------------------------------------------------------------------------------
+class Conv1dFn(Function):
+    """y = [relu](conv1d(x, w) + b) with hand-written forward / dgrad / wgrad kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, relu):
+        x = x.contiguous()
+        out = conv1d_forward(x, w.contiguous(), None if b is None else b.contiguous(), stride, pad, relu=relu)
+        ctx.save_for_backward(x, w, out if relu else None)
+        ctx.cfg = (stride, pad, relu, b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, out = ctx.saved_tensors
+        stride, pad, relu, has_b = ctx.cfg
+        g = g.contiguous()
+        if relu:
+            g = ops.relu_bwd(g, out)
+        Cout, Cin, k = w.shape
+        B = x.shape[0]
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = conv1d_dgrad(g, ops.permute_weight(w.contiguous()), x.shape[2], stride, pad)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(w)
+            conv1d_wgrad(g, x, dW, stride, pad, _wgrad_ws(Cout, Cin, k, B, g.shape[2], g.device))
+        if has_b and ctx.needs_input_grad[2]:
+            db = ops.bias_grad(g, torch.empty(Cout, dtype=torch.float32, device=g.device))
+        return dx, dW, db, None, None, None
+
+
+class ConvTranspose1dFn(Function):
+    """y = [relu](conv_transpose1d(x, w, stride=1) + b); out_len trims the output to its first out_len positions."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, pad, relu, out_len):
+        x = x.contiguous()
+        out = convT1d_forward(x, ops.permute_weight(w.contiguous()), None if b is None else b.contiguous(), pad,
+                              out_len=out_len, relu=relu)
+        ctx.save_for_backward(x, w, out if relu else None)
+        ctx.cfg = (pad, relu, b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, out = ctx.saved_tensors
+        pad, relu, has_b = ctx.cfg
+        g = g.contiguous()
+        if relu:
+            g = ops.relu_bwd(g, out)
+        Cin, Cout, k = w.shape
+        B = x.shape[0]
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = convT1d_dgrad(g, w.contiguous(), x.shape[2], pad)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(w)
+            convT1d_wgrad(g, x, dW, pad, _wgrad_ws(Cin, Cout, k, B, x.shape[2], g.device))
+        if has_b and ctx.needs_input_grad[2]:
+            db = ops.bias_grad(g, torch.empty(Cout, dtype=torch.float32, device=g.device))
+        return dx, dW, db, None, None, None
+
+
+class ReluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        out = ops.relu_fwd(x.contiguous())
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        return ops.relu_bwd(g.contiguous(), out)
+
+
+class AddFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.add(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+class Upsample2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample2_fwd(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.upsample2_bwd(g.contiguous())
+
+
+class JitterFn(Function):
+    @staticmethod
+    def forward(ctx, x, src):
+        ctx.save_for_backward(src)
+        return ops.jitter_fwd(x.contiguous(), src)
+
+    @staticmethod
+    def backward(ctx, g):
+        (src,) = ctx.saved_tensors
+        return ops.jitter_bwd(g.contiguous(), src), None
+
+
+class MseLossFn(Function):
+    """nn.MSELoss()(recon, target) with target given as a strided (b, c, l) view; one pass computes loss and gradient."""
+
+    @staticmethod
+    def forward(ctx, recon, target):
+        recon = recon.contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=recon.device)
+        grad = torch.empty_like(recon)
+        ops.mse_fwd_bwd(recon, target, target.stride(), 1.0, loss, grad, ops.mse_workspace(recon.device))
+        ctx.save_for_backward(grad)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None      # g is the scalar upstream gradient (1.0 in the trainer)
+
+
+def conv1d(x, w, b, stride=1, pad=0, relu=False):
+    return Conv1dFn.apply(x, w, b, stride, pad, relu)
+
+
+def conv_transpose1d(x, w, b, pad=0, relu=False, out_len=None):
+    return ConvTranspose1dFn.apply(x, w, b, pad, relu, out_len)
+
+
+def relu(x):
+    return ReluFn.apply(x)
+
+
+def add(a, b):
+    return AddFn.apply(a, b)
+
+
+def upsample2(x):
+    return Upsample2Fn.apply(x)
+
+
+def jitter(x, src):
+    return JitterFn.apply(x, src)
+
+
+def mse_loss(recon, target):
+    return MseLossFn.apply(recon, target)
+
+
+# ------------------------------------------------------------------------------------------------
+# VQ bottleneck Function
+# ------------------------------------------------------------------------------------------------
+class VQFn(Function):
+    """The bottleneck of VectorQuantizer / VectorQuantizerEMA (reference vector_quantizer_ema.py:101-179).
+
+    forward(z, codebook, state) -> (quantized_ste, scalars) where scalars = [sse, e_latent, perplexity, beta*e_latent,
+    e_latent + beta*e_latent].  `state` is a dict owned by the module: ws, layout, beta, ema (None or dict with
+    cluster_size, ema_w, decay, eps), training, stats_allreduce (callable or None), want (dict of optional output
+    buffers filled in place: idx, stats, dmin2, distances, q_rows).
+    backward: grad_z = g_q + g_loss * 2 beta (x - q) / (N D); non-EMA also grad_E (vector_quantizer.py:136-139).
+    """
+
+    @staticmethod
+    def forward(ctx, z, codebook, state):
+        z = z.contiguous()
+        layout, beta, ws = state['layout'], state['beta'], state['ws']
+        K, D = codebook.shape
+        ema = state['ema']
+        cb = codebook.detach()
+        want = state['want']
+        idx, stats = ops.vq_assign(z, cb, layout, ws, idx=want.get('idx'), stats=want.get('stats'),
+                                   dmin2=want.get('dmin2'), distances=want.get('distances'))
+        N = idx.numel()
+        n_total = N
+        if state['training'] and ema is not None:
+            if state.get('stats_allreduce') is not None:
+                n_total = state['stats_allreduce'](stats, N)
+            ops.vq_ema_update(ema['cluster_size'], ema['ema_w'], cb, stats, ema['decay'], ema['eps'])
+        out, scalars = ops.vq_quantize(z, idx, cb, layout, ws, stats[:K], n_total, beta, q_rows=want.get('q_rows'))
+        ctx.save_for_backward(z, idx, cb, stats)
+        ctx.cfg = (layout, beta, ema is not None, N, D)
+        want['idx'] = idx
+        want['stats'] = stats
+        return out, scalars
+
+    @staticmethod
+    def backward(ctx, g_out, g_scalars):
+        z, idx, cb, stats = ctx.saved_tensors
+        layout, beta, is_ema, N, D = ctx.cfg
+        dev = z.device
+        if g_scalars is None:
+            g_scalars = torch.zeros(8, dtype=torch.float32, device=dev)
+        g_scalars = g_scalars.contiguous()
+        # the loss the modules expose is scalars[3] (EMA) or scalars[4] (non-EMA); both are affine in e_latent:
+        #   EMA:      vq_loss = beta * e_latent                       -> d/dz = g * 2 beta (x - q) / (N D)
+        #   non-EMA:  vq_loss = q_latent + beta * e_latent (same value; q_latent's input is detached) -> same d/dz
+        gl = g_scalars[3:4] if is_ema else g_scalars[4:5]
+        if g_out is None:
+            g_out = torch.zeros_like(z)
+        gz = ops.vq_backward(g_out.contiguous(), gl, 2.0 * beta / (N * D), z, idx, cb, layout)
+        gE = None
+        if not is_ema and ctx.needs_input_grad[1]:
+            gE = ops.vq_grad_codebook(stats, cb, gl, 2.0 / (N * D))
+        return gz, gE, None

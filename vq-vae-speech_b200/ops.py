@@ -1,0 +1,305 @@
+"""Tensor-level wrappers over the C ABI (include/vqs_b200.h).  torch is used for device memory and streams only:
+every function here launches hand-written kernels from libvqs_b200.so on torch's current CUDA stream and never falls
+back to a torch/ATen implementation (CPU tensors raise)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_BDT_AS_DTB, LAYOUT_FLAT_ND, ConvGemmDesc, WgradDesc
+
+MASK_NONE, MASK_FLOAT, MASK_U8 = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# When a recorder list is installed (trainer.FusedTrainStep builds its schedule this way) launches are appended to it as
+# (c_function, args, keepalive) instead of being issued; replaying the list re-issues them with the then-current stream.
+_RECORDER = None
+
+
+def set_recorder(rec):
+    global _RECORDER
+    prev = _RECORDER
+    _RECORDER = rec
+    return prev
+
+
+def record_callable(fn):
+    """Adds a host callable (e.g. an NCCL collective) to the schedule being recorded; runs it now when not recording."""
+    if _RECORDER is not None:
+        _RECORDER.append((None, fn, None))
+    else:
+        fn()
+
+
+def _call(name, args, keep=None):
+    fn = getattr(_lib.load(), name)
+    if _RECORDER is not None:
+        _RECORDER.append((fn, args, keep))
+        return
+    _lib.check(fn(*args, _stream()))
+
+
+def replay(schedule):
+    st = _stream()
+    for fn, args, _ in schedule:
+        if fn is None:
+            args()
+        else:
+            rc = fn(*args, st)
+            if rc != 0:
+                _lib.check(rc)
+
+
+def _p(t, dtype=torch.float32):
+    """Device pointer of a contiguous CUDA tensor of the expected dtype (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('libvqs_b200 has no CPU path: got a tensor on %s' % t.device)
+    if t.dtype != dtype:
+        raise RuntimeError('expected %s tensor, got %s' % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError('expected a contiguous tensor, got strides %s for shape %s' % (t.stride(), tuple(t.shape)))
+    return t.data_ptr()
+
+
+def _pany(t):
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise RuntimeError('expected a contiguous CUDA tensor')
+    return t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# VQ bottleneck
+# ------------------------------------------------------------------------------------------------
+def vq_workspace_bytes(K, D):
+    return int(_lib.load().vqs_vq_workspace_bytes(K, D))
+
+
+def vq_workspace(K, D, device):
+    return torch.empty(vq_workspace_bytes(K, D), dtype=torch.uint8, device=device)
+
+
+def vq_shape(z, layout, D):
+    """(B, D, T) triple the C ABI expects.  FLAT_ND: z is (N, D) -> (N, D, 1) i.e. B=N, T=1."""
+    if layout == LAYOUT_FLAT_ND:
+        if z.dim() != 2 or z.shape[1] != D:
+            raise RuntimeError('flat layout expects (N, %d), got %s' % (D, tuple(z.shape)))
+        return z.shape[0], D, 1
+    if z.dim() != 3 or z.shape[1] != D:
+        raise RuntimeError('VQ input must be (B, %d, T), got %s' % (D, tuple(z.shape)))
+    return z.shape[0], D, z.shape[2]
+
+
+def vq_assign(z, codebook, layout, ws, idx=None, stats=None, dmin2=None, distances=None):
+    K, D = codebook.shape
+    B, _, T = vq_shape(z, layout, D)
+    N = B * T
+    if idx is None:
+        idx = torch.empty(N, dtype=torch.int64, device=z.device)
+    if stats is None:
+        stats = torch.empty(K * (D + 1), dtype=torch.float32, device=z.device)
+    _call('vqs_vq_assign', (_p(z), layout, B, D, T, _p(codebook), K, _p(idx, torch.int64), _p(stats),
+                                         _p(dmin2), _p(distances), _pany(ws), ws.numel()))
+    return idx, stats
+
+
+def vq_one_hot(idx, K, out=None):
+    N = idx.numel()
+    if out is None:
+        out = torch.empty(N, K, dtype=torch.float32, device=idx.device)
+    _call('vqs_vq_one_hot', (_p(idx, torch.int64), N, K, _p(out)))
+    return out
+
+
+def vq_ema_update(cluster_size, ema_w, embedding, stats, decay, eps):
+    K, D = embedding.shape
+    _call('vqs_vq_ema_update', (_p(cluster_size), _p(ema_w), _p(embedding), _p(stats), float(decay),
+                                             float(1 - decay), float(eps), float(K * eps), K, D))
+
+
+def vq_quantize(z, idx, codebook, layout, ws, counts, n_rows_total, beta, out=None, q_rows=None, scalars=None):
+    K, D = codebook.shape
+    B, _, T = vq_shape(z, layout, D)
+    if out is None:
+        out = torch.empty_like(z)
+    if scalars is None:
+        scalars = torch.empty(8, dtype=torch.float32, device=z.device)
+    _call('vqs_vq_quantize', (_p(z), layout, B, D, T, _p(idx, torch.int64), _p(codebook), K, _p(out),
+                                           _p(q_rows), _p(counts), float(n_rows_total), float(beta), _p(scalars),
+                                           _pany(ws), ws.numel()))
+    return out, scalars
+
+
+def vq_backward(g_out, g_loss, coef, z, idx, codebook, layout, out=None):
+    K, D = codebook.shape
+    B, _, T = vq_shape(z, layout, D)
+    if out is None:
+        out = torch.empty_like(z)
+    _call('vqs_vq_backward', (_p(g_out), _p(g_loss), float(coef), _p(z), layout, B, D, T,
+                                           _p(idx, torch.int64), _p(codebook), K, _p(out)))
+    return out
+
+
+def vq_grad_codebook(stats, codebook, g_loss, coef, out=None, accumulate=False):
+    K, D = codebook.shape
+    if out is None:
+        out = torch.empty_like(codebook)
+    _call('vqs_vq_grad_codebook', (_p(stats), _p(codebook), _p(g_loss), float(coef), K, D, _p(out),
+                                                int(accumulate)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# conv-like implicit GEMM
+# ------------------------------------------------------------------------------------------------
+def conv_gemm(A, X, out, M, Cred, ksz, B, Lin, Lout, l_mul, j_mul, off, l_div=1, x_strides=None, x_relu=False,
+              bias=None, add_pre=None, add_pre_relu=False, relu=False, mask_out=None, mask=None, mask_kind=MASK_NONE,
+              add_post=None, out2=None, mask2=None, mask2_kind=MASK_NONE):
+    """acc[b,m,l] = sum_{c,j} A[m, c*ksz+j] * X'[b, c, (l*l_mul + j*j_mul + off)/l_div] followed by the fused epilogue
+    documented in include/vqs_b200.h.  x_strides = (batch, channel, position) element strides of X (default NCL)."""
+    d = ConvGemmDesc()
+    d.A = _p(A)
+    d.X = X.data_ptr() if x_strides is not None else _p(X)
+    d.M, d.Cred, d.ksz = M, Cred, ksz
+    d.B, d.Lin, d.Lout = B, Lin, Lout
+    if x_strides is None:
+        x_strides = (Cred * Lin, Lin, 1)
+    d.x_sb, d.x_sc, d.x_sl = x_strides
+    d.l_mul, d.j_mul, d.off, d.l_div = l_mul, j_mul, off, l_div
+    d.x_relu = int(x_relu)
+    d.bias = _p(bias)
+    d.add_pre = _p(add_pre)
+    d.add_pre_relu = int(add_pre_relu)
+    d.relu = int(relu)
+    d.mask_out = _p(mask_out, torch.uint8)
+    d.mask = _pany(mask)
+    d.mask_kind = mask_kind if mask is not None else MASK_NONE
+    d.add_post = _p(add_post)
+    d.out = _p(out)
+    d.out2 = _p(out2)
+    d.mask2 = _pany(mask2)
+    d.mask2_kind = mask2_kind if mask2 is not None else MASK_NONE
+    _call('vqs_conv_gemm', (ctypes.byref(d),), d)
+    return out
+
+
+def wgrad_workspace_bytes(M, Cred, ksz, B, La):
+    return int(_lib.load().vqs_wgrad_workspace_bytes(M, Cred, ksz, B, La))
+
+
+def wgrad_gemm(Aact, X, dW, M, Cred, ksz, B, La, Lx, l_mul, j_mul, off, ws, x_relu=False, accumulate=False):
+    d = WgradDesc()
+    d.Aact = _p(Aact)
+    d.X = _p(X)
+    d.M, d.Cred, d.ksz = M, Cred, ksz
+    d.B, d.La, d.Lx = B, La, Lx
+    d.l_mul, d.j_mul, d.off = l_mul, j_mul, off
+    d.x_relu = int(x_relu)
+    d.dW = _p(dW)
+    d.accumulate = int(accumulate)
+    _call('vqs_wgrad_gemm', (ctypes.byref(d), _pany(ws), 0 if ws is None else ws.numel()), d)
+    return dW
+
+
+def bias_grad(g, db, accumulate=False):
+    B, M, L = g.shape
+    _call('vqs_bias_grad', (_p(g), B, M, L, _p(db), int(accumulate)))
+    return db
+
+
+def permute_weight(w, out=None):
+    d0, d1, k = w.shape
+    if out is None:
+        out = torch.empty(d1, d0, k, dtype=torch.float32, device=w.device)
+    _call('vqs_permute_weight', (_p(w), d0, d1, k, _p(out)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# element-wise pieces
+# ------------------------------------------------------------------------------------------------
+def upsample2_fwd(x, out=None):
+    B, C, L = x.shape
+    if out is None:
+        out = torch.empty(B, C, 2 * L, dtype=torch.float32, device=x.device)
+    _call('vqs_upsample2_fwd', (_p(x), B * C, L, _p(out)))
+    return out
+
+
+def upsample2_bwd(g, out=None):
+    B, C, L2 = g.shape
+    if out is None:
+        out = torch.empty(B, C, L2 // 2, dtype=torch.float32, device=g.device)
+    _call('vqs_upsample2_bwd', (_p(g), B * C, L2 // 2, _p(out)))
+    return out
+
+
+def jitter_fwd(x, src, out=None):
+    B, C, L = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _call('vqs_jitter_fwd', (_p(x), B * C, L, _p(src, torch.int32), _p(out)))
+    return out
+
+
+def jitter_bwd(g, src, out=None):
+    B, C, L = g.shape
+    if out is None:
+        out = torch.empty_like(g)
+    _call('vqs_jitter_bwd', (_p(g), B * C, L, _p(src, torch.int32), _p(out)))
+    return out
+
+
+def relu_fwd(x, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    _call('vqs_relu_fwd', (_p(x), x.numel(), _p(out)))
+    return out
+
+
+def relu_bwd(g, act, out=None):
+    if out is None:
+        out = torch.empty_like(g)
+    _call('vqs_relu_bwd', (_p(g), _p(act), g.numel(), _p(out)))
+    return out
+
+
+def add(a, b, out=None):
+    if out is None:
+        out = torch.empty_like(a)
+    _call('vqs_add', (_p(a), _p(b), a.numel(), _p(out)))
+    return out
+
+
+def blc_to_ncl(x, out=None):
+    B, L, C = x.shape
+    if out is None:
+        out = torch.empty(B, C, L, dtype=torch.float32, device=x.device)
+    _call('vqs_blc_to_ncl', (_p(x), B, L, C, _p(out)))
+    return out
+
+
+def mse_workspace(device):
+    return torch.empty(148 * 8 * 8 * 2, dtype=torch.uint8, device=device)
+
+
+def mse_fwd_bwd(recon, target, target_strides, g_scale, loss, grad, ws):
+    """loss[0] = mean((recon - target)^2); grad = g_scale * 2 (recon - target) / numel (grad may be None)."""
+    B, C, L = recon.shape
+    sb, sc, sl = target_strides
+    _call('vqs_mse_fwd_bwd', (_p(recon), target.data_ptr(), B, C, L, sb, sc, sl, float(g_scale), _p(loss),
+                                           _p(grad), _pany(ws), ws.numel()))
+    return loss, grad
+
+
+def amsgrad_step(p, g, m, v, vmax, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, g_scale=1.0, inc_step=True):
+    _call('vqs_amsgrad_step', (_p(p), _p(g), _p(m), _p(v), _p(vmax), p.numel(), _p(step, torch.int64),
+                                            int(inc_step), float(lr), float(beta1), float(beta2), float(eps),
+                                            float(g_scale)))
