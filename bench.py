@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native VQ-VAE-Speech training hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): vq44-mfcc39 full training step -- ConvolutionalEncoder + VectorQuantizerEMA(44x64,
+decay 0.99) + DeconvolutionalDecoder, MSE + vq_loss, Adam(lr 2e-4, amsgrad) -- on synthetic normalised-MFCC-39 batches of
+VCTK shape (T = 47 frames), fp32, per-GPU batch fixed (weak scaling), gradients and EMA statistics allreduced over NCCL.
+Prints ONE JSON line (rank 0).  A "step" is one full training iteration on one batch.
+
+  value      utterances/s over all ranks, inputs resident in HBM, K steps timed with CUDA events, max over ranks
+  e2e        the same through FusedTrainStep.step() with HOST (pinned) batches: H2D copy + step + D2H of the losses
+  roofline   the dominant kernel family of the timed region (per-launch CUDA events recorded inside the timed region)
+  vq         the fused VQ fwd+bwd+EMA metric of BASELINE.json on N = 2^22 rows against the HBM roofline
+  cpu_baseline  oracle/torch_port.py (torch CPU operators = the reference's own backend) on the box's host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='utterances per GPU per step')
+    ap.add_argument('--frames', type=int, default=47, help='MFCC frames per utterance (length 7680 -> 47)')
+    ap.add_argument('--decay', type=float, default=0.99)
+    ap.add_argument('--codes', type=int, default=44)
+    ap.add_argument('--vq-rows', type=int, default=1 << 22)
+    ap.add_argument('--skip-vq', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return dict(hbm=float(p['hbm_gbs']), tensor=float(p['bf16_tflops_sustained']),
+                    tensor_burst=float(p['bf16_tflops']), src='measured')
+    except Exception:
+        return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, src='fallback')
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.3] or [r for _, r in self.rows]
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def model_config(args):
+    from vq_vae_speech_b200.trainer import reference_config
+    return reference_config(decay=args.decay, num_embeddings=args.codes, batch_size=args.batch)
+
+
+def flops_of(entry):
+    """Algorithmic FLOPs of one recorded launch (2 * MACs that touch real data), from its descriptor."""
+    fn, _, d = entry
+    name = fn.__name__
+    if name == 'vqs_conv_gemm':
+        return 2.0 * d.M * d.Cred * d.ksz * d.B * d.Lout / d.l_div
+    if name == 'vqs_wgrad_gemm':
+        return 2.0 * d.M * d.Cred * d.ksz * d.B * d.La
+    return 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle/torch_port.py on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_train_throughput(cfg, batch, frames, seconds, warmup=2, min_steps=3, max_steps=200, fixed_steps=None):
+    import torch
+    from oracle.torch_port import PortTrainer
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tr = PortTrainer(cfg, seed=1234)
+    gen = torch.Generator().manual_seed(1234)
+    xs = [torch.randn(batch, frames, 39, generator=gen) for _ in range(4)]
+    for i in range(warmup):
+        tr.step(xs[i % 4])
+    n, t0 = 0, time.perf_counter()
+    while True:
+        tr.step(xs[n % 4])
+        n += 1
+        el = time.perf_counter() - t0
+        if fixed_steps is not None:
+            if n >= fixed_steps:
+                break
+        elif (el >= seconds and n >= min_steps) or n >= max_steps:
+            break
+    el = time.perf_counter() - t0
+    return dict(value=batch * n / el, ms_per_step=1e3 * el / n, steps=n, cores=cores, threads=torch.get_num_threads())
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (torch CPU operators) on the host cores.
+    Rank 0 alone runs; each step is a bounded sample (a smaller batch when needed) of the same workload."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cfg = model_config(args)
+    # bound the run to a few minutes: calibrate one step at the full per-GPU batch, shrink the sample batch if needed
+    batch = args.batch
+    probe = cpu_train_throughput(cfg, batch, args.frames, 0.0, warmup=1, fixed_steps=1)
+    budget_s = 150.0
+    need = probe['ms_per_step'] * 1e-3 * (args.steps + args.warmup)
+    while need > budget_s and batch > 2:
+        batch = max(2, batch // 2)
+        need /= 2
+    r = cpu_train_throughput(cfg, batch, args.frames, 0.0, warmup=args.warmup, fixed_steps=args.steps)
+    sample = 'torch-CPU port of the reference step (oracle/torch_port.py), %d threads, batch %d x %d frames per step' % (
+        r['threads'], batch, args.frames)
+    line = {
+        'impl': 'reference', 'metric': 'train_utterances_per_sec', 'value': r['value'], 'unit': 'utterances/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, 1, batch_override=batch),
+        'cpu_baseline': {'value': r['value'], 'unit': 'utterances/s', 'cores': r['cores'], 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': r['value'], 'unit': 'utterances/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world, batch_override=None):
+    b = batch_override if batch_override is not None else args.batch
+    return {'workload': 'vq44-mfcc39 full training step (encoder + VectorQuantizerEMA %dx64 + decoder, MSE + vq_loss, '
+                        'AMSGrad lr 2e-4), synthetic MFCC-39, T=%d' % (args.codes, args.frames),
+            'per_gpu_batch': b, 'global_batch': b * world, 'frames': args.frames, 'decay': args.decay,
+            'parallelism': 'dp%d' % world,
+            'l2': 'no explicit flush: every step streams weights + optimizer state + activations >> 126 MB L2'}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def vq_bench(dev, pk, rows, K=44, D=64, iters=20):
+    """BASELINE.json's first metric: VQ rows/s for fused fwd + bwd + EMA, N rows resident in HBM (1 GiB at N = 2^22, far
+    beyond L2).  Kernels: vqs_vq_assign, vqs_vq_ema_update, vqs_vq_quantize, vqs_vq_backward, each bracketed by events."""
+    import torch
+    from vq_vae_speech_b200 import ops, LAYOUT_BDT_AS_DTB, LAYOUT_FLAT_ND
+    out = {}
+    T = 128
+    B = rows // T
+    N = B * T
+    gen = torch.Generator(device=dev).manual_seed(7)
+    W0 = torch.randn(K, D, device=dev, generator=gen)
+    for lname, layout, shape in (('bdt', LAYOUT_BDT_AS_DTB, (B, D, T)), ('flat', LAYOUT_FLAT_ND, (N, D))):
+        z = torch.randn(*shape, device=dev, generator=gen)
+        g = torch.randn(*shape, device=dev, generator=gen)
+        W = W0.clone()
+        cs = torch.zeros(K, device=dev)
+        ew = torch.randn(K, D, device=dev, generator=gen)
+        ws = ops.vq_workspace(K, D, dev)
+        idx = torch.empty(N, dtype=torch.int64, device=dev)
+        stats = torch.empty(K * (D + 1), device=dev)
+        q = torch.empty_like(z)
+        gz = torch.empty_like(z)
+        sc = torch.zeros(8, device=dev)
+        one = torch.ones(1, device=dev)
+        names = ['assign', 'ema_update', 'quantize', 'backward']
+        acc = dict((n, 0.0) for n in names)
+
+        def once(evs):
+            def br(name, f):
+                if evs is None:
+                    f()
+                    return
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                f()
+                e1.record()
+                evs.append((name, e0, e1))
+            br('assign', lambda: ops.vq_assign(z, W, layout, ws, idx=idx, stats=stats))
+            br('ema_update', lambda: ops.vq_ema_update(cs, ew, W, stats, 0.99, 1e-5))
+            br('quantize', lambda: ops.vq_quantize(z, idx, W, layout, ws, stats[:K], N, 0.25, out=q, scalars=sc))
+            br('backward', lambda: ops.vq_backward(g, one, 2 * 0.25 / (N * D), z, idx, W, layout, out=gz))
+        for _ in range(3):
+            once(None)
+        torch.cuda.synchronize()
+        evs = []
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(iters):
+            once(evs)
+        t1.record()
+        torch.cuda.synchronize()
+        total_ms = t0.elapsed_time(t1) / iters
+        for n, e0, e1 in evs:
+            acc[n] += e0.elapsed_time(e1) / iters
+        alg_bytes = (20 * D + 16) * N                       # fwd 8D+8, bwd 12D+8 per row
+        out[lname] = {'rows': N, 'rows_per_s': N / (total_ms * 1e-3), 'ms': total_ms,
+                      'kernel_ms': dict((k, round(v, 4)) for k, v in acc.items()),
+                      'algorithmic_gbs': alg_bytes / (total_ms * 1e-3) / 1e9,
+                      'frac_of_hbm_peak': alg_bytes / (total_ms * 1e-3) / 1e9 / pk['hbm']}
+        del z, g, q, gz
+    out['peak_gbs'] = pk['hbm']
+    out['peak_source'] = pk['src']
+    out['bytes_per_row'] = 20 * D + 16
+    out['K'], out['D'] = K, D
+    return out
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py --impl b200 needs a CUDA device: the product has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    from vq_vae_speech_b200 import _lib, ops
+    from vq_vae_speech_b200.convolutional_vq_vae import ConvolutionalVQVAE
+    from vq_vae_speech_b200.trainer import FusedTrainStep
+    pk = peaks()
+    cfg = model_config(args)
+    torch.manual_seed(1234)                 # same weights on every rank (replicated model)
+    model = ConvolutionalVQVAE(cfg, dev).to(dev).train()
+    B, T = args.batch, args.frames
+    eng = FusedTrainStep(model, B, T, cfg['learning_rate'])
+    gen = torch.Generator().manual_seed(1234 + rank)        # each rank trains on its own shard of the global batch
+    host = [torch.randn(B, T, 39, generator=gen).pin_memory() for _ in range(8)]
+    devb = [h.to(dev) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (>= 3): first step eager, later ones through the CUDA graph when single-GPU ----
+    W = max(args.warmup, 3)
+    for i in range(W):
+        eng.load_batch(devb[i % 8])
+        eng.step()
+    eng.losses()
+    # ---- timed region: K steps, inputs resident in HBM; every launch bracketed by CUDA events on the launch stream ----
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    lc0 = _lib.launch_count()
+    events = []
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    t0.record()
+    for i in range(args.steps):
+        eng.load_batch(devb[i % 8])
+        ops.replay(eng.schedule, events)
+        eng.steps_done += 1
+    t1.record()
+    barrier()
+    w1 = time.perf_counter()
+    launches = _lib.launch_count() - lc0
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    clocks = sampler.stop(w0, w1) if sampler else None
+    ms_per_step = ms / args.steps
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel accounting of the timed region ----
+    fam = {}
+    for i, e0, e1 in events:
+        entry = eng.schedule[i]
+        name = entry[0].__name__
+        f = fam.setdefault(name, [0.0, 0.0, 0])
+        f[0] += e0.elapsed_time(e1)
+        f[1] += flops_of(entry)
+        f[2] += 1
+    kern_ms = sum(v[0] for v in fam.values())
+    dom = max(fam.items(), key=lambda kv: kv[1][0])
+    dname, (dms, dflops, dn) = dom
+    achieved = dflops / (dms * 1e-3) / 1e12
+    roofline = {'bound': 'tensor', 'kernel': dname, 'achieved': achieved, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['tensor'], 'traffic': None, 'peak_source': pk['src'] + ' bf16 sustained',
+                'launches_per_step': dn // args.steps, 'avg_launch_ms': dms / dn,
+                'share_of_step_kernel_time': dms / kern_ms,
+                'note': 'exact-fp32 CUDA-core implicit GEMM (1e-5 parity mode); FLOPs = 2*M*Cred*k*B*L per launch'}
+    breakdown = dict((k, {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[2] // args.steps,
+                          'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[1] else None}) for k, v in fam.items())
+
+    # ---- the same K steps through the CUDA graph (single GPU), no per-launch events ----
+    graph_ms = None
+    if eng.use_graph:
+        for i in range(2):
+            eng.load_batch(devb[i % 8])
+            eng.step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            eng.load_batch(devb[i % 8])
+            eng.step()
+        g1.record()
+        torch.cuda.synchronize()
+        graph_ms = g0.elapsed_time(g1) / args.steps
+
+    # ---- e2e: host (pinned) batches -> H2D -> step -> D2H of the losses, every step ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for i in range(args.steps):
+        eng.step(host[i % 8])          # H2D copy from pinned memory + the step
+        last = eng.losses()            # 16-byte D2H + stream sync
+    e1.record()
+    barrier()
+    ems = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ems], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ems = float(tms.item())
+    e2e = {'value': B * world * args.steps / (ems * 1e-3), 'unit': 'utterances/s',
+           'h2d_bytes_per_step': B * T * 39 * 4, 'd2h_bytes_per_step': 16, 'ms_per_step': ems / args.steps,
+           'last_losses': last}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    vq = None
+    if not args.skip_vq and world == 1:
+        vq = vq_bench(dev, pk, args.vq_rows, K=args.codes)
+    cpu = None
+    if not args.skip_cpu and world == 1:
+        r = cpu_train_throughput(cfg, B, T, args.cpu_seconds)
+        cpu = {'value': r['value'], 'unit': 'utterances/s', 'cores': r['cores'], 'kind': 'port',
+               'sample': 'torch-CPU port of the reference step (oracle/torch_port.py: the reference\'s own ATen/oneDNN/MKL '
+                         'operators), %d threads, %d steps of batch %d x %d frames (%.1f ms/step)' % (
+                             r['threads'], r['steps'], B, T, r['ms_per_step'])}
+    line = {
+        'metric': 'train_utterances_per_sec', 'value': value, 'unit': 'utterances/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
+        'ms_per_step_cuda_graph': graph_ms, 'kernel_breakdown': breakdown, 'vq': vq,
+        'params': eng.n_params, 'flops_per_step': sum(flops_of(e) for e in eng.schedule if e[0] is not None),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

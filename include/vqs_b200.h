@@ -207,9 +207,11 @@ int vqs_blc_to_ncl(const float* in, int B, int L, int C, float* out, vqs_stream_
  *   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; vmax <- max(vmax, v)
  *   p <- p - (lr / bc1) * m / (sqrt(vmax) / sqrt(bc2) + eps),  bc1 = 1 - b1^step, bc2 = 1 - b2^step
  * `step` is read from a device int64 (incremented by the kernel launch BEFORE use when inc_step != 0) so that the call
- * is CUDA-graph replayable.  g_scale multiplies the gradient first (1/world_size after a sum-allreduce). */
+ * is CUDA-graph replayable.  g_scale multiplies the gradient first (1/world_size after a sum-allreduce).  Hyper-parameters
+ * are doubles: the scalar algebra (1 - beta, bias corrections, lr / bc1) is done in double and rounded to fp32 once, as
+ * torch does with its Python-float hyper-parameters. */
 int vqs_amsgrad_step(float* p, const float* g, float* m, float* v, float* vmax, long long n, long long* step,
-                     int inc_step, float lr, float beta1, float beta2, float eps, float g_scale, vqs_stream_t stream);
+                     int inc_step, double lr, double beta1, double beta2, double eps, double g_scale, vqs_stream_t stream);
 
 #ifdef __cplusplus
 }

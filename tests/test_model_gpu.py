@@ -1,0 +1,157 @@
+"""GPU parity of the full encoder + VQ + decoder training step against golden vectors produced by the unmodified
+reference (tests/golden/model_*.npz: `ConvolutionalVQVAE` + `Adam(amsgrad=True)` for several consecutive steps), for
+both product paths: the drop-in nn.Modules under autograd, and the fused / CUDA-graph training step."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+MODEL_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, 'model_*.npz')))
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    return torch.device('cuda:0')
+
+
+def _cfg(g):
+    cfg = dict(output_features_filters=13, augment_output_features=True, output_features_dim=47, verbose=False,
+               input_features_dim=47, use_kaiming_normal=False, input_features_type='mfcc', input_features_filters=13,
+               augment_input_features=True, sampling_rate=16000, use_speaker_conditioning=False,
+               record_codebook_stats=False)
+    for k in ('num_hiddens', 'num_residual_layers', 'embedding_dim', 'num_embeddings', 'residual_channels'):
+        cfg[k] = int(g['cfg_' + k])
+    for k in ('decay', 'commitment_cost', 'jitter_probability', 'learning_rate'):
+        cfg[k] = float(g['cfg_' + k])
+    cfg['use_jitter'] = bool(g['cfg_use_jitter'])
+    return cfg
+
+
+def _build(g, dev):
+    from vq_vae_speech_b200.convolutional_vq_vae import ConvolutionalVQVAE
+    cfg = _cfg(g)
+    model = ConvolutionalVQVAE(cfg, dev)
+    sd = {k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('init.')}
+    model.load_state_dict(sd)
+    return model.to(dev).train(), cfg
+
+
+def _check_final(model, g, cfg, steps):
+    # Adam divides by sqrt(v): where |grad| is at fp32-noise level the direction itself is noise, so post-step parameters
+    # are compared against the size of the cumulative update (lr * steps), like tests/test_oracle_golden.py
+    budget = 0.05 * cfg['learning_rate'] * steps
+    sd = model.state_dict()
+    for k, ref in g.items():
+        if not k.startswith('final.'):
+            continue
+        n = k[6:]
+        got = sd[n].detach().cpu().numpy()
+        if n.startswith('_vq.') and cfg['decay'] > 0:
+            assert rel_err(got, ref) < TOL, n
+        else:
+            assert float(np.max(np.abs(got - ref))) < budget, n
+
+
+@pytest.mark.parametrize('case', MODEL_CASES)
+def test_module_path_matches_reference(case):
+    """Drop-in nn.Modules + autograd + our fused AMSGrad == reference modules + torch Adam(amsgrad=True)."""
+    dev = _dev()
+    from vq_vae_speech_b200 import functional as F, ops
+    g = load_golden(case)
+    model, cfg = _build(g, dev)
+    params = [p for p in model.parameters()]
+    state = {}
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    if cfg['use_jitter']:
+        np.random.seed(int(g['seed']))
+    steps = int(g['steps'])
+    for s in range(steps):
+        x = torch.from_numpy(g[f'x{s}']).to(dev)
+        for p in params:
+            p.grad = None
+        recon, vq_loss, losses, perplexity, idx, _ = model(x, None, None)
+        recon_loss = F.mse_loss(recon, x.permute(0, 2, 1))
+        loss = vq_loss + recon_loss
+        loss.backward()
+        if cfg['use_jitter']:
+            assert np.array_equal(model._decoder._jitter.last_plan, g[f'jitter_src{s}'])
+        assert np.array_equal(idx.cpu().numpy().reshape(-1), g[f'idx{s}'].reshape(-1))
+        assert tuple(recon.shape) == g[f'recon{s}'].shape
+        assert rel_err(recon.detach().cpu().numpy(), g[f'recon{s}']) < TOL
+        assert rel_err(vq_loss.item(), g[f'vq_loss{s}']) < TOL
+        assert rel_err(recon_loss.item(), g[f'recon_loss{s}']) < TOL
+        assert rel_err(perplexity.item(), g[f'perplexity{s}']) < TOL
+        if s == 0:
+            for n, p in model.named_parameters():
+                key = 'grad0.' + n
+                if key in g:
+                    assert p.grad is not None, n
+                    assert rel_err(p.grad.cpu().numpy(), g[key]) < 2e-5, n
+                else:
+                    assert p.grad is None, n
+        first = True
+        for p in params:            # Adam(amsgrad=True): parameters without a gradient are skipped (EMA codebook)
+            if p.grad is None:
+                continue
+            if p not in state:
+                state[p] = [torch.zeros_like(p) for _ in range(3)]
+            m, v, vm = state[p]
+            ops.amsgrad_step(p.data, p.grad.contiguous(), m, v, vm, step, cfg['learning_rate'], inc_step=first)
+            first = False
+    _check_final(model, g, cfg, steps)
+
+
+@pytest.mark.parametrize('case', MODEL_CASES)
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_fused_step_matches_reference(case, use_graph):
+    """The hand-scheduled (and CUDA-graph captured) training step == the reference trainer iteration."""
+    dev = _dev()
+    from vq_vae_speech_b200.trainer import FusedTrainStep
+    g = load_golden(case)
+    model, cfg = _build(g, dev)
+    B, T = int(g['B']), int(g['T'])
+    eng = FusedTrainStep(model, B, T, cfg['learning_rate'], use_graph=use_graph)
+    if cfg['use_jitter']:
+        np.random.seed(int(g['seed']))
+    steps = int(g['steps'])
+    for s in range(steps):
+        eng.step(torch.from_numpy(g[f'x{s}']))
+        out = eng.losses()
+        if cfg['use_jitter']:
+            assert np.array_equal(eng.last_plan, g[f'jitter_src{s}'])
+        assert np.array_equal(eng.encoding_indices().cpu().numpy().reshape(-1), g[f'idx{s}'].reshape(-1))
+        assert rel_err(eng.buf['recon'].cpu().numpy(), g[f'recon{s}']) < TOL
+        assert rel_err(out['vq_loss'], g[f'vq_loss{s}']) < TOL
+        assert rel_err(out['reconstruction_loss'], g[f'recon_loss{s}']) < TOL
+        assert rel_err(out['perplexity'], g[f'perplexity{s}']) < TOL
+        if s == 0:
+            grads = eng.gradients()
+            for k, ref in g.items():
+                if k.startswith('grad0.') and '_layers.1.' not in k:
+                    assert rel_err(grads[k[6:]].cpu().numpy(), ref) < 2e-5, k
+    assert eng.graph is not None or not use_graph
+    _check_final(model, g, cfg, steps)
+
+
+def test_state_dict_keys_and_init_match_reference():
+    """Same constructor order -> same initial weights under the same torch seed; same state_dict keys."""
+    _dev()
+    from vq_vae_speech_b200.convolutional_vq_vae import ConvolutionalVQVAE
+    for case in MODEL_CASES:
+        g = load_golden(case)
+        cfg = _cfg(g)
+        torch.manual_seed(int(g['seed']))
+        np.random.seed(int(g['seed']))
+        model = ConvolutionalVQVAE(cfg, 'cpu')
+        sd = model.state_dict()
+        keys = sorted(k[5:] for k in g if k.startswith('init.'))
+        assert sorted(sd.keys()) == keys
+        for k in keys:
+            assert np.array_equal(sd[k].numpy(), g['init.' + k]), k

@@ -127,3 +127,30 @@ def test_model_oracle_matches_reference(case):
             assert rel_err(p[n], ref) < TOL, n          # EMA state is not touched by Adam
         else:
             assert float(np.max(np.abs(p[n] - ref))) < budget, n
+
+
+@pytest.mark.parametrize('case', MODEL_CASES)
+def test_torch_port_matches_reference(case):
+    """oracle/torch_port.py (what bench.py times as the CPU baseline) reproduces the reference's training steps."""
+    import torch
+    from oracle.torch_port import PortTrainer
+    g = load_golden(case)
+    cfg = dict(output_features_filters=13, augment_output_features=True, input_features_filters=13,
+               augment_input_features=True, use_jitter=bool(g['cfg_use_jitter']))
+    for k in ('num_hiddens', 'num_residual_layers', 'embedding_dim', 'num_embeddings', 'residual_channels'):
+        cfg[k] = int(g['cfg_' + k])
+    for k in ('decay', 'commitment_cost', 'jitter_probability', 'learning_rate'):
+        cfg[k] = float(g['cfg_' + k])
+    torch.set_num_threads(1)
+    tr = PortTrainer(cfg, seed=int(g['seed']))
+    tr.model.load_reference_state({k[5:]: v for k, v in g.items() if k.startswith('init.')})
+    np.random.seed(int(g['seed']))
+    for s in range(int(g['steps'])):
+        r = tr.step(torch.from_numpy(g[f'x{s}']))
+        if cfg['use_jitter']:
+            assert np.array_equal(r['jitter_src'], g[f'jitter_src{s}'])
+        assert np.array_equal(r['encoding_indices'].numpy().reshape(-1), g[f'idx{s}'].reshape(-1))
+        assert rel_err(r['reconstructed_x'].numpy(), g[f'recon{s}']) < TOL
+        assert rel_err(r['vq_loss'], g[f'vq_loss{s}']) < TOL
+        assert rel_err(r['reconstruction_loss'], g[f'recon_loss{s}']) < TOL
+        assert rel_err(r['perplexity'], g[f'perplexity{s}']) < TOL

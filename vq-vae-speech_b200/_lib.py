@@ -72,7 +72,7 @@ PROTOTYPES = {
     'vqs_add': (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     'vqs_blc_to_ncl': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'vqs_amsgrad_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int,
-                                 c_float, c_float, c_float, c_float, c_float, c_void_p]),
+                                 c_double, c_double, c_double, c_double, c_double, c_void_p]),
 }
 
 _LIB = None

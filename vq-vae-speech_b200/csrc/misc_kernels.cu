@@ -154,13 +154,15 @@ __global__ void step_inc_kernel(long long* step) { step[0] += 1; }
 __global__ void __launch_bounds__(256) amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                       float* __restrict__ m, float* __restrict__ v,
                                                       float* __restrict__ vmax, long long n4, long long n,
-                                                      const long long* __restrict__ step, float lr, float b1, float b2,
-                                                      float eps, float gscale) {
+                                                      const long long* __restrict__ step, double lr_d, double b1_d,
+                                                      double b2_d, float eps, float gscale) {
+  // scalar algebra in double, then rounded to fp32 once -- what torch does with its Python-float hyper-parameters
+  // (1 - beta2 = 0.001 exactly-rounded, not 1.f - 0.999f which is off by 1.3e-5 relative)
   const double t = (double)step[0];
-  const float bc1 = (float)(1.0 - pow((double)b1, t));
-  const float bc2s = (float)sqrt(1.0 - pow((double)b2, t));
-  const float step_size = lr / bc1;
-  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+  const float bc2s = (float)sqrt(1.0 - pow(b2_d, t));
+  const float step_size = (float)(lr_d / (1.0 - pow(b1_d, t)));
+  const float b2 = (float)b2_d;
+  const float omb1 = (float)(1.0 - b1_d), omb2 = (float)(1.0 - b2_d);
   GRID_STRIDE(i, n4) {
     float4 P = reinterpret_cast<float4*>(p)[i];
     float4 G = reinterpret_cast<const float4*>(g)[i];
@@ -276,7 +278,7 @@ extern "C" int vqs_mse_fwd_bwd(const float* recon, const float* target, int B, i
 }
 
 extern "C" int vqs_amsgrad_step(float* p, const float* g, float* m, float* v, float* vmax, long long n, long long* step,
-                                int inc_step, float lr, float beta1, float beta2, float eps, float g_scale,
+                                int inc_step, double lr, double beta1, double beta2, double eps, double g_scale,
                                 vqs_stream_t stream) {
   VQS_CHECK_ARG(p && g && m && v && vmax && step && n > 0, "vqs_amsgrad_step: bad arguments");
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -286,7 +288,8 @@ extern "C" int vqs_amsgrad_step(float* p, const float* g, float* m, float* v, fl
     step_inc_kernel<<<1, 1, 0, st>>>(step);
     VQS_LAUNCH_CHECK();
   }
-  amsgrad_kernel<<<ew_grid(n, 8), 256, 0, st>>>(p, g, m, v, vmax, n4, n, step, lr, beta1, beta2, eps, g_scale);
+  amsgrad_kernel<<<ew_grid(n, 8), 256, 0, st>>>(p, g, m, v, vmax, n4, n, step, lr, beta1, beta2, (float)eps,
+                                                (float)g_scale);
   VQS_LAUNCH_CHECK();
   return 0;
 }

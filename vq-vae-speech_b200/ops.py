@@ -43,15 +43,32 @@ def _call(name, args, keep=None):
     _lib.check(fn(*args, _stream()))
 
 
-def replay(schedule):
+def replay(schedule, events=None):
+    """Re-issues a recorded schedule on the current stream.  With `events` (a list) every launch is bracketed by a pair of
+    CUDA events recorded on that same stream and (index, start, end) is appended -- bench.py's per-kernel timing."""
     st = _stream()
-    for fn, args, _ in schedule:
+    if events is None:
+        for fn, args, _ in schedule:
+            if fn is None:
+                args()
+            else:
+                rc = fn(*args, st)
+                if rc != 0:
+                    _lib.check(rc)
+        return
+    cur = torch.cuda.current_stream()
+    for i, (fn, args, _) in enumerate(schedule):
         if fn is None:
             args()
-        else:
-            rc = fn(*args, st)
-            if rc != 0:
-                _lib.check(rc)
+            continue
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        rc = fn(*args, st)
+        e1.record(cur)
+        if rc != 0:
+            _lib.check(rc)
+        events.append((i, e0, e1))
 
 
 def _p(t, dtype=torch.float32):

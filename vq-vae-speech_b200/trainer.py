@@ -1,0 +1,432 @@
+"""Fused, data-parallel training step: the B200-native replacement of ConvolutionalTrainer.iterate
+(/root/reference/src/experiments/convolutional_trainer.py:44-74: zero_grad -> model -> MSE + vq_loss -> backward ->
+Adam(lr, amsgrad=True).step()).
+
+Instead of going through autograd, the step is a hand-scheduled sequence of libvqs_b200 launches over preallocated
+buffers (activations, one flat parameter buffer, one flat gradient buffer, flat AMSGrad state).  The sequence is recorded
+once (ops.set_recorder) and then either replayed launch by launch or captured into a CUDA graph, so a training step costs
+one graph launch on the host.  Under data parallelism (one process per GPU, torch.distributed / NCCL) each rank runs the
+step on its batch shard; the EMA statistics [counts | dw] are sum-allreduced between the assignment and the EMA update,
+and the flat gradient buffer is allreduced in two buckets (decoder first, overlapping the encoder's backward).
+
+Parity contract: per rank, the step equals the reference step on that rank's shard with the same
+codebook; EMA statistics are the sum over shards; gradients are the average over shards.
+"""
+import numpy as np
+import torch
+
+from . import functional as F
+from . import ops
+from ._lib import LAYOUT_BDT_AS_DTB
+from .modules import jitter_plan
+from .ops import MASK_FLOAT, MASK_U8
+from .vector_quantizer import VectorQuantizerEMA
+
+_ALIGN = 64  # floats; every parameter starts 256-byte aligned inside the flat buffers
+
+
+class FusedTrainStep(object):
+    """Owns the flat parameter / gradient / optimizer buffers of `model` (a vq_vae_speech_b200 ConvolutionalVQVAE on a
+    CUDA device; its parameters are re-pointed at views of the flat buffer, state_dict() keeps working) and runs training
+    steps for a fixed (batch_size, T) shape."""
+
+    def __init__(self, model, batch_size, num_frames, learning_rate, use_graph=True, process_group=None,
+                 betas=(0.9, 0.999), eps=1e-8):
+        self.model = model
+        self.B, self.T = int(batch_size), int(num_frames)
+        self.lr, self.betas, self.eps = float(learning_rate), betas, float(eps)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.dev = next(model.parameters()).device
+        if self.dev.type != 'cuda':
+            raise RuntimeError('FusedTrainStep needs the model on a CUDA device (no CPU path)')
+        enc, dec, vq = model._encoder, model._decoder, model._vq
+        for m in model.modules():
+            if hasattr(m, 'weight_g'):
+                raise NotImplementedError('weight-normalised convs (use_kaiming_normal) run through the autograd '
+                                          'module path, not the fused step')
+        self.is_ema = isinstance(vq, VectorQuantizerEMA)
+        self.nl = enc._residual_stack._num_residual_layers
+        if self.nl < 1:
+            raise NotImplementedError('num_residual_layers must be >= 1')
+        self.use_jitter = bool(dec._use_jitter)
+        self._flatten_parameters()
+        self._alloc_buffers()
+        self.schedule = []
+        prev = ops.set_recorder(self.schedule)
+        try:
+            self._emit_step()
+        finally:
+            ops.set_recorder(prev)
+        self.n_launch_calls = sum(1 for f, _, _ in self.schedule if f is not None)
+        self.graph = None
+        self.use_graph = bool(use_graph) and self.world == 1
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def _trainable(self):
+        seen, out = set(), []
+        for name, p in self.model.named_parameters():      # named_parameters() de-duplicates the shared Residual
+            if id(p) in seen:
+                continue
+            seen.add(id(p))
+            if self.is_ema and name.startswith('_vq.'):
+                continue       # EMA codebook / ema_w never receive a gradient; Adam skips them
+            out.append((name, p))
+        return out
+
+    def _flatten_parameters(self):
+        params = self._trainable()
+        offs, total = [], 0
+        for _, p in params:
+            offs.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        dev = self.dev
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_vmax = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.opt_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.grads, self.param_names = {}, []
+        first_decoder = None
+        with torch.no_grad():
+            for (name, p), off in zip(params, offs):
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                self.grads[name] = self.flat_g[off:off + p.numel()].view_as(p)
+                self.param_names.append(name)
+                if first_decoder is None and name.startswith('_decoder.'):
+                    first_decoder = off
+        self.bucket_split = first_decoder if first_decoder is not None else total
+        self.n_params = sum(p.numel() for _, p in params)
+
+    def _p(self, name):
+        return dict(self.model.named_parameters())[name].data
+
+    def _alloc_buffers(self):
+        m = self.model
+        B, T, dev = self.B, self.T, self.dev
+        Fi = m._encoder._conv_1.in_channels
+        C = m._encoder._conv_1.out_channels
+        R_enc = m._encoder._residual_stack._layers[0]._block[1].out_channels
+        R_dec = m._decoder._residual_stack._layers[0]._block[1].out_channels
+        D = m._pre_vq_conv.out_channels
+        K = m._vq._num_embeddings
+        Fo = m._decoder._conv_trans_3.out_channels
+        Tq = T // 2 + 1
+        L2 = 2 * Tq
+        self.dims = dict(B=B, T=T, Fi=Fi, C=C, R_enc=R_enc, R_dec=R_dec, D=D, K=K, Fo=Fo, Tq=Tq, L2=L2)
+        if Fo != Fi:
+            raise NotImplementedError('the fused step trains input == target features (MFCC-39 both sides)')
+        if L2 + 3 < T:
+            raise RuntimeError('decoder output shorter than the input')
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        u8 = lambda *s: torch.empty(*s, dtype=torch.uint8, device=dev)
+        b = self.buf = {}
+        b['x_in'] = f(B, T, Fi)                  # the (B, T, F) feature batch as the loader delivers it
+        b['x'] = f(B, Fi, T)
+        b['a1'], b['h2'], b['m2'] = f(B, C, T), f(B, C, T), u8(B, C, T)
+        b['a3'], b['h4'], b['m4'], b['h5'], b['m5'] = f(B, C, Tq), f(B, C, Tq), u8(B, C, Tq), f(B, C, Tq), u8(B, C, Tq)
+        for i in range(self.nl):
+            b['e_hh%d' % i] = f(B, R_enc, Tq)
+            if i > 0:
+                b['e_x%d' % i] = f(B, C, Tq)
+        b['enc_out'], b['m_e'] = f(B, C, Tq), u8(B, C, Tq)
+        b['z'], b['q'], b['qj'] = f(B, D, Tq), f(B, D, Tq), f(B, D, Tq)
+        b['idx'] = torch.empty(B * Tq, dtype=torch.int64, device=dev)
+        b['stats'] = f(K * (D + 1))
+        b['vq_scalars'] = torch.zeros(8, dtype=torch.float32, device=dev)
+        b['jitter_src'] = torch.arange(Tq, dtype=torch.int32, device=dev)
+        b['d1'], b['u'] = f(B, C, Tq), f(B, C, L2)
+        for i in range(self.nl):
+            b['d_hh%d' % i] = f(B, R_dec, L2)
+            if i > 0:
+                b['d_x%d' % i] = f(B, C, L2)
+        b['s'], b['t1'], b['t2'] = f(B, C, L2), f(B, C, L2), f(B, C, L2 + 2)
+        b['recon'], b['g_recon'] = f(B, Fo, T), f(B, Fo, T)
+        b['recon_loss'] = torch.zeros(1, dtype=torch.float32, device=dev)
+        b['one'] = torch.ones(1, dtype=torch.float32, device=dev)
+        # backward scratch: two ping-pong gradient buffers per resolution + hidden-gradient buffers
+        b['gA2'], b['gB2'] = f(B, C, L2 + 2), f(B, C, L2 + 2)
+        b['gH2'] = f(B, max(R_dec, C), L2)
+        b['gA1'], b['gB1'], b['gC1'] = f(B, C, Tq), f(B, C, Tq), f(B, C, Tq)
+        b['gH1'] = f(B, max(R_enc, C), Tq)
+        b['gT_a'], b['gT_b'] = f(B, C, T), f(B, C, T)
+        b['gq'], b['gqj'], b['gz'] = f(B, D, Tq), f(B, D, Tq), f(B, D, Tq)
+        # permuted weights (the (d1, d0, k) arrangement dgrad / transposed-conv forward read as a dense GEMM operand)
+        self.wperm = {}
+        for name in self.param_names:
+            if name.endswith('weight') and not name.startswith('_vq.') and name != '_encoder._conv_1.weight':
+                p = self._p(name)
+                self.wperm[name] = f(p.shape[1], p.shape[0], p.shape[2])
+        ws_bytes = 16
+        for (M, Cr, k, La) in [(C, Fi, 3, T), (C, C, 3, T), (C, C, 4, Tq), (C, C, 3, Tq), (R_enc, C, 3, Tq),
+                               (C, R_enc, 1, Tq), (D, C, 3, Tq), (C, D, 3, Tq), (R_dec, C, 3, L2), (C, R_dec, 1, L2),
+                               (C, C, 3, L2), (C, C, 3, L2), (C, Fo, 2, L2 + 2)]:
+            ws_bytes = max(ws_bytes, ops.wgrad_workspace_bytes(M, Cr, k, B, La))
+        self.ws_wgrad = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self.ws_vq = ops.vq_workspace(K, D, dev)
+        self.ws_mse = ops.mse_workspace(dev)
+        self.host_scalars = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.dev_scalars = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------------------------------------
+    # the step, emitted once through the recorder
+    # ------------------------------------------------------------------------------------------------
+    def _view(self, name, C, L):
+        """(B, C, L) view at the head of a scratch buffer."""
+        return self.buf[name].view(-1)[:self.B * C * L].view(self.B, C, L)
+
+    def _allreduce_stats(self):
+        torch.distributed.all_reduce(self.buf['stats'], group=self.pg)
+
+    def _allreduce_bucket(self, lo, hi):
+        self._works.append(torch.distributed.all_reduce(self.flat_g[lo:hi], group=self.pg, async_op=True))
+
+    def _wait_buckets(self):
+        for w in self._works:
+            w.wait()
+        self._works = []
+
+    def _emit_step(self):
+        m, b, d = self.model, self.buf, self.dims
+        B, T, Tq, L2, C, D, K, Fi, Fo = d['B'], d['T'], d['Tq'], d['L2'], d['C'], d['D'], d['K'], d['Fi'], d['Fo']
+        E, DEC = '_encoder.', '_decoder.'
+        RS1, RS2 = '_residual_stack._layers.0._block.1.weight', '_residual_stack._layers.0._block.3.weight'
+        P, G, WP, ws = self._p, self.grads, self.wperm, self.ws_wgrad
+        nl = self.nl
+        self._works = []
+
+        # ---- 0. weight re-arrangements for this step's dgrad / transposed-conv GEMMs ----
+        for name, out in WP.items():
+            ops.permute_weight(P(name), out)
+
+        # ---- 1. encoder forward (convolutional_encoder.py:118-146) ----
+        ops.blc_to_ncl(b['x_in'], b['x'])                                            # vq_vae.py:118
+        F.conv1d_forward(b['x'], P(E + '_conv_1.weight'), P(E + '_conv_1.bias'), 1, 1, out=b['a1'], relu=True)
+        F.conv1d_forward(b['a1'], P(E + '_conv_2.weight'), P(E + '_conv_2.bias'), 1, 1, out=b['h2'], relu=True,
+                         mask_out=b['m2'], add_post=b['a1'])
+        F.conv1d_forward(b['h2'], P(E + '_conv_3.weight'), P(E + '_conv_3.bias'), 2, 2, out=b['a3'], relu=True)
+        F.conv1d_forward(b['a3'], P(E + '_conv_4.weight'), P(E + '_conv_4.bias'), 1, 1, out=b['h4'], relu=True,
+                         mask_out=b['m4'], add_post=b['a3'])
+        F.conv1d_forward(b['h4'], P(E + '_conv_5.weight'), P(E + '_conv_5.bias'), 1, 1, out=b['h5'], relu=True,
+                         mask_out=b['m5'], add_post=b['h4'])
+        # residual stack: x_{i+1} = relu(x_i) + conv2(relu(conv1(relu(x_i)))), then relu, then + h5 (outer skip)
+        xs = [b['h5']] + [b['e_x%d' % i] for i in range(1, nl)]
+        for i in range(nl):
+            F.conv1d_forward(xs[i], P(E + RS1), None, 1, 1, out=b['e_hh%d' % i], x_relu=True, relu=True)
+            if i + 1 < nl:
+                F.conv1d_forward(b['e_hh%d' % i], P(E + RS2), None, 1, 0, out=xs[i + 1], add_pre=xs[i],
+                                 add_pre_relu=True)
+            else:
+                F.conv1d_forward(b['e_hh%d' % i], P(E + RS2), None, 1, 0, out=b['enc_out'], add_pre=xs[i],
+                                 add_pre_relu=True, relu=True, mask_out=b['m_e'], add_post=b['h5'])
+        F.conv1d_forward(b['enc_out'], P('_pre_vq_conv.weight'), P('_pre_vq_conv.bias'), 1, 1, out=b['z'])
+
+        # ---- 2. VQ bottleneck ----
+        vq = m._vq
+        cb = vq._embedding.weight.data
+        ops.vq_assign(b['z'], cb, LAYOUT_BDT_AS_DTB, self.ws_vq, idx=b['idx'], stats=b['stats'])
+        n_rows_total = B * Tq
+        if self.is_ema:
+            if self.world > 1:
+                ops.record_callable(self._allreduce_stats)
+                n_rows_total = B * Tq * self.world
+            ops.vq_ema_update(vq._ema_cluster_size, vq._ema_w.data, cb, b['stats'], vq._decay, vq._epsilon)
+        beta = float(vq._commitment_cost)
+        ops.vq_quantize(b['z'], b['idx'], cb, LAYOUT_BDT_AS_DTB, self.ws_vq, b['stats'][:K], n_rows_total, beta,
+                        out=b['q'], scalars=b['vq_scalars'])
+
+        # ---- 3. decoder forward (deconvolutional_decoder.py:100-137) ----
+        dec_in = b['q']
+        if self.use_jitter:
+            ops.jitter_fwd(b['q'], b['jitter_src'], b['qj'])
+            dec_in = b['qj']
+        F.conv1d_forward(dec_in, P(DEC + '_conv_1.weight'), P(DEC + '_conv_1.bias'), 1, 1, out=b['d1'])
+        ops.upsample2_fwd(b['d1'], b['u'])
+        xd = [b['u']] + [b['d_x%d' % i] for i in range(1, nl)]
+        for i in range(nl):
+            F.conv1d_forward(xd[i], P(DEC + RS1), None, 1, 1, out=b['d_hh%d' % i], x_relu=True, relu=True)
+            last = i + 1 == nl
+            F.conv1d_forward(b['d_hh%d' % i], P(DEC + RS2), None, 1, 0, out=b['s'] if last else xd[i + 1],
+                             add_pre=xd[i], add_pre_relu=True, relu=last)
+        F.convT1d_forward(b['s'], WP[DEC + '_conv_trans_1.weight'], P(DEC + '_conv_trans_1.bias'), 1, out=b['t1'],
+                          relu=True)
+        F.convT1d_forward(b['t1'], WP[DEC + '_conv_trans_2.weight'], P(DEC + '_conv_trans_2.bias'), 0, out=b['t2'],
+                          relu=True)
+        F.convT1d_forward(b['t2'], WP[DEC + '_conv_trans_3.weight'], P(DEC + '_conv_trans_3.bias'), 0, out_len=T,
+                          out=b['recon'])                                          # trimmed to T (vq_vae.py:133-137)
+
+        # ---- 4. loss (trainer.py:54-56): MSE against the input features, gradient in the same pass ----
+        ops.mse_fwd_bwd(b['recon'], b['x'], (Fi * T, T, 1), 1.0, b['recon_loss'], b['g_recon'], self.ws_mse)
+
+        # ---- 5. decoder backward ----
+        gq2 = self._view('gA2', C, L2 + 2)
+        F.convT1d_wgrad(b['g_recon'], b['t2'], G[DEC + '_conv_trans_3.weight'], 0, ws)
+        ops.bias_grad(b['g_recon'], G[DEC + '_conv_trans_3.bias'])
+        F.convT1d_dgrad(b['g_recon'], P(DEC + '_conv_trans_3.weight'), L2 + 2, 0, out=gq2, mask=b['t2'],
+                        mask_kind=MASK_FLOAT)
+        gq1 = self._view('gB2', C, L2)
+        F.convT1d_wgrad(gq2, b['t1'], G[DEC + '_conv_trans_2.weight'], 0, ws)
+        ops.bias_grad(gq2, G[DEC + '_conv_trans_2.bias'])
+        F.convT1d_dgrad(gq2, P(DEC + '_conv_trans_2.weight'), L2, 0, out=gq1, mask=b['t1'], mask_kind=MASK_FLOAT)
+        g = self._view('gA2', C, L2)
+        F.convT1d_wgrad(gq1, b['s'], G[DEC + '_conv_trans_1.weight'], 1, ws)
+        ops.bias_grad(gq1, G[DEC + '_conv_trans_1.bias'])
+        F.convT1d_dgrad(gq1, P(DEC + '_conv_trans_1.weight'), L2, 1, out=g, mask=b['s'], mask_kind=MASK_FLOAT)
+        other = self._view('gB2', C, L2)
+        R_dec = d['R_dec']
+        gh = self._view('gH2', R_dec, L2)
+        for n, i in enumerate(reversed(range(nl))):
+            acc = n > 0                                      # the shared Residual: second application accumulates
+            F.conv1d_wgrad(g, b['d_hh%d' % i], G[DEC + RS2], 1, 0, ws, accumulate=acc)
+            F.conv1d_dgrad(g, WP[DEC + RS2], L2, 1, 0, out=gh, mask=b['d_hh%d' % i], mask_kind=MASK_FLOAT)
+            F.conv1d_wgrad(gh, xd[i], G[DEC + RS1], 1, 1, ws, x_relu=True, accumulate=acc)
+            F.conv1d_dgrad(gh, WP[DEC + RS1], L2, 1, 1, out=other, add_pre=g, mask=xd[i], mask_kind=MASK_FLOAT)
+            g, other = other, g
+        ops.upsample2_bwd(g, b['gA1'])
+        gd1 = b['gA1']
+        F.conv1d_wgrad(gd1, dec_in, G[DEC + '_conv_1.weight'], 1, 1, ws)
+        ops.bias_grad(gd1, G[DEC + '_conv_1.bias'])
+        gq = b['gq']
+        if self.use_jitter:
+            F.conv1d_dgrad(gd1, WP[DEC + '_conv_1.weight'], Tq, 1, 1, out=b['gqj'])
+            ops.jitter_bwd(b['gqj'], b['jitter_src'], gq)
+        else:
+            F.conv1d_dgrad(gd1, WP[DEC + '_conv_1.weight'], Tq, 1, 1, out=gq)
+        if self.world > 1:       # decoder gradients are complete: start their allreduce under the encoder's backward
+            ops.record_callable(lambda: self._allreduce_bucket(self.bucket_split, self.flat_g.numel()))
+
+        # ---- 6. VQ backward (autograd of ema.py:165-169 / vector_quantizer.py:136-141), upstream d(loss)/d(vq_loss) = 1
+        n_local = B * Tq
+        ops.vq_backward(gq, b['one'], 2.0 * beta / (n_local * D), b['z'], b['idx'], cb, LAYOUT_BDT_AS_DTB, out=b['gz'])
+        if not self.is_ema:
+            ops.vq_grad_codebook(b['stats'], cb, b['one'], 2.0 / (n_local * D), out=G['_vq._embedding.weight'])
+
+        # ---- 7. encoder backward ----
+        gz = b['gz']
+        F.conv1d_wgrad(gz, b['enc_out'], G['_pre_vq_conv.weight'], 1, 1, ws)
+        ops.bias_grad(gz, G['_pre_vq_conv.bias'])
+        ge, g = b['gC1'], b['gA1']
+        F.conv1d_dgrad(gz, WP['_pre_vq_conv.weight'], Tq, 1, 1, out=ge, out2=g, mask2=b['m_e'], mask2_kind=MASK_U8)
+        other = b['gB1']
+        R_enc = d['R_enc']
+        gh = self._view('gH1', R_enc, Tq)
+        gp5 = None
+        for n, i in enumerate(reversed(range(nl))):
+            acc = n > 0
+            F.conv1d_wgrad(g, b['e_hh%d' % i], G[E + RS2], 1, 0, ws, accumulate=acc)
+            F.conv1d_dgrad(g, WP[E + RS2], Tq, 1, 0, out=gh, mask=b['e_hh%d' % i], mask_kind=MASK_FLOAT)
+            F.conv1d_wgrad(gh, xs[i], G[E + RS1], 1, 1, ws, x_relu=True, accumulate=acc)
+            if i > 0:
+                F.conv1d_dgrad(gh, WP[E + RS1], Tq, 1, 1, out=other, add_pre=g, mask=xs[i], mask_kind=MASK_FLOAT)
+                g, other = other, g
+            else:
+                # gh5 = ((g + dgrad) * (h5 > 0)) + ge ; gp5 = gh5 * m5
+                F.conv1d_dgrad(gh, WP[E + RS1], Tq, 1, 1, out=other, add_pre=g, mask=xs[0], mask_kind=MASK_FLOAT,
+                               add_post=ge, out2=g, mask2=b['m5'], mask2_kind=MASK_U8)
+                gh5, gp5 = other, g
+        # conv_5: h5 = relu(p5) + h4
+        F.conv1d_wgrad(gp5, b['h4'], G[E + '_conv_5.weight'], 1, 1, ws)
+        ops.bias_grad(gp5, G[E + '_conv_5.bias'])
+        gh4, gp4 = b['gC1'], self._view('gH1', C, Tq)      # ge (gC1) is dead after gh5 was formed
+        F.conv1d_dgrad(gp5, WP[E + '_conv_5.weight'], Tq, 1, 1, out=gh4, add_pre=gh5, out2=gp4, mask2=b['m4'],
+                       mask2_kind=MASK_U8)
+        # conv_4: h4 = relu(p4) + a3 ; then a3 = relu(p3)
+        F.conv1d_wgrad(gp4, b['a3'], G[E + '_conv_4.weight'], 1, 1, ws)
+        ops.bias_grad(gp4, G[E + '_conv_4.bias'])
+        gp3 = b['gA1']
+        F.conv1d_dgrad(gp4, WP[E + '_conv_4.weight'], Tq, 1, 1, out=gp3, add_pre=gh4, mask=b['a3'],
+                       mask_kind=MASK_FLOAT)
+        # conv_3 (k4 s2 p2): a3 = relu(conv3(h2))
+        F.conv1d_wgrad(gp3, b['h2'], G[E + '_conv_3.weight'], 2, 2, ws)
+        ops.bias_grad(gp3, G[E + '_conv_3.bias'])
+        gh2, gp2 = b['gT_a'], b['gT_b']
+        F.conv1d_dgrad(gp3, WP[E + '_conv_3.weight'], T, 2, 2, out=gh2, out2=gp2, mask2=b['m2'], mask2_kind=MASK_U8)
+        # conv_2: h2 = relu(p2) + a1 ; a1 = relu(p1)
+        F.conv1d_wgrad(gp2, b['a1'], G[E + '_conv_2.weight'], 1, 1, ws)
+        ops.bias_grad(gp2, G[E + '_conv_2.bias'])
+        gp1 = self._view('gA2', C, T)
+        F.conv1d_dgrad(gp2, WP[E + '_conv_2.weight'], T, 1, 1, out=gp1, add_pre=gh2, mask=b['a1'],
+                       mask_kind=MASK_FLOAT)
+        F.conv1d_wgrad(gp1, b['x'], G[E + '_conv_1.weight'], 1, 1, ws)
+        ops.bias_grad(gp1, G[E + '_conv_1.bias'])
+
+        # ---- 8. gradient allreduce (average) + fused AMSGrad over the flat buffers (trainer.py:41-42,68) ----
+        g_scale = 1.0
+        if self.world > 1:
+            ops.record_callable(lambda: self._allreduce_bucket(0, self.bucket_split))
+            ops.record_callable(self._wait_buckets)
+            g_scale = 1.0 / self.world
+        ops.amsgrad_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, self.opt_step, self.lr,
+                         self.betas[0], self.betas[1], self.eps, g_scale=g_scale)
+
+    # ------------------------------------------------------------------------------------------------
+    def _run_schedule(self):
+        ops.replay(self.schedule)
+
+    def load_batch(self, x_btf, non_blocking=True):
+        """Stages one (B, T, F) feature batch (host pinned or device tensor) into the static input buffer."""
+        self.buf['x_in'].copy_(x_btf, non_blocking=non_blocking)
+
+    def set_jitter_plan(self, src):
+        self.buf['jitter_src'].copy_(torch.as_tensor(np.asarray(src, dtype=np.int32)), non_blocking=True)
+
+    def step(self, x_btf=None):
+        """One training step on the batch currently staged (or on x_btf).  Returns nothing; `losses()` reads results."""
+        if x_btf is not None:
+            self.load_batch(x_btf)
+        if self.use_jitter:
+            self.last_plan = jitter_plan(self.dims['Tq'], self.model._decoder._jitter._probability)
+            self.set_jitter_plan(self.last_plan)
+        if not self.use_graph or self.steps_done == 0:
+            self._run_schedule()       # the first step always runs launch by launch (loads every kernel before capture)
+        else:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        self.steps_done += 1
+
+    def _capture(self):
+        """Captures the recorded schedule into one CUDA graph.  The schedule is pure (no host sync, no allocation), and
+        all state it touches lives in static buffers, so the capture pass itself performs no work."""
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            self._run_schedule()
+        self.graph = g
+
+    def losses(self):
+        """{'loss', 'reconstruction_loss', 'vq_loss', 'perplexity'} of the last step: one packed 16-byte D2H copy + sync
+        (the reference does three .item() syncs per step, trainer.py:57,58,70)."""
+        sc = self.buf['vq_scalars']
+        self.dev_scalars[0:1].copy_(self.buf['recon_loss'])
+        self.dev_scalars[1:2].copy_(sc[3:4] if self.is_ema else sc[4:5])
+        self.dev_scalars[2:3].copy_(sc[2:3])
+        self.host_scalars.copy_(self.dev_scalars, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        r, v, p = (float(self.host_scalars[i]) for i in range(3))
+        return {'loss': r + v, 'reconstruction_loss': r, 'vq_loss': v, 'perplexity': p}
+
+    def encoding_indices(self):
+        return self.buf['idx'].view(-1, 1)
+
+    def gradients(self):
+        """name -> gradient view (valid after a step; world>1: already summed over ranks, not yet divided)."""
+        return dict(self.grads)
+
+
+def reference_config(**over):
+    """The hot-path keys of configurations/vctk_features.yaml (:36-85) with the vq44-mfcc39 experiment's values."""
+    cfg = dict(output_features_filters=13, augment_output_features=True, output_features_dim=47, verbose=False,
+               input_features_dim=47, num_hiddens=768, num_residual_layers=2, use_kaiming_normal=False,
+               input_features_type='mfcc', input_features_filters=13, augment_input_features=True,
+               sampling_rate=16000, embedding_dim=64, decay=0.0, num_embeddings=44, commitment_cost=0.25,
+               residual_channels=768, use_jitter=False, jitter_probability=0.12, use_speaker_conditioning=False,
+               record_codebook_stats=False, learning_rate=2e-4, batch_size=2)
+    cfg.update(over)
+    return cfg
