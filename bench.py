@@ -37,6 +37,8 @@ def parse():
     ap.add_argument('--frames', type=int, default=47, help='MFCC frames per utterance (length 7680 -> 47)')
     ap.add_argument('--decay', type=float, default=0.99)
     ap.add_argument('--codes', type=int, default=44)
+    ap.add_argument('--precision', default='3xtf32', choices=['fp32', '3xtf32', 'tf32'],
+                    help='GEMM engine of the conv GEMMs: 3xtf32 = tcgen05 with the fp32-accurate split (1e-5 parity)')
     ap.add_argument('--vq-rows', type=int, default=1 << 22)
     ap.add_argument('--skip-vq', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
@@ -175,7 +177,7 @@ def workload_config(args, world, batch_override=None):
     return {'workload': 'vq44-mfcc39 full training step (encoder + VectorQuantizerEMA %dx64 + decoder, MSE + vq_loss, '
                         'AMSGrad lr 2e-4), synthetic MFCC-39, T=%d' % (args.codes, args.frames),
             'per_gpu_batch': b, 'global_batch': b * world, 'frames': args.frames, 'decay': args.decay,
-            'parallelism': 'dp%d' % world,
+            'parallelism': 'dp%d' % world, 'gemm_engine': getattr(args, 'precision', None),
             'l2': 'no explicit flush: every step streams weights + optimizer state + activations >> 126 MB L2'}
 
 
@@ -270,7 +272,7 @@ def run_b200(args):
     torch.manual_seed(1234)                 # same weights on every rank (replicated model)
     model = ConvolutionalVQVAE(cfg, dev).to(dev).train()
     B, T = args.batch, args.frames
-    eng = FusedTrainStep(model, B, T, cfg['learning_rate'])
+    eng = FusedTrainStep(model, B, T, cfg['learning_rate'], precision=args.precision)
     gen = torch.Generator().manual_seed(1234 + rank)        # each rank trains on its own shard of the global batch
     host = [torch.randn(B, T, 39, generator=gen).pin_memory() for _ in range(8)]
     devb = [h.to(dev) for h in host]
@@ -328,7 +330,9 @@ def run_b200(args):
                 'frac': achieved / pk['tensor'], 'traffic': None, 'peak_source': pk['src'] + ' bf16 sustained',
                 'launches_per_step': dn // args.steps, 'avg_launch_ms': dms / dn,
                 'share_of_step_kernel_time': dms / kern_ms,
-                'note': 'exact-fp32 CUDA-core implicit GEMM (1e-5 parity mode); FLOPs = 2*M*Cred*k*B*L per launch'}
+                'note': {'fp32': 'exact-fp32 CUDA-core implicit GEMM', '3xtf32': 'tcgen05 kind::tf32, 3 MMAs per product '
+                         '(fp32-accurate split, 1e-5 parity)', 'tf32': 'tcgen05 kind::tf32 single pass'}[args.precision]
+                + '; achieved counts ALGORITHMIC FLOPs = 2*M*Cred*k*B*L per launch (the split\'s extra MMAs are not counted)'}
     breakdown = dict((k, {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[2] // args.steps,
                           'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[1] else None}) for k, v in fam.items())
 

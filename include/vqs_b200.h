@@ -105,6 +105,15 @@ int vqs_vq_grad_codebook(const float* stats, const float* codebook, const float*
 /* ------------------------------------------------------------------------------------------------ */
 /* Conv1d / ConvTranspose1d as implicit GEMM                                                        */
 /* ------------------------------------------------------------------------------------------------ */
+/* GEMM engines.  FP32: exact-fp32 FMA on CUDA cores.  TF32 / TF32X3: tcgen05 tensor cores with TMEM accumulators --
+ * single-pass TF32 (what cuDNN does by default for the reference's convs on a GPU) or the 3xTF32 split
+ * (x = hi + lo, acc += Al*Bh + Ah*Bl + Ah*Bh, fp32-accurate: same 1e-5 parity bar as FP32).  Shapes the tensor-core
+ * kernels do not cover (conv-like GEMM: A not tap-major, Cred % 32 != 0 or rows not 16-byte aligned; wgrad: reduction
+ * shorter than 32) silently use FP32. */
+#define VQS_PREC_FP32 0
+#define VQS_PREC_TF32 1
+#define VQS_PREC_TF32X3 2
+
 /* One descriptor covers nn.Conv1d forward, its dgrad, nn.ConvTranspose1d (stride 1) forward and its dgrad:
  *
  *   acc[b, m, l] = sum_{c < Cred, j < ksz} A[m, c*ksz + j] * X'[b, c, p(l, j)]
@@ -113,7 +122,8 @@ int vqs_vq_grad_codebook(const float* stats, const float* codebook, const float*
  *
  * A is a row-major (M, Cred*ksz) matrix: the nn.Conv1d weight (Cout, Cin, k) as is for a forward conv and
  * the nn.ConvTranspose1d weight (Cin, Cout, k) as is for its dgrad; vqs_permute_weight produces the
- * (d1, d0, k) arrangement the other two cases need.
+ * (d1, d0, k) arrangement the other two cases need.  With a_tap_major != 0, A is instead (M, ksz, Cred) -- reduction
+ * index j*Cred + c -- the arrangement the tensor-core engines require (vqs_permute_weight modes 1 and 2).
  *
  * Epilogue, per output element (b, m, l), out tensors are NCL (B, M, Lout):
  *   v = acc + bias[m]                       (bias may be NULL)
@@ -127,6 +137,7 @@ int vqs_vq_grad_codebook(const float* stats, const float* codebook, const float*
 typedef struct vqs_conv_gemm_desc {
   const float* A;
   const float* X;
+  int a_tap_major;
   int M, Cred, ksz;
   int B, Lin, Lout;
   long long x_sb, x_sc, x_sl;
@@ -144,6 +155,7 @@ typedef struct vqs_conv_gemm_desc {
   float* out2;
   const void* mask2;
   int mask2_kind;
+  int precision; /* VQS_PREC_* : which GEMM engine computes acc */
 } vqs_conv_gemm_desc;
 
 int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream);
@@ -164,6 +176,7 @@ typedef struct vqs_wgrad_desc {
   int x_relu;
   float* dW;
   int accumulate;
+  int precision; /* VQS_PREC_* */
 } vqs_wgrad_desc;
 
 size_t vqs_wgrad_workspace_bytes(int M, int Cred, int ksz, int B, int La);
@@ -172,8 +185,11 @@ int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t workspace_by
 /* db[m] (+)= sum_{b, l} g[b, m, l]   (g NCL (B, M, L)). */
 int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int accumulate, vqs_stream_t stream);
 
-/* out[d1][d0][k] = w[d0][d1][k]  (swap the two channel dims of a conv weight). */
-int vqs_permute_weight(const float* w, int d0, int d1, int k, float* out, vqs_stream_t stream);
+/* Re-arrangements of a conv weight w[d0][d1][k]:
+ *   mode 0: out[d1][d0][k]   (swap the channel dims)
+ *   mode 1: out[d0][k][d1]   (tap-major, same orientation)
+ *   mode 2: out[d1][k][d0]   (tap-major, channel dims swapped) */
+int vqs_permute_weight(const float* w, int d0, int d1, int k, int mode, float* out, vqs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* element-wise pieces of the path                                                                  */

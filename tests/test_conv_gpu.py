@@ -9,6 +9,17 @@ from oracle import model_oracle as mo
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
+# GEMM engines: exact-fp32 CUDA cores, tcgen05 3xTF32 (same 1e-5 bar), tcgen05 single-pass TF32 (stated tolerance: the
+# 10-bit TF32 mantissa gives ~5e-4 relative error per product; 3e-3 of the output scale bounds the accumulated error)
+PRECS = [('fp32', 1e-5), ('3xtf32', 1e-5), ('tf32', 3e-3)]
+
+
+@pytest.fixture(params=PRECS, ids=[p[0] for p in PRECS])
+def prec(request):
+    from vq_vae_speech_b200 import ops
+    prev = ops.set_precision(request.param[0])
+    yield request.param
+    ops.set_precision(prev)
 
 
 def _dev():
@@ -24,13 +35,14 @@ def _t(a, dev, dtype=np.float32):
 CONV_CASES = [  # (B, Cin, Cout, L, k, stride, pad)
     (2, 39, 48, 47, 3, 1, 1), (2, 48, 48, 47, 4, 2, 2), (3, 48, 64, 24, 3, 1, 1), (2, 96, 80, 24, 1, 1, 0),
     (5, 64, 768, 24, 3, 1, 1), (64, 768, 768, 24, 3, 1, 1), (16, 768, 64, 96, 3, 1, 1), (2, 7, 2, 9, 3, 1, 1),
-    (4, 130, 200, 47, 4, 2, 2), (1, 768, 768, 5, 3, 1, 1),
+    (4, 130, 200, 47, 4, 2, 2), (1, 768, 768, 5, 3, 1, 1), (3, 64, 96, 47, 4, 2, 2), (9, 256, 160, 31, 2, 1, 0),
 ]
 
 
 @pytest.mark.parametrize('B,Cin,Cout,L,k,stride,pad', CONV_CASES)
-def test_conv1d_fwd_dgrad_wgrad(B, Cin, Cout, L, k, stride, pad):
+def test_conv1d_fwd_dgrad_wgrad(B, Cin, Cout, L, k, stride, pad, prec):
     dev = _dev()
+    TOL = prec[1]
     from vq_vae_speech_b200 import functional as F, ops
     rng = np.random.RandomState(B * 31 + Cin)
     x = rng.randn(B, Cin, L)
@@ -38,12 +50,14 @@ def test_conv1d_fwd_dgrad_wgrad(B, Cin, Cout, L, k, stride, pad):
     b = rng.randn(Cout)
     y_o = mo.conv1d_fwd(x, w, b, stride, pad)
     xd, wd, bd = _t(x, dev), _t(w, dev), _t(b, dev)
-    y = F.conv1d_forward(xd, wd, bd, stride, pad)
+    A, tap = F.gemm_weight(wd, 'conv_fwd')      # tap-major (Cout, k, Cin) for the tensor-core engines when Cin % 32 == 0
+    y = F.conv1d_forward(xd, A, bd, stride, pad, tap=tap)
     assert tuple(y.shape) == y_o.shape
     assert rel_err(y.cpu().numpy(), y_o) < TOL
     gy = rng.randn(*y_o.shape)
     gyd = _t(gy, dev)
-    dx = F.conv1d_dgrad(gyd, ops.permute_weight(wd), L, stride, pad)
+    A, tap = F.gemm_weight(wd, 'conv_dgrad')
+    dx = F.conv1d_dgrad(gyd, A, L, stride, pad, tap=tap)
     assert rel_err(dx.cpu().numpy(), mo.conv1d_dgrad(gy, w, L, stride, pad)) < TOL
     dW = torch.empty_like(wd)
     F.conv1d_wgrad(gyd, xd, dW, stride, pad, F._wgrad_ws(Cout, Cin, k, B, y.shape[2], dev))
@@ -62,8 +76,9 @@ CONVT_CASES = [  # (B, Cin, Cout, L, k, pad)
 
 
 @pytest.mark.parametrize('B,Cin,Cout,L,k,pad', CONVT_CASES)
-def test_conv_transpose1d_fwd_dgrad_wgrad(B, Cin, Cout, L, k, pad):
+def test_conv_transpose1d_fwd_dgrad_wgrad(B, Cin, Cout, L, k, pad, prec):
     dev = _dev()
+    TOL = prec[1]
     from vq_vae_speech_b200 import functional as F, ops
     rng = np.random.RandomState(B * 17 + Cout)
     x = rng.randn(B, Cin, L)
@@ -71,19 +86,21 @@ def test_conv_transpose1d_fwd_dgrad_wgrad(B, Cin, Cout, L, k, pad):
     b = rng.randn(Cout)
     y_o = mo.convT1d_fwd(x, w, b, pad)
     xd, wd, bd = _t(x, dev), _t(w, dev), _t(b, dev)
-    y = F.convT1d_forward(xd, ops.permute_weight(wd), bd, pad)
+    A, tap = F.gemm_weight(wd, 'convT_fwd')
+    y = F.convT1d_forward(xd, A, bd, pad, tap=tap)
     assert tuple(y.shape) == y_o.shape
     assert rel_err(y.cpu().numpy(), y_o) < TOL
     # trimmed output (convolutional_vq_vae.py:133-137 drops the tail): only the first `keep` positions are computed,
     # and the backward sees zero gradient beyond them
     keep = y_o.shape[2] - 3
-    yt = F.convT1d_forward(xd, ops.permute_weight(wd), bd, pad, out_len=keep)
+    yt = F.convT1d_forward(xd, A, bd, pad, out_len=keep, tap=tap)
     assert rel_err(yt.cpu().numpy(), y_o[:, :, :keep]) < TOL
     gy = rng.randn(B, Cout, keep)
     gfull = np.zeros_like(y_o)
     gfull[:, :, :keep] = gy
     gyd = _t(gy, dev)
-    dx = F.convT1d_dgrad(gyd, wd, L, pad)
+    A, tap = F.gemm_weight(wd, 'convT_dgrad')
+    dx = F.convT1d_dgrad(gyd, A, L, pad, tap=tap)
     assert rel_err(dx.cpu().numpy(), mo.convT1d_dgrad(gfull, w, L, pad)) < TOL
     dW = torch.empty_like(wd)
     F.convT1d_wgrad(gyd, xd, dW, pad, F._wgrad_ws(Cin, Cout, k, B, L, dev))
@@ -92,11 +109,12 @@ def test_conv_transpose1d_fwd_dgrad_wgrad(B, Cin, Cout, L, k, pad):
     assert rel_err(ops.bias_grad(gyd, torch.empty(Cout, device=dev)).cpu().numpy(), db_o) < TOL
 
 
-def test_fused_epilogue_and_strided_input():
+def test_fused_epilogue_and_strided_input(prec):
     dev = _dev()
+    TOL = prec[1]
     from vq_vae_speech_b200 import functional as F, ops
     rng = np.random.RandomState(0)
-    B, Cin, Cout, L = 3, 39, 48, 47
+    B, Cin, Cout, L = 3, 39, 64, 47
     x_blc = rng.randn(B, L, Cin)                      # (B, T, F) feature batch, read through strides (no permute copy)
     w = rng.randn(Cout, Cin, 3) / 10
     b = rng.randn(Cout)
@@ -117,7 +135,8 @@ def test_fused_epilogue_and_strided_input():
     w2 = rng.randn(Cout, Cout, 3) / 10
     act = rng.randn(B, Cout, L)
     out2 = torch.empty(B, Cout, L, device=dev)
-    y2 = F.conv1d_forward(_t(x, dev), _t(w2, dev), None, 1, 1, x_relu=True, mask=_t(act, dev), mask_kind=ops.MASK_FLOAT,
+    A2, tap2 = F.gemm_weight(_t(w2, dev), 'conv_fwd')
+    y2 = F.conv1d_forward(_t(x, dev), A2, None, 1, 1, tap=tap2, x_relu=True, mask=_t(act, dev), mask_kind=ops.MASK_FLOAT,
                           add_post=_t(res, dev), out2=out2, mask2=mask_out, mask2_kind=ops.MASK_U8)
     v = mo.conv1d_fwd(np.maximum(x, 0), w2, None, 1, 1) * (act > 0) + res
     assert rel_err(y2.cpu().numpy(), v) < TOL
@@ -143,6 +162,8 @@ def test_elementwise_ops():
     assert np.array_equal(ops.blc_to_ncl(xd).cpu().numpy(), x.transpose(0, 2, 1).astype(np.float32))
     w = rng.randn(5, 7, 3)
     assert np.array_equal(ops.permute_weight(_t(w, dev)).cpu().numpy(), w.transpose(1, 0, 2).astype(np.float32))
+    assert np.array_equal(ops.permute_weight(_t(w, dev), mode=1).cpu().numpy(), w.transpose(0, 2, 1).astype(np.float32))
+    assert np.array_equal(ops.permute_weight(_t(w, dev), mode=2).cpu().numpy(), w.transpose(1, 2, 0).astype(np.float32))
     # MSE forward + backward against a strided (B, T, F) target
     recon = rng.randn(3, 13, 24)
     tgt_btf = rng.randn(3, 24, 13)

@@ -11,12 +11,14 @@ LIB_PATH = os.path.join(HERE, 'csrc', 'libvqs_b200.so')
 
 LAYOUT_FLAT_ND = 0
 LAYOUT_BDT_AS_DTB = 1
+PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, '3xtf32': PREC_TF32X3}
 
 
 class ConvGemmDesc(Structure):
     """struct vqs_conv_gemm_desc (include/vqs_b200.h)."""
     _fields_ = [
-        ('A', c_void_p), ('X', c_void_p),
+        ('A', c_void_p), ('X', c_void_p), ('a_tap_major', c_int),
         ('M', c_int), ('Cred', c_int), ('ksz', c_int),
         ('B', c_int), ('Lin', c_int), ('Lout', c_int),
         ('x_sb', c_longlong), ('x_sc', c_longlong), ('x_sl', c_longlong),
@@ -25,6 +27,7 @@ class ConvGemmDesc(Structure):
         ('bias', c_void_p), ('add_pre', c_void_p), ('add_pre_relu', c_int), ('relu', c_int),
         ('mask_out', c_void_p), ('mask', c_void_p), ('mask_kind', c_int),
         ('add_post', c_void_p), ('out', c_void_p), ('out2', c_void_p), ('mask2', c_void_p), ('mask2_kind', c_int),
+        ('precision', c_int),
     ]
 
 
@@ -36,7 +39,7 @@ class WgradDesc(Structure):
         ('B', c_int), ('La', c_int), ('Lx', c_int),
         ('l_mul', c_int), ('j_mul', c_int), ('off', c_int),
         ('x_relu', c_int),
-        ('dW', c_void_p), ('accumulate', c_int),
+        ('dW', c_void_p), ('accumulate', c_int), ('precision', c_int),
     ]
 
 
@@ -60,7 +63,7 @@ PROTOTYPES = {
     'vqs_wgrad_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     'vqs_wgrad_gemm': (c_int, [POINTER(WgradDesc), c_void_p, c_size_t, c_void_p]),
     'vqs_bias_grad': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
-    'vqs_permute_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'vqs_permute_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'vqs_upsample2_fwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     'vqs_upsample2_bwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     'vqs_jitter_fwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p]),

@@ -8,6 +8,7 @@
 // activation tensor (padding, stride, transposed-conv tap flip, nearest-neighbour index and input ReLU are all index
 // arithmetic in the loader), so no im2col buffer ever exists in HBM.
 #include "vqs_common.cuh"
+#include "gemm_params.cuh"
 
 namespace vqs {
 namespace {
@@ -50,13 +51,6 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ As, const
 // ------------------------------------------------------------------------------------------------
 // conv-like GEMM (forward conv, dgrad, transposed conv forward, transposed conv dgrad)
 // ------------------------------------------------------------------------------------------------
-struct ConvParams {
-  vqs_conv_gemm_desc d;
-  int Ktot, Ntot;
-  int a_vec;  // A rows are 16-byte aligned and Ktot % 4 == 0
-  FastDiv divL;
-};
-
 __device__ __forceinline__ bool mask_on(const void* m, int kind, size_t i) {
   if (kind == 1) return reinterpret_cast<const float*>(m)[i] > 0.f;
   return reinterpret_cast<const unsigned char*>(m)[i] != 0;
@@ -114,7 +108,15 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const ConvParams p)
 #pragma unroll
     for (int i = 0; i < B_LD; ++i) {
       int kk = k0 + brow0 + B_STEP * i;
-      int c = kk / KSZ, j = kk - c * KSZ;
+      int c, j;
+      if (d.a_tap_major) {   // kk = j*Cred + c
+        uint32_t jj = p.divCred.div((uint32_t)kk);
+        j = (int)jj;
+        c = kk - j * d.Cred;
+      } else {               // kk = c*ksz + j
+        c = kk / KSZ;
+        j = kk - c * KSZ;
+      }
       int pn = lbase + j * d.j_mul;
       bool ok = n_ok && kk < Ktot && pn >= 0;
       if (d.l_div == 2) {
@@ -214,13 +216,6 @@ int launch_conv(const ConvParams& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // wgrad GEMM: dW[m, (c, j)] = sum_{(b, l)} Aact[b, m, l] * X'[b, c, l*l_mul + j*j_mul + off]
 // ------------------------------------------------------------------------------------------------
-struct WgradParams {
-  vqs_wgrad_desc d;
-  int Nw, Kred, splits, kt_per_split;
-  float* partial;  // [splits][M*Nw] or NULL (direct)
-  FastDiv divLa;
-};
-
 template <int BM, int BN, int KSZ>
 __global__ void __launch_bounds__(NTHREADS) wgrad_gemm_kernel(const WgradParams p) {
   using C = TileCfg<BM, BN>;
@@ -342,13 +337,14 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
 struct WgradPlan {
   int bm, bn, splits, kt_per_split;
 };
-WgradPlan plan_wgrad(int M, int Nw, int Kred) {
+// bk = reduction elements per k-tile of the engine (16: CUDA cores, 32: tcgen05); tc tiles are always 128 x 128
+WgradPlan plan_wgrad(int M, int Nw, int Kred, int bk = BK, bool tc = false) {
   WgradPlan pl;
-  pl.bm = (M > 64) ? 128 : 64;
-  pl.bn = (Nw > 64) ? 128 : 64;
+  pl.bm = (tc || M > 64) ? 128 : 64;
+  pl.bn = (tc || Nw > 64) ? 128 : 64;
   long long tiles = (long long)((M + pl.bm - 1) / pl.bm) * ((Nw + pl.bn - 1) / pl.bn);
-  int ktiles = (Kred + BK - 1) / BK;
-  long long want = (2ll * num_sms() + tiles - 1) / tiles;
+  int ktiles = (Kred + bk - 1) / bk;
+  long long want = ((tc ? 3ll : 2ll) * num_sms() + tiles - 1) / tiles;
   int max_s = ktiles / 4 > 0 ? ktiles / 4 : 1;
   int s = (int)(want < 1 ? 1 : want);
   if (s > max_s) s = max_s;
@@ -378,14 +374,27 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
   if (threadIdx.x == 0) db[m] = accumulate ? db[m] + red[0] : red[0];
 }
 
-__global__ void permute_weight_kernel(const float* __restrict__ w, int d0, int d1, int k, float* __restrict__ out) {
+__global__ void permute_weight_kernel(const float* __restrict__ w, int d0, int d1, int k, int mode,
+                                      float* __restrict__ out) {
   const long long n = (long long)d0 * d1 * k;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    // i indexes out[b][a][j]
-    int j = (int)(i % k);
-    long long t = i / k;
-    int a = (int)(t % d0);
-    int b = (int)(t / d0);
+    int a, b, j;  // source element w[a][b][j]
+    if (mode == 0) {          // i indexes out[b][a][j]
+      j = (int)(i % k);
+      long long t = i / k;
+      a = (int)(t % d0);
+      b = (int)(t / d0);
+    } else if (mode == 1) {   // i indexes out[a][j][b]
+      b = (int)(i % d1);
+      long long t = i / d1;
+      j = (int)(t % k);
+      a = (int)(t / k);
+    } else {                  // i indexes out[b][j][a]
+      a = (int)(i % d0);
+      long long t = i / d0;
+      j = (int)(t % k);
+      b = (int)(t / k);
+    }
     out[i] = w[((size_t)a * d1 + b) * k + j];
   }
 }
@@ -409,7 +418,11 @@ extern "C" int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream) {
   p.Ntot = d->B * d->Lout;
   p.a_vec = (p.Ktot % 4 == 0) && ((reinterpret_cast<uintptr_t>(d->A) & 15) == 0);
   p.divL = FastDiv((uint32_t)d->Lout);
+  p.cpb = d->Cred / 32 > 0 ? d->Cred / 32 : 1;
+  p.divCpb = FastDiv((uint32_t)p.cpb);
+  p.divCred = FastDiv((uint32_t)d->Cred);
   cudaStream_t st = (cudaStream_t)stream;
+  if (d->precision != VQS_PREC_FP32 && conv_tc_supported(p)) return launch_conv_tc(p, d->precision, st);
   // tile choice: big tiles once they fill the machine, small tiles otherwise
   long long big = (long long)((d->M + 127) / 128) * ((p.Ntot + 127) / 128);
   if (d->M > 64 && p.Ntot > 64 && big >= num_sms()) return launch_conv<128, 128>(p, st);
@@ -420,7 +433,9 @@ extern "C" int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream) {
 extern "C" size_t vqs_wgrad_workspace_bytes(int M, int Cred, int ksz, int B, int La) {
   if (M <= 0 || Cred <= 0 || ksz <= 0 || B <= 0 || La <= 0) return 0;
   WgradPlan pl = plan_wgrad(M, Cred * ksz, B * La);
-  return pl.splits > 1 ? (size_t)pl.splits * M * Cred * ksz * sizeof(float) : 0;
+  WgradPlan pt = plan_wgrad(M, Cred * ksz, B * La, 32, true);
+  int s = pl.splits > pt.splits ? pl.splits : pt.splits;
+  return s > 1 ? (size_t)s * M * Cred * ksz * sizeof(float) : 0;
 }
 
 extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t workspace_bytes, vqs_stream_t stream) {
@@ -432,7 +447,8 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
   p.d = *d;
   p.Nw = d->Cred * d->ksz;
   p.Kred = d->B * d->La;
-  WgradPlan pl = plan_wgrad(d->M, p.Nw, p.Kred);
+  const bool tc = d->precision != VQS_PREC_FP32 && wgrad_tc_supported(p);
+  WgradPlan pl = tc ? plan_wgrad(d->M, p.Nw, p.Kred, 32, true) : plan_wgrad(d->M, p.Nw, p.Kred);
   p.splits = pl.splits;
   p.kt_per_split = pl.kt_per_split;
   p.divLa = FastDiv((uint32_t)d->La);
@@ -444,7 +460,8 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
   p.partial = pl.splits > 1 ? (float*)workspace : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   int e;
-  if (pl.bm == 128 && pl.bn == 128) e = launch_wgrad<128, 128>(p, st);
+  if (tc) e = launch_wgrad_tc(p, d->precision, st);
+  else if (pl.bm == 128 && pl.bn == 128) e = launch_wgrad<128, 128>(p, st);
   else if (pl.bm == 128) e = launch_wgrad<128, 64>(p, st);
   else if (pl.bn == 128) e = launch_wgrad<64, 128>(p, st);
   else e = launch_wgrad<64, 64>(p, st);
@@ -466,12 +483,12 @@ extern "C" int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int
   return 0;
 }
 
-extern "C" int vqs_permute_weight(const float* w, int d0, int d1, int k, float* out, vqs_stream_t stream) {
-  VQS_CHECK_ARG(w && out && d0 > 0 && d1 > 0 && k > 0, "vqs_permute_weight: bad arguments");
+extern "C" int vqs_permute_weight(const float* w, int d0, int d1, int k, int mode, float* out, vqs_stream_t stream) {
+  VQS_CHECK_ARG(w && out && d0 > 0 && d1 > 0 && k > 0 && mode >= 0 && mode <= 2, "vqs_permute_weight: bad arguments");
   long long n = (long long)d0 * d1 * k;
   long long blocks = (n + 255) / 256;
   permute_weight_kernel<<<(int)(blocks < 8 * num_sms() ? blocks : 8 * num_sms()), 256, 0, (cudaStream_t)stream>>>(
-      w, d0, d1, k, out);
+      w, d0, d1, k, mode, out);
   VQS_LAUNCH_CHECK();
   return 0;
 }

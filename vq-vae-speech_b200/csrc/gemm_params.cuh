@@ -1,0 +1,29 @@
+// Parameter blocks shared by the CUDA-core (conv_kernels.cu) and tcgen05 (gemm_tc.cu) implicit-GEMM kernels.
+#pragma once
+#include "vqs_common.cuh"
+
+namespace vqs {
+
+struct ConvParams {
+  vqs_conv_gemm_desc d;
+  int Ktot, Ntot;
+  int a_vec;  // A rows are 16-byte aligned and Ktot % 4 == 0
+  int cpb;    // 32-wide k-blocks per tap (tap-major A): Cred / 32
+  FastDiv divL, divCpb, divCred;
+};
+
+struct WgradParams {
+  vqs_wgrad_desc d;
+  int Nw, Kred, splits, kt_per_split;
+  float* partial;  // [splits][M*Nw] or NULL (direct)
+  FastDiv divLa;
+};
+
+
+// tcgen05 launchers (gemm_tc.cu).  precision: 1 = single-pass TF32, 2 = 3xTF32 (fp32-accurate split).
+int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st);
+int launch_wgrad_tc(const WgradParams& p, int precision, cudaStream_t st);
+bool conv_tc_supported(const ConvParams& p);
+bool wgrad_tc_supported(const WgradParams& p);
+
+}  // namespace vqs

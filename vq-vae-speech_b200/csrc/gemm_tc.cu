@@ -1,0 +1,588 @@
+// tcgen05 (5th-generation tensor core) implicit-GEMM kernels for the conv / wgrad GEMMs of the training step.
+//
+//   D[128 x BN] (fp32, TMEM) += A[128 x 32] (smem, K-major, 128B swizzle) * B[BN x 32]^T (smem, K-major, 128B swizzle)
+//
+// kind::tf32 MMAs issued by one thread, accumulators in tensor memory, operands produced by 8 "producer" warps that gather
+// the implicit-GEMM operands straight from the NCL activation / weight tensors (padding, stride, tap flip, input ReLU are
+// index arithmetic, exactly as in the CUDA-core kernels) and write them into the UMMA canonical shared-memory layout.
+// Two precisions:
+//   1  single-pass TF32: operands are used as stored (the tensor core reads the top 19 bits) -- what cuDNN does by default
+//      for the reference's convs on a GPU (torch.backends.cudnn.allow_tf32 = True);
+//   2  3xTF32: every operand is split x = hi + lo (hi = top 19 bits, lo = x - hi exactly), D += Al*Bh + Ah*Bl + Ah*Bh.
+//      Dropped terms are <= 2^-21 relative, accumulation is fp32 -> meets the 1e-5 parity bar of the exact-fp32 path
+//      while running on the tensor pipe.  fp32 operands cost 4 B per element, so one 128x128 tile needs 1 KB of operands per
+//      k: at ~42 B/clk/SM of L2 bandwidth the single-pass variant is operand-bandwidth-bound at about a third of the TF32
+//      peak and the three MMAs of the split ride in that shadow -- the exact mode is (almost) free.
+//      The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of accumulation
+//      steps (measured: 1.8e-5 relative after 864 MMAs into one accumulator).  Mode 2 therefore spreads the main term
+//      Ah*Bh round-robin over three TMEM accumulators and keeps the small correction terms in a fourth; the epilogue adds
+//      the four in fp32 round-to-nearest.  All 512 TMEM columns are used (BN = 128).
+//
+// Warp roles (544 threads): warps 0-15 producers (warps 0-3 double as the epilogue: TMEM lane quarter = warp id),
+// warp 16 = TMEM allocator + MMA issuer.  Pipelines: full[stage] (one arrival per producer warp) / empty[stage]
+// (tcgen05.commit), tmem_full (tcgen05.commit after the last k-block).
+//
+// K order of the conv-like GEMM is TAP-MAJOR: kk = j*Cred + c, A = [M][ksz][Cred] (vqs_permute_weight modes 1/2), so a
+// 32-wide k-block has ONE tap j and 32 consecutive channels: the padding / stride / bounds arithmetic of the gather is
+// done once per k-block per thread and the loads walk a constant channel stride (first build: (c, j) order, 815
+// instructions per thread per k-block, issue-bound at 43 TFLOP/s -- profiles/r01c_ncu_full_gemm_tc_vq.txt).
+#include <type_traits>
+
+#include "gemm_params.cuh"
+
+namespace vqs {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BKF = 32;                    // k-elements (floats) per stage row = one 128-byte swizzle atom
+constexpr int N_PROD_WARPS = 16;
+constexpr int N_PROD = N_PROD_WARPS * 32;
+constexpr int TC_THREADS = N_PROD + 32;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;  // bounded mbarrier waits: trap instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, cta_group::1
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset = 1024 B, bits [32,46)
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell), bits [46,48)
+  d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// byte offset of element (row r, k) inside a [rows x 32 float] K-major SWIZZLE_128B tile (tile base 1024-aligned)
+__device__ __forceinline__ uint32_t sw128_off(int r, int k) {
+  return (uint32_t)(r * 128 + ((((k >> 2) ^ (r & 7)) << 4) | ((k & 3) << 2)));
+}
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+template <int BN, int PASSES>
+struct TcCfg {
+  static constexpr int NOPS = (PASSES == 3) ? 2 : 1;                // hi (+ lo) copies per operand
+  static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 4 ? 4 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int NACC = (PASSES == 3) ? 4 : 1;                // TMEM accumulators of BN columns each
+  static constexpr int TMEM_COLS = NACC * BN;
+  static_assert(STAGES >= 2, "need at least a double buffer");
+};
+
+struct TcShared {
+  uint64_t full[4], empty[4], tmem_full;
+  uint32_t tmem_base;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// producers
+// ---------------------------------------------------------------------------------------------------
+template <int PASSES>
+__device__ __forceinline__ void st_elem(uint8_t* hi, uint8_t* lo, uint32_t off, float v) {
+  if (PASSES == 3) {
+    float h = tf32_hi(v);
+    *reinterpret_cast<float*>(hi + off) = h;
+    *reinterpret_cast<float*>(lo + off) = v - h;
+  } else {
+    *reinterpret_cast<float*>(hi + off) = v;
+  }
+}
+template <int PASSES>
+__device__ __forceinline__ void st_vec4(uint8_t* hi, uint8_t* lo, uint32_t off, float4 v) {
+  if (PASSES == 3) {
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  } else {
+    *reinterpret_cast<float4*>(hi + off) = v;
+  }
+}
+
+// MODE 0: conv-like GEMM (A = dense weights [M][Ktot], B gathered from NCL activations)
+// MODE 1: wgrad GEMM     (A = Aact[b, m, l], B = X'[b, c, l*l_mul + j*j_mul + off], reduction over (b, l))
+template <int MODE>
+struct TcParams;
+template <>
+struct TcParams<0> {
+  ConvParams p;
+};
+template <>
+struct TcParams<1> {
+  WgradParams p;
+};
+
+// Producer register stage: every global load of one k-block is issued before the first shared-memory store, and the
+// loads of k-block i+1 are in flight while k-block i is being stored (software pipelining across the empty-slot wait).
+template <int BN>
+struct ConvRegs {
+  static constexpr int TPR = N_PROD / BN;   // threads per B row: 4 (BN = 128) or 8 (BN = 64)
+  static constexpr int CH = 8 / TPR;        // 16-byte chunks of a B row per thread: 2 or 1
+  static constexpr int AI = BM * 8 / N_PROD;  // A chunks per thread: 2
+  float4 a[AI];
+  float b[CH * 4];
+};
+
+template <int BN>
+__device__ __forceinline__ void load_conv(const ConvParams& p, int kb, ConvRegs<BN>& rg, int m0, int ptid, bool n_ok,
+                                          const float* xb, int lbase, int bk0) {
+  const vqs_conv_gemm_desc& d = p.d;
+  // tap-major K: k-block kb = tap j, channels [c0, c0 + 32)
+  const uint32_t j = p.divCpb.div((uint32_t)kb);
+  const int c0 = (kb - (int)j * p.cpb) * BKF;
+  const int c = ptid & 7;  // A: float4 along k; 8 consecutive threads cover one 128-byte row
+  const float* arow = d.A + (size_t)kb * BKF + c * 4;
+#pragma unroll
+  for (int i = 0; i < ConvRegs<BN>::AI; ++i) {
+    const int m = m0 + (ptid >> 3) + i * (N_PROD / 8);
+    rg.a[i] = (m < d.M) ? __ldg(reinterpret_cast<const float4*>(arow + (size_t)m * p.Ktot))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // B: thread = column n (fixed (b, l)); one bounds decision per k-block, then a constant channel stride
+  int pn = lbase + (int)j * d.j_mul;
+  bool ok = n_ok && pn >= 0;
+  if (d.l_div == 2) {
+    ok = ok && ((pn & 1) == 0);
+    pn >>= 1;
+  }
+  ok = ok && pn < d.Lin;
+  const float* ptr = xb + (long long)pn * d.x_sl + (long long)(c0 + bk0 * 4) * d.x_sc;
+#pragma unroll
+  for (int e = 0; e < ConvRegs<BN>::CH * 4; ++e) rg.b[e] = ok ? __ldg(ptr + (long long)e * d.x_sc) : 0.f;
+}
+
+template <int BN, int PASSES>
+__device__ __forceinline__ void store_conv(const ConvParams& p, const ConvRegs<BN>& rg, uint8_t* sA_hi, uint8_t* sA_lo,
+                                           uint8_t* sB_hi, uint8_t* sB_lo, int ptid, int brow, int bk0) {
+  const int c = ptid & 7;
+#pragma unroll
+  for (int i = 0; i < ConvRegs<BN>::AI; ++i) {
+    const int r = (ptid >> 3) + i * (N_PROD / 8);
+    st_vec4<PASSES>(sA_hi, sA_lo, (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)), rg.a[i]);
+  }
+  const bool rl = p.d.x_relu != 0;
+#pragma unroll
+  for (int ci = 0; ci < ConvRegs<BN>::CH; ++ci) {
+    float4 v = make_float4(rg.b[ci * 4 + 0], rg.b[ci * 4 + 1], rg.b[ci * 4 + 2], rg.b[ci * 4 + 3]);
+    if (rl) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    st_vec4<PASSES>(sB_hi, sB_lo, (uint32_t)(brow * 128 + (((bk0 + ci) ^ (brow & 7)) << 4)), v);
+  }
+}
+
+template <int BN>
+struct WgradRegs {
+  static constexpr int RA = BM / N_PROD_WARPS, RB = BN / N_PROD_WARPS;  // rows per warp
+  float a[RA];
+  float b[RB];
+};
+// per-thread row constants of the wgrad loaders (rows are fixed for the whole kernel, only (b, l) moves)
+template <int BN>
+struct WgradRows {
+  int xoff[WgradRegs<BN>::RB];   // c * Lx
+  int pj[WgradRegs<BN>::RB];     // j * j_mul + off   (very negative for rows beyond Nw)
+  int na;                        // number of valid A rows of this warp
+};
+
+template <int BN>
+__device__ __forceinline__ void load_wgrad(const WgradParams& p, int kb, WgradRegs<BN>& rg, const WgradRows<BN>& rows,
+                                           int m0, int pwarp, int lane) {
+  const vqs_wgrad_desc& d = p.d;
+  const int kk = kb * BKF + lane;           // lane = k index within the block: global reads run along l (coalesced)
+  const bool k_ok = kk < p.Kred;
+  uint32_t b = 0, l = 0;
+  if (k_ok) p.divLa.divmod((uint32_t)kk, b, l);
+  const float* ab = d.Aact + ((size_t)b * d.M + m0 + pwarp) * d.La + l;
+  const float* xb = d.X + ((size_t)b * d.Cred) * d.Lx;
+  const int lp = (int)l * d.l_mul;
+  const size_t astep = (size_t)N_PROD_WARPS * d.La;
+#pragma unroll
+  for (int i = 0; i < WgradRegs<BN>::RA; ++i) rg.a[i] = (k_ok && i < rows.na) ? __ldg(ab + i * astep) : 0.f;
+#pragma unroll
+  for (int i = 0; i < WgradRegs<BN>::RB; ++i) {
+    const int pn = lp + rows.pj[i];
+    rg.b[i] = (k_ok && pn >= 0 && pn < d.Lx) ? __ldg(xb + rows.xoff[i] + pn) : 0.f;
+  }
+}
+
+template <int BN, int PASSES>
+__device__ __forceinline__ void store_wgrad(const WgradParams& p, const WgradRegs<BN>& rg, uint8_t* sA_hi,
+                                            uint8_t* sA_lo, uint8_t* sB_hi, uint8_t* sB_lo, int pwarp, int lane) {
+#pragma unroll
+  for (int i = 0; i < WgradRegs<BN>::RA; ++i) {
+    const int r = pwarp + i * N_PROD_WARPS;
+    st_elem<PASSES>(sA_hi, sA_lo, sw128_off(r, lane), rg.a[i]);
+  }
+  const bool rl = p.d.x_relu != 0;
+#pragma unroll
+  for (int i = 0; i < WgradRegs<BN>::RB; ++i) {
+    const int r = pwarp + i * N_PROD_WARPS;
+    st_elem<PASSES>(sB_hi, sB_lo, sw128_off(r, lane), rl ? fmaxf(rg.b[i], 0.f) : rg.b[i]);
+  }
+}
+
+__device__ __forceinline__ bool tc_mask_on(const void* m, int kind, size_t i) {
+  if (kind == 1) return reinterpret_cast<const float*>(m)[i] > 0.f;
+  return reinterpret_cast<const unsigned char*>(m)[i] != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+template <int MODE, int BN, int PASSES, int KSZ>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<MODE> prm) {
+  using Cfg = TcCfg<BN, PASSES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  TcShared* sh = reinterpret_cast<TcShared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  int nkb, kb_begin;
+  if constexpr (MODE == 0) {
+    nkb = (prm.p.Ktot + BKF - 1) / BKF;
+    kb_begin = 0;
+  } else {
+    const int total = (prm.p.Kred + BKF - 1) / BKF;
+    kb_begin = blockIdx.z * prm.p.kt_per_split;
+    int kb_end = kb_begin + prm.p.kt_per_split;
+    if (kb_end > total) kb_end = total;
+    nkb = kb_end - kb_begin;
+    if (nkb < 0) nkb = 0;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&sh->full[s], N_PROD_WARPS);
+      mbar_init(&sh->empty[s], 1);
+    }
+    mbar_init(&sh->tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == N_PROD_WARPS) tmem_alloc(&sh->tmem_base, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp < N_PROD_WARPS) {
+    // ================= producers =================
+    const int ptid = tid;
+    // per-thread constants of the conv B loader
+    bool n_ok = false;
+    const float* xb = nullptr;
+    int lbase = 0, brow = 0, bk0 = 0;
+    if constexpr (MODE == 0) {
+      constexpr int TPR = N_PROD / BN;
+      brow = ptid / TPR;
+      bk0 = (ptid % TPR) * (8 / TPR);
+      const int n = n0 + brow;
+      n_ok = n < prm.p.Ntot;
+      uint32_t bb = 0, ll = 0;
+      if (n_ok) prm.p.divL.divmod((uint32_t)n, bb, ll);
+      xb = prm.p.d.X + (long long)bb * prm.p.d.x_sb;
+      lbase = (int)ll * prm.p.d.l_mul + prm.p.d.off;
+    }
+    using Regs = typename std::conditional<MODE == 0, ConvRegs<BN>, WgradRegs<BN>>::type;
+    Regs cur, nxt;
+    WgradRows<BN> rows;
+    if constexpr (MODE == 1) {
+      const vqs_wgrad_desc& d = prm.p.d;
+#pragma unroll
+      for (int i = 0; i < WgradRegs<BN>::RB; ++i) {
+        const int n = n0 + warp + i * N_PROD_WARPS;
+        const int c = n / KSZ, j = n - c * KSZ;
+        rows.xoff[i] = c * d.Lx;
+        rows.pj[i] = (n < prm.p.Nw) ? j * d.j_mul + d.off : -(1 << 29);
+      }
+      int na = (d.M - m0 - warp + N_PROD_WARPS - 1) / N_PROD_WARPS;
+      rows.na = na < 0 ? 0 : na;
+    }
+    auto load = [&](int kb, Regs& rg) {
+      if constexpr (MODE == 0) load_conv<BN>(prm.p, kb, rg, m0, ptid, n_ok, xb, lbase, bk0);
+      else load_wgrad<BN>(prm.p, kb, rg, rows, m0, warp, lane);
+    };
+    if (nkb > 0) load(kb_begin, cur);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % Cfg::STAGES;
+      const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
+      if (i + 1 < nkb) load(kb_begin + i + 1, nxt);      // next k-block's loads fly during this block's wait + stores
+      mbar_wait(&sh->empty[s], ph ^ 1u);
+      uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+      uint8_t* sA_hi = st;
+      uint8_t* sB_hi = st + Cfg::A_BYTES;
+      uint8_t* sA_lo = st + Cfg::A_BYTES + Cfg::B_BYTES;
+      uint8_t* sB_lo = sA_lo + Cfg::A_BYTES;
+      if constexpr (MODE == 0) store_conv<BN, PASSES>(prm.p, cur, sA_hi, sA_lo, sB_hi, sB_lo, ptid, brow, bk0);
+      else store_wgrad<BN, PASSES>(prm.p, cur, sA_hi, sA_lo, sB_hi, sB_lo, warp, lane);
+      fence_proxy_async();  // this thread's generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->full[s]);          // one arrival per producer warp
+      cur = nxt;
+    }
+  } else {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
+        mbar_wait(&sh->full[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint64_t a_hi = make_desc_sw128(st);
+        const uint64_t b_hi = make_desc_sw128(st + Cfg::A_BYTES);
+        const uint64_t a_lo = make_desc_sw128(st + Cfg::A_BYTES + Cfg::B_BYTES);
+        const uint64_t b_lo = make_desc_sw128(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKF / 8; ++k) {
+          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // +32 bytes per K = 8 step inside the swizzle atom
+          const uint32_t first = (i == 0 && k == 0) ? 0u : 1u;
+          if (PASSES == 3) {
+            // accumulator 0: correction terms; accumulators 1..3: the main term, round-robin per K = 8 step
+            const int g = i * (BKF / 8) + k;
+            umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, first);
+            umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32(tmem_base + (uint32_t)((1 + g % 3) * BN), a_hi + adv, b_hi + adv, idesc, g < 3 ? 0u : 1u);
+          } else {
+            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
+          }
+        }
+        umma_commit(&sh->empty[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(&sh->tmem_full);   // accumulator complete
+    }
+    __syncwarp();
+  }
+
+  // ================= epilogue: warps 0-3, TMEM lane quarter = warp id =================
+  if (warp < 4) {
+    float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 33);  // stage buffers are idle by now
+    if (nkb > 0) {
+      mbar_wait(&sh->tmem_full, 0);
+      tc_fence_after();
+    }
+    int Ncols;
+    if constexpr (MODE == 0) Ncols = prm.p.Ntot;
+    else Ncols = prm.p.Nw;
+#pragma unroll 1
+    for (int blk = 0; blk < BN / 32; ++blk) {
+      float v[32];
+      if (nkb > 0) {
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(blk * 32);
+        if (Cfg::NACC == 4) {
+          float t1[32];
+          tmem_ld32(ta + 1 * BN, v);
+          tmem_ld32(ta + 2 * BN, t1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += t1[j];
+          tmem_ld32(ta + 3 * BN, t1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += t1[j];
+          tmem_ld32(ta, t1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += t1[j];
+        } else {
+          tmem_ld32(ta, v);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+      __syncwarp();
+      const int n = n0 + blk * 32 + lane;
+      const bool n_ok = n < Ncols;
+      if constexpr (MODE == 0) {
+        const vqs_conv_gemm_desc& d = prm.p.d;
+        uint32_t b = 0, l = 0;
+        if (n_ok) prm.p.divL.divmod((uint32_t)n, b, l);
+        const size_t col = (size_t)b * d.M * d.Lout + l;
+        // 8 rows at a time: all global reads of the batch are issued before the first use (the serial version paid one
+        // load latency per row: +50 us per 768x768x3 layer, profiles/r01c)
+        const float bias_on = d.bias ? 1.f : 0.f;
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += 8) {
+          const int mb = m0 + warp * 32 + rb;
+          if (mb >= d.M) break;
+          float x[8], pre[8], post[8];
+          bool k1[8], k2[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const bool live = n_ok && (mb + q < d.M);
+            const size_t o = col + (size_t)(mb + q) * d.Lout;
+            x[q] = stg[(rb + q) * 33 + lane];
+            pre[q] = (live && d.add_pre) ? d.add_pre[o] : 0.f;
+            post[q] = (live && d.add_post) ? d.add_post[o] : 0.f;
+            k1[q] = (live && d.mask_kind) ? tc_mask_on(d.mask, d.mask_kind, o) : true;
+            k2[q] = (live && d.out2 && d.mask2_kind) ? tc_mask_on(d.mask2, d.mask2_kind, o) : true;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int m = mb + q;
+            if (!n_ok || m >= d.M) continue;
+            const size_t o = col + (size_t)m * d.Lout;
+            float v1 = x[q];
+            if (bias_on != 0.f) v1 += __ldg(d.bias + m);
+            v1 += d.add_pre_relu ? fmaxf(pre[q], 0.f) : pre[q];
+            if (d.relu) v1 = fmaxf(v1, 0.f);
+            if (d.mask_out) d.mask_out[o] = v1 > 0.f ? 1 : 0;
+            if (!k1[q]) v1 = 0.f;
+            v1 += post[q];
+            d.out[o] = v1;
+            if (d.out2) d.out2[o] = k2[q] ? v1 : 0.f;
+          }
+        }
+      } else {
+        const vqs_wgrad_desc& d = prm.p.d;
+        float* out = prm.p.partial ? prm.p.partial + (size_t)blockIdx.z * d.M * prm.p.Nw : d.dW;
+        const bool accum = (prm.p.partial == nullptr) && d.accumulate;
+        for (int r = 0; r < 32; ++r) {
+          const int m = m0 + warp * 32 + r;
+          if (m >= d.M) break;
+          if (!n_ok) continue;
+          const size_t o = (size_t)m * prm.p.Nw + n;
+          const float x = stg[r * 33 + lane];
+          out[o] = accum ? out[o] + x : x;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == N_PROD_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int MODE, int BN, int PASSES, int KSZ>
+int launch_tc_t(const TcParams<MODE>& prm, dim3 grid, cudaStream_t st) {
+  using Cfg = TcCfg<BN, PASSES>;
+  auto kern = gemm_tc_kernel<MODE, BN, PASSES, KSZ>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    VQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(prm);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int MODE, int BN, int PASSES>
+int launch_tc_k(const TcParams<MODE>& prm, int ksz, dim3 grid, cudaStream_t st) {
+  switch (ksz) {
+    case 1: return launch_tc_t<MODE, BN, PASSES, 1>(prm, grid, st);
+    case 2: return launch_tc_t<MODE, BN, PASSES, 2>(prm, grid, st);
+    case 3: return launch_tc_t<MODE, BN, PASSES, 3>(prm, grid, st);
+    case 4: return launch_tc_t<MODE, BN, PASSES, 4>(prm, grid, st);
+  }
+  set_error("tcgen05 GEMM: kernel size %d not supported (1..4)", ksz);
+  return VQS_ERR_ARG;
+}
+
+template <int MODE>
+int launch_tc(const TcParams<MODE>& prm, int ksz, int bn, int precision, dim3 grid, cudaStream_t st) {
+  if (precision == 2) {
+    if (bn == 128) return launch_tc_k<MODE, 128, 3>(prm, ksz, grid, st);
+    return launch_tc_k<MODE, 64, 3>(prm, ksz, grid, st);
+  }
+  if (bn == 128) return launch_tc_k<MODE, 128, 1>(prm, ksz, grid, st);
+  return launch_tc_k<MODE, 64, 1>(prm, ksz, grid, st);
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvParams& p) {
+  return p.a_vec && p.d.a_tap_major && p.d.Cred % BKF == 0 && p.d.ksz >= 1;
+}
+bool wgrad_tc_supported(const WgradParams& p) { return p.d.ksz >= 1 && p.d.ksz <= 4 && p.Kred >= 32; }
+
+int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
+  TcParams<0> prm;
+  prm.p = p;
+  const int mt = (p.d.M + BM - 1) / BM;
+  // BN = 128 when that still gives every SM a tile, else 64 (twice the tiles)
+  int bn = ((long long)mt * ((p.Ntot + 127) / 128) >= num_sms() * 3 / 4) ? 128 : 64;
+  dim3 grid((p.Ntot + bn - 1) / bn, mt, 1);
+  return launch_tc<0>(prm, p.d.ksz, bn, precision, grid, st);
+}
+
+int launch_wgrad_tc(const WgradParams& p, int precision, cudaStream_t st) {
+  TcParams<1> prm;
+  prm.p = p;
+  const int bn = 128;
+  dim3 grid((p.Nw + bn - 1) / bn, (p.d.M + BM - 1) / BM, p.splits);
+  return launch_tc<1>(prm, p.d.ksz, bn, precision, grid, st);
+}
+
+}  // namespace vqs

@@ -10,6 +10,22 @@ from ._lib import LAYOUT_BDT_AS_DTB, LAYOUT_FLAT_ND, ConvGemmDesc, WgradDesc
 
 MASK_NONE, MASK_FLOAT, MASK_U8 = 0, 1, 2
 
+# GEMM engine used by conv_gemm / wgrad_gemm when the caller does not pass one: 'fp32' (exact, CUDA cores),
+# 'tf32' (tcgen05, single pass) or '3xtf32' (tcgen05, fp32-accurate split).  Captured into recorded schedules.
+_PRECISION = _lib.PREC_TF32X3
+
+
+def set_precision(name):
+    """Selects the default GEMM engine; returns the previous one (name)."""
+    global _PRECISION
+    prev = [k for k, v in _lib.PRECISIONS.items() if v == _PRECISION][0]
+    _PRECISION = _lib.PRECISIONS[name]
+    return prev
+
+
+def get_precision():
+    return [k for k, v in _lib.PRECISIONS.items() if v == _PRECISION][0]
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -178,12 +194,13 @@ def vq_grad_codebook(stats, codebook, g_loss, coef, out=None, accumulate=False):
 # ------------------------------------------------------------------------------------------------
 def conv_gemm(A, X, out, M, Cred, ksz, B, Lin, Lout, l_mul, j_mul, off, l_div=1, x_strides=None, x_relu=False,
               bias=None, add_pre=None, add_pre_relu=False, relu=False, mask_out=None, mask=None, mask_kind=MASK_NONE,
-              add_post=None, out2=None, mask2=None, mask2_kind=MASK_NONE):
+              add_post=None, out2=None, mask2=None, mask2_kind=MASK_NONE, precision=None, a_tap_major=False):
     """acc[b,m,l] = sum_{c,j} A[m, c*ksz+j] * X'[b, c, (l*l_mul + j*j_mul + off)/l_div] followed by the fused epilogue
     documented in include/vqs_b200.h.  x_strides = (batch, channel, position) element strides of X (default NCL)."""
     d = ConvGemmDesc()
     d.A = _p(A)
     d.X = X.data_ptr() if x_strides is not None else _p(X)
+    d.a_tap_major = int(a_tap_major)
     d.M, d.Cred, d.ksz = M, Cred, ksz
     d.B, d.Lin, d.Lout = B, Lin, Lout
     if x_strides is None:
@@ -203,6 +220,7 @@ def conv_gemm(A, X, out, M, Cred, ksz, B, Lin, Lout, l_mul, j_mul, off, l_div=1,
     d.out2 = _p(out2)
     d.mask2 = _pany(mask2)
     d.mask2_kind = mask2_kind if mask2 is not None else MASK_NONE
+    d.precision = _PRECISION if precision is None else _lib.PRECISIONS[precision]
     _call('vqs_conv_gemm', (ctypes.byref(d),), d)
     return out
 
@@ -211,7 +229,8 @@ def wgrad_workspace_bytes(M, Cred, ksz, B, La):
     return int(_lib.load().vqs_wgrad_workspace_bytes(M, Cred, ksz, B, La))
 
 
-def wgrad_gemm(Aact, X, dW, M, Cred, ksz, B, La, Lx, l_mul, j_mul, off, ws, x_relu=False, accumulate=False):
+def wgrad_gemm(Aact, X, dW, M, Cred, ksz, B, La, Lx, l_mul, j_mul, off, ws, x_relu=False, accumulate=False,
+               precision=None):
     d = WgradDesc()
     d.Aact = _p(Aact)
     d.X = _p(X)
@@ -221,6 +240,7 @@ def wgrad_gemm(Aact, X, dW, M, Cred, ksz, B, La, Lx, l_mul, j_mul, off, ws, x_re
     d.x_relu = int(x_relu)
     d.dW = _p(dW)
     d.accumulate = int(accumulate)
+    d.precision = _PRECISION if precision is None else _lib.PRECISIONS[precision]
     _call('vqs_wgrad_gemm', (ctypes.byref(d), _pany(ws), 0 if ws is None else ws.numel()), d)
     return dW
 
@@ -231,12 +251,18 @@ def bias_grad(g, db, accumulate=False):
     return db
 
 
-def permute_weight(w, out=None):
+def permute_weight(w, out=None, mode=0):
+    """w[d0][d1][k] -> mode 0: [d1][d0][k]; mode 1: [d0][k][d1] (tap-major); mode 2: [d1][k][d0] (tap-major, swapped)."""
     d0, d1, k = w.shape
     if out is None:
-        out = torch.empty(d1, d0, k, dtype=torch.float32, device=w.device)
-    _call('vqs_permute_weight', (_p(w), d0, d1, k, _p(out)))
+        shape = {0: (d1, d0, k), 1: (d0, k, d1), 2: (d1, k, d0)}[mode]
+        out = torch.empty(*shape, dtype=torch.float32, device=w.device)
+    _call('vqs_permute_weight', (_p(w), d0, d1, k, mode, _p(out)))
     return out
+
+
+def tensor_core_engine():
+    return _PRECISION != _lib.PREC_FP32
 
 
 # ------------------------------------------------------------------------------------------------

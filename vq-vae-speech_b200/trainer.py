@@ -31,8 +31,11 @@ class FusedTrainStep(object):
     steps for a fixed (batch_size, T) shape."""
 
     def __init__(self, model, batch_size, num_frames, learning_rate, use_graph=True, process_group=None,
-                 betas=(0.9, 0.999), eps=1e-8):
+                 betas=(0.9, 0.999), eps=1e-8, precision='3xtf32'):
+        """precision: GEMM engine of the conv / wgrad GEMMs -- '3xtf32' (tcgen05, fp32-accurate split; default), 'tf32'
+        (tcgen05 single pass: cuDNN's default numerics for the reference on a GPU) or 'fp32' (exact FMA on CUDA cores)."""
         self.model = model
+        self.precision = precision
         self.B, self.T = int(batch_size), int(num_frames)
         self.lr, self.betas, self.eps = float(learning_rate), betas, float(eps)
         self.pg = process_group
@@ -56,10 +59,12 @@ class FusedTrainStep(object):
         self._alloc_buffers()
         self.schedule = []
         prev = ops.set_recorder(self.schedule)
+        prev_prec = ops.set_precision(precision)
         try:
             self._emit_step()
         finally:
             ops.set_recorder(prev)
+            ops.set_precision(prev_prec)
         self.n_launch_calls = sum(1 for f, _, _ in self.schedule if f is not None)
         self.graph = None
         self.use_graph = bool(use_graph) and self.world == 1
@@ -157,12 +162,24 @@ class FusedTrainStep(object):
         b['gH1'] = f(B, max(R_enc, C), Tq)
         b['gT_a'], b['gT_b'] = f(B, C, T), f(B, C, T)
         b['gq'], b['gqj'], b['gz'] = f(B, D, Tq), f(B, D, Tq), f(B, D, Tq)
-        # permuted weights (the (d1, d0, k) arrangement dgrad / transposed-conv forward read as a dense GEMM operand)
+        # GEMM-ready weight arrangements, rebuilt at the top of every step by vqs_permute_weight: (name, role) ->
+        # (buffer or None when the parameter is used as is, tap_major, permute mode)
         self.wperm = {}
         for name in self.param_names:
-            if name.endswith('weight') and not name.startswith('_vq.') and name != '_encoder._conv_1.weight':
-                p = self._p(name)
-                self.wperm[name] = f(p.shape[1], p.shape[0], p.shape[2])
+            if not name.endswith('weight') or name.startswith('_vq.'):
+                continue
+            p = self._p(name)
+            roles = ('convT_fwd', 'convT_dgrad') if '_conv_trans_' in name else ('conv_fwd', 'conv_dgrad')
+            for role in roles:
+                if name == '_encoder._conv_1.weight' and role == 'conv_dgrad':
+                    continue                       # the input features need no gradient
+                tap, mode = F.gemm_weight_layout(tuple(p.shape), role, self.precision)
+                buf = None
+                if mode is not None:
+                    shape = {0: (p.shape[1], p.shape[0], p.shape[2]), 1: (p.shape[0], p.shape[2], p.shape[1]),
+                             2: (p.shape[1], p.shape[2], p.shape[0])}[mode]
+                    buf = f(*shape)
+                self.wperm[(name, role)] = (buf, tap, mode)
         ws_bytes = 16
         for (M, Cr, k, La) in [(C, Fi, 3, T), (C, C, 3, T), (C, C, 4, Tq), (C, C, 3, Tq), (R_enc, C, 3, Tq),
                                (C, R_enc, 1, Tq), (D, C, 3, Tq), (C, D, 3, Tq), (R_dec, C, 3, L2), (C, R_dec, 1, L2),
@@ -202,30 +219,51 @@ class FusedTrainStep(object):
         self._works = []
 
         # ---- 0. weight re-arrangements for this step's dgrad / transposed-conv GEMMs ----
-        for name, out in WP.items():
-            ops.permute_weight(P(name), out)
+        for (name, role), (buf, tap, mode) in WP.items():
+            if buf is not None:
+                ops.permute_weight(P(name), buf, mode=mode)
+
+        def A(name, role):
+            buf, tap, mode = WP[(name, role)]
+            return (buf if buf is not None else P(name)), tap
+
+        def cfwd(xin, name, bias, stride, pad, **kw):
+            a, tap = A(name, 'conv_fwd')
+            return F.conv1d_forward(xin, a, bias, stride, pad, tap=tap, **kw)
+
+        def cdgrad(gy, name, Lx, stride, pad, **kw):
+            a, tap = A(name, 'conv_dgrad')
+            return F.conv1d_dgrad(gy, a, Lx, stride, pad, tap=tap, **kw)
+
+        def tfwd(xin, name, bias, pad, **kw):
+            a, tap = A(name, 'convT_fwd')
+            return F.convT1d_forward(xin, a, bias, pad, tap=tap, **kw)
+
+        def tdgrad(gy, name, Lx, pad, **kw):
+            a, tap = A(name, 'convT_dgrad')
+            return F.convT1d_dgrad(gy, a, Lx, pad, tap=tap, **kw)
 
         # ---- 1. encoder forward (convolutional_encoder.py:118-146) ----
         ops.blc_to_ncl(b['x_in'], b['x'])                                            # vq_vae.py:118
-        F.conv1d_forward(b['x'], P(E + '_conv_1.weight'), P(E + '_conv_1.bias'), 1, 1, out=b['a1'], relu=True)
-        F.conv1d_forward(b['a1'], P(E + '_conv_2.weight'), P(E + '_conv_2.bias'), 1, 1, out=b['h2'], relu=True,
+        cfwd(b['x'], E + '_conv_1.weight', P(E + '_conv_1.bias'), 1, 1, out=b['a1'], relu=True)
+        cfwd(b['a1'], E + '_conv_2.weight', P(E + '_conv_2.bias'), 1, 1, out=b['h2'], relu=True,
                          mask_out=b['m2'], add_post=b['a1'])
-        F.conv1d_forward(b['h2'], P(E + '_conv_3.weight'), P(E + '_conv_3.bias'), 2, 2, out=b['a3'], relu=True)
-        F.conv1d_forward(b['a3'], P(E + '_conv_4.weight'), P(E + '_conv_4.bias'), 1, 1, out=b['h4'], relu=True,
+        cfwd(b['h2'], E + '_conv_3.weight', P(E + '_conv_3.bias'), 2, 2, out=b['a3'], relu=True)
+        cfwd(b['a3'], E + '_conv_4.weight', P(E + '_conv_4.bias'), 1, 1, out=b['h4'], relu=True,
                          mask_out=b['m4'], add_post=b['a3'])
-        F.conv1d_forward(b['h4'], P(E + '_conv_5.weight'), P(E + '_conv_5.bias'), 1, 1, out=b['h5'], relu=True,
+        cfwd(b['h4'], E + '_conv_5.weight', P(E + '_conv_5.bias'), 1, 1, out=b['h5'], relu=True,
                          mask_out=b['m5'], add_post=b['h4'])
         # residual stack: x_{i+1} = relu(x_i) + conv2(relu(conv1(relu(x_i)))), then relu, then + h5 (outer skip)
         xs = [b['h5']] + [b['e_x%d' % i] for i in range(1, nl)]
         for i in range(nl):
-            F.conv1d_forward(xs[i], P(E + RS1), None, 1, 1, out=b['e_hh%d' % i], x_relu=True, relu=True)
+            cfwd(xs[i], E + RS1, None, 1, 1, out=b['e_hh%d' % i], x_relu=True, relu=True)
             if i + 1 < nl:
-                F.conv1d_forward(b['e_hh%d' % i], P(E + RS2), None, 1, 0, out=xs[i + 1], add_pre=xs[i],
+                cfwd(b['e_hh%d' % i], E + RS2, None, 1, 0, out=xs[i + 1], add_pre=xs[i],
                                  add_pre_relu=True)
             else:
-                F.conv1d_forward(b['e_hh%d' % i], P(E + RS2), None, 1, 0, out=b['enc_out'], add_pre=xs[i],
+                cfwd(b['e_hh%d' % i], E + RS2, None, 1, 0, out=b['enc_out'], add_pre=xs[i],
                                  add_pre_relu=True, relu=True, mask_out=b['m_e'], add_post=b['h5'])
-        F.conv1d_forward(b['enc_out'], P('_pre_vq_conv.weight'), P('_pre_vq_conv.bias'), 1, 1, out=b['z'])
+        cfwd(b['enc_out'], '_pre_vq_conv.weight', P('_pre_vq_conv.bias'), 1, 1, out=b['z'])
 
         # ---- 2. VQ bottleneck ----
         vq = m._vq
@@ -246,19 +284,19 @@ class FusedTrainStep(object):
         if self.use_jitter:
             ops.jitter_fwd(b['q'], b['jitter_src'], b['qj'])
             dec_in = b['qj']
-        F.conv1d_forward(dec_in, P(DEC + '_conv_1.weight'), P(DEC + '_conv_1.bias'), 1, 1, out=b['d1'])
+        cfwd(dec_in, DEC + '_conv_1.weight', P(DEC + '_conv_1.bias'), 1, 1, out=b['d1'])
         ops.upsample2_fwd(b['d1'], b['u'])
         xd = [b['u']] + [b['d_x%d' % i] for i in range(1, nl)]
         for i in range(nl):
-            F.conv1d_forward(xd[i], P(DEC + RS1), None, 1, 1, out=b['d_hh%d' % i], x_relu=True, relu=True)
+            cfwd(xd[i], DEC + RS1, None, 1, 1, out=b['d_hh%d' % i], x_relu=True, relu=True)
             last = i + 1 == nl
-            F.conv1d_forward(b['d_hh%d' % i], P(DEC + RS2), None, 1, 0, out=b['s'] if last else xd[i + 1],
+            cfwd(b['d_hh%d' % i], DEC + RS2, None, 1, 0, out=b['s'] if last else xd[i + 1],
                              add_pre=xd[i], add_pre_relu=True, relu=last)
-        F.convT1d_forward(b['s'], WP[DEC + '_conv_trans_1.weight'], P(DEC + '_conv_trans_1.bias'), 1, out=b['t1'],
+        tfwd(b['s'], DEC + '_conv_trans_1.weight', P(DEC + '_conv_trans_1.bias'), 1, out=b['t1'],
                           relu=True)
-        F.convT1d_forward(b['t1'], WP[DEC + '_conv_trans_2.weight'], P(DEC + '_conv_trans_2.bias'), 0, out=b['t2'],
+        tfwd(b['t1'], DEC + '_conv_trans_2.weight', P(DEC + '_conv_trans_2.bias'), 0, out=b['t2'],
                           relu=True)
-        F.convT1d_forward(b['t2'], WP[DEC + '_conv_trans_3.weight'], P(DEC + '_conv_trans_3.bias'), 0, out_len=T,
+        tfwd(b['t2'], DEC + '_conv_trans_3.weight', P(DEC + '_conv_trans_3.bias'), 0, out_len=T,
                           out=b['recon'])                                          # trimmed to T (vq_vae.py:133-137)
 
         # ---- 4. loss (trainer.py:54-56): MSE against the input features, gradient in the same pass ----
@@ -268,25 +306,25 @@ class FusedTrainStep(object):
         gq2 = self._view('gA2', C, L2 + 2)
         F.convT1d_wgrad(b['g_recon'], b['t2'], G[DEC + '_conv_trans_3.weight'], 0, ws)
         ops.bias_grad(b['g_recon'], G[DEC + '_conv_trans_3.bias'])
-        F.convT1d_dgrad(b['g_recon'], P(DEC + '_conv_trans_3.weight'), L2 + 2, 0, out=gq2, mask=b['t2'],
+        tdgrad(b['g_recon'], DEC + '_conv_trans_3.weight', L2 + 2, 0, out=gq2, mask=b['t2'],
                         mask_kind=MASK_FLOAT)
         gq1 = self._view('gB2', C, L2)
         F.convT1d_wgrad(gq2, b['t1'], G[DEC + '_conv_trans_2.weight'], 0, ws)
         ops.bias_grad(gq2, G[DEC + '_conv_trans_2.bias'])
-        F.convT1d_dgrad(gq2, P(DEC + '_conv_trans_2.weight'), L2, 0, out=gq1, mask=b['t1'], mask_kind=MASK_FLOAT)
+        tdgrad(gq2, DEC + '_conv_trans_2.weight', L2, 0, out=gq1, mask=b['t1'], mask_kind=MASK_FLOAT)
         g = self._view('gA2', C, L2)
         F.convT1d_wgrad(gq1, b['s'], G[DEC + '_conv_trans_1.weight'], 1, ws)
         ops.bias_grad(gq1, G[DEC + '_conv_trans_1.bias'])
-        F.convT1d_dgrad(gq1, P(DEC + '_conv_trans_1.weight'), L2, 1, out=g, mask=b['s'], mask_kind=MASK_FLOAT)
+        tdgrad(gq1, DEC + '_conv_trans_1.weight', L2, 1, out=g, mask=b['s'], mask_kind=MASK_FLOAT)
         other = self._view('gB2', C, L2)
         R_dec = d['R_dec']
         gh = self._view('gH2', R_dec, L2)
         for n, i in enumerate(reversed(range(nl))):
             acc = n > 0                                      # the shared Residual: second application accumulates
             F.conv1d_wgrad(g, b['d_hh%d' % i], G[DEC + RS2], 1, 0, ws, accumulate=acc)
-            F.conv1d_dgrad(g, WP[DEC + RS2], L2, 1, 0, out=gh, mask=b['d_hh%d' % i], mask_kind=MASK_FLOAT)
+            cdgrad(g, DEC + RS2, L2, 1, 0, out=gh, mask=b['d_hh%d' % i], mask_kind=MASK_FLOAT)
             F.conv1d_wgrad(gh, xd[i], G[DEC + RS1], 1, 1, ws, x_relu=True, accumulate=acc)
-            F.conv1d_dgrad(gh, WP[DEC + RS1], L2, 1, 1, out=other, add_pre=g, mask=xd[i], mask_kind=MASK_FLOAT)
+            cdgrad(gh, DEC + RS1, L2, 1, 1, out=other, add_pre=g, mask=xd[i], mask_kind=MASK_FLOAT)
             g, other = other, g
         ops.upsample2_bwd(g, b['gA1'])
         gd1 = b['gA1']
@@ -294,10 +332,10 @@ class FusedTrainStep(object):
         ops.bias_grad(gd1, G[DEC + '_conv_1.bias'])
         gq = b['gq']
         if self.use_jitter:
-            F.conv1d_dgrad(gd1, WP[DEC + '_conv_1.weight'], Tq, 1, 1, out=b['gqj'])
+            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=b['gqj'])
             ops.jitter_bwd(b['gqj'], b['jitter_src'], gq)
         else:
-            F.conv1d_dgrad(gd1, WP[DEC + '_conv_1.weight'], Tq, 1, 1, out=gq)
+            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=gq)
         if self.world > 1:       # decoder gradients are complete: start their allreduce under the encoder's backward
             ops.record_callable(lambda: self._allreduce_bucket(self.bucket_split, self.flat_g.numel()))
 
@@ -312,7 +350,7 @@ class FusedTrainStep(object):
         F.conv1d_wgrad(gz, b['enc_out'], G['_pre_vq_conv.weight'], 1, 1, ws)
         ops.bias_grad(gz, G['_pre_vq_conv.bias'])
         ge, g = b['gC1'], b['gA1']
-        F.conv1d_dgrad(gz, WP['_pre_vq_conv.weight'], Tq, 1, 1, out=ge, out2=g, mask2=b['m_e'], mask2_kind=MASK_U8)
+        cdgrad(gz, '_pre_vq_conv.weight', Tq, 1, 1, out=ge, out2=g, mask2=b['m_e'], mask2_kind=MASK_U8)
         other = b['gB1']
         R_enc = d['R_enc']
         gh = self._view('gH1', R_enc, Tq)
@@ -320,38 +358,38 @@ class FusedTrainStep(object):
         for n, i in enumerate(reversed(range(nl))):
             acc = n > 0
             F.conv1d_wgrad(g, b['e_hh%d' % i], G[E + RS2], 1, 0, ws, accumulate=acc)
-            F.conv1d_dgrad(g, WP[E + RS2], Tq, 1, 0, out=gh, mask=b['e_hh%d' % i], mask_kind=MASK_FLOAT)
+            cdgrad(g, E + RS2, Tq, 1, 0, out=gh, mask=b['e_hh%d' % i], mask_kind=MASK_FLOAT)
             F.conv1d_wgrad(gh, xs[i], G[E + RS1], 1, 1, ws, x_relu=True, accumulate=acc)
             if i > 0:
-                F.conv1d_dgrad(gh, WP[E + RS1], Tq, 1, 1, out=other, add_pre=g, mask=xs[i], mask_kind=MASK_FLOAT)
+                cdgrad(gh, E + RS1, Tq, 1, 1, out=other, add_pre=g, mask=xs[i], mask_kind=MASK_FLOAT)
                 g, other = other, g
             else:
                 # gh5 = ((g + dgrad) * (h5 > 0)) + ge ; gp5 = gh5 * m5
-                F.conv1d_dgrad(gh, WP[E + RS1], Tq, 1, 1, out=other, add_pre=g, mask=xs[0], mask_kind=MASK_FLOAT,
+                cdgrad(gh, E + RS1, Tq, 1, 1, out=other, add_pre=g, mask=xs[0], mask_kind=MASK_FLOAT,
                                add_post=ge, out2=g, mask2=b['m5'], mask2_kind=MASK_U8)
                 gh5, gp5 = other, g
         # conv_5: h5 = relu(p5) + h4
         F.conv1d_wgrad(gp5, b['h4'], G[E + '_conv_5.weight'], 1, 1, ws)
         ops.bias_grad(gp5, G[E + '_conv_5.bias'])
         gh4, gp4 = b['gC1'], self._view('gH1', C, Tq)      # ge (gC1) is dead after gh5 was formed
-        F.conv1d_dgrad(gp5, WP[E + '_conv_5.weight'], Tq, 1, 1, out=gh4, add_pre=gh5, out2=gp4, mask2=b['m4'],
+        cdgrad(gp5, E + '_conv_5.weight', Tq, 1, 1, out=gh4, add_pre=gh5, out2=gp4, mask2=b['m4'],
                        mask2_kind=MASK_U8)
         # conv_4: h4 = relu(p4) + a3 ; then a3 = relu(p3)
         F.conv1d_wgrad(gp4, b['a3'], G[E + '_conv_4.weight'], 1, 1, ws)
         ops.bias_grad(gp4, G[E + '_conv_4.bias'])
         gp3 = b['gA1']
-        F.conv1d_dgrad(gp4, WP[E + '_conv_4.weight'], Tq, 1, 1, out=gp3, add_pre=gh4, mask=b['a3'],
+        cdgrad(gp4, E + '_conv_4.weight', Tq, 1, 1, out=gp3, add_pre=gh4, mask=b['a3'],
                        mask_kind=MASK_FLOAT)
         # conv_3 (k4 s2 p2): a3 = relu(conv3(h2))
         F.conv1d_wgrad(gp3, b['h2'], G[E + '_conv_3.weight'], 2, 2, ws)
         ops.bias_grad(gp3, G[E + '_conv_3.bias'])
         gh2, gp2 = b['gT_a'], b['gT_b']
-        F.conv1d_dgrad(gp3, WP[E + '_conv_3.weight'], T, 2, 2, out=gh2, out2=gp2, mask2=b['m2'], mask2_kind=MASK_U8)
+        cdgrad(gp3, E + '_conv_3.weight', T, 2, 2, out=gh2, out2=gp2, mask2=b['m2'], mask2_kind=MASK_U8)
         # conv_2: h2 = relu(p2) + a1 ; a1 = relu(p1)
         F.conv1d_wgrad(gp2, b['a1'], G[E + '_conv_2.weight'], 1, 1, ws)
         ops.bias_grad(gp2, G[E + '_conv_2.bias'])
         gp1 = self._view('gA2', C, T)
-        F.conv1d_dgrad(gp2, WP[E + '_conv_2.weight'], T, 1, 1, out=gp1, add_pre=gh2, mask=b['a1'],
+        cdgrad(gp2, E + '_conv_2.weight', T, 1, 1, out=gp1, add_pre=gh2, mask=b['a1'],
                        mask_kind=MASK_FLOAT)
         F.conv1d_wgrad(gp1, b['x'], G[E + '_conv_1.weight'], 1, 1, ws)
         ops.bias_grad(gp1, G[E + '_conv_1.bias'])
