@@ -145,24 +145,32 @@ struct TcShared {
 // ---------------------------------------------------------------------------------------------------
 // producers
 // ---------------------------------------------------------------------------------------------------
+// Explicit shared-space stores on 32-bit addresses (generic-pointer stores compile to ST + 64-bit address arithmetic:
+// 128 generic ST and 420 IMAD in the first build's producer loop).
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 template <int PASSES>
-__device__ __forceinline__ void st_elem(uint8_t* hi, uint8_t* lo, uint32_t off, float v) {
+__device__ __forceinline__ void st_elem(uint32_t hi, uint32_t lo, float v) {
   if (PASSES == 3) {
     float h = tf32_hi(v);
-    *reinterpret_cast<float*>(hi + off) = h;
-    *reinterpret_cast<float*>(lo + off) = v - h;
+    sts_f32(hi, h);
+    sts_f32(lo, v - h);
   } else {
-    *reinterpret_cast<float*>(hi + off) = v;
+    sts_f32(hi, v);
   }
 }
 template <int PASSES>
-__device__ __forceinline__ void st_vec4(uint8_t* hi, uint8_t* lo, uint32_t off, float4 v) {
+__device__ __forceinline__ void st_vec4(uint32_t hi, uint32_t lo, float4 v) {
   if (PASSES == 3) {
     float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    sts_v4(hi, h);
+    sts_v4(lo, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
   } else {
-    *reinterpret_cast<float4*>(hi + off) = v;
+    sts_v4(hi, v);
   }
 }
 
@@ -218,21 +226,22 @@ __device__ __forceinline__ void load_conv(const ConvParams& p, int kb, ConvRegs<
   for (int e = 0; e < ConvRegs<BN>::CH * 4; ++e) rg.b[e] = ok ? __ldg(ptr + (long long)e * d.x_sc) : 0.f;
 }
 
+// offA = byte offset of this thread's first A chunk, offB[ci] of its B chunks (k-block invariant)
 template <int BN, int PASSES>
-__device__ __forceinline__ void store_conv(const ConvParams& p, const ConvRegs<BN>& rg, uint8_t* sA_hi, uint8_t* sA_lo,
-                                           uint8_t* sB_hi, uint8_t* sB_lo, int ptid, int brow, int bk0) {
-  const int c = ptid & 7;
+__device__ __forceinline__ void store_conv(const ConvParams& p, const ConvRegs<BN>& rg, uint32_t sA_hi, uint32_t sA_lo,
+                                           uint32_t sB_hi, uint32_t sB_lo, uint32_t offA,
+                                           const uint32_t (&offB)[ConvRegs<BN>::CH]) {
 #pragma unroll
   for (int i = 0; i < ConvRegs<BN>::AI; ++i) {
-    const int r = (ptid >> 3) + i * (N_PROD / 8);
-    st_vec4<PASSES>(sA_hi, sA_lo, (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)), rg.a[i]);
+    const uint32_t o = offA + (uint32_t)(i * (N_PROD / 8) * 128);   // rows step by 64: (r & 7) unchanged
+    st_vec4<PASSES>(sA_hi + o, sA_lo + o, rg.a[i]);
   }
   const bool rl = p.d.x_relu != 0;
 #pragma unroll
   for (int ci = 0; ci < ConvRegs<BN>::CH; ++ci) {
     float4 v = make_float4(rg.b[ci * 4 + 0], rg.b[ci * 4 + 1], rg.b[ci * 4 + 2], rg.b[ci * 4 + 3]);
     if (rl) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-    st_vec4<PASSES>(sB_hi, sB_lo, (uint32_t)(brow * 128 + (((bk0 + ci) ^ (brow & 7)) << 4)), v);
+    st_vec4<PASSES>(sB_hi + offB[ci], sB_lo + offB[ci], v);
   }
 }
 
@@ -271,19 +280,20 @@ __device__ __forceinline__ void load_wgrad(const WgradParams& p, int kb, WgradRe
   }
 }
 
+// off0 = sw128_off(warp, lane); rows step by 16 so (r & 7) and with it the swizzled chunk stay fixed: +2048 B per row step
 template <int BN, int PASSES>
-__device__ __forceinline__ void store_wgrad(const WgradParams& p, const WgradRegs<BN>& rg, uint8_t* sA_hi,
-                                            uint8_t* sA_lo, uint8_t* sB_hi, uint8_t* sB_lo, int pwarp, int lane) {
+__device__ __forceinline__ void store_wgrad(const WgradParams& p, const WgradRegs<BN>& rg, uint32_t sA_hi,
+                                            uint32_t sA_lo, uint32_t sB_hi, uint32_t sB_lo, uint32_t off0) {
 #pragma unroll
   for (int i = 0; i < WgradRegs<BN>::RA; ++i) {
-    const int r = pwarp + i * N_PROD_WARPS;
-    st_elem<PASSES>(sA_hi, sA_lo, sw128_off(r, lane), rg.a[i]);
+    const uint32_t o = off0 + (uint32_t)(i * N_PROD_WARPS * 128);
+    st_elem<PASSES>(sA_hi + o, sA_lo + o, rg.a[i]);
   }
   const bool rl = p.d.x_relu != 0;
 #pragma unroll
   for (int i = 0; i < WgradRegs<BN>::RB; ++i) {
-    const int r = pwarp + i * N_PROD_WARPS;
-    st_elem<PASSES>(sB_hi, sB_lo, sw128_off(r, lane), rl ? fmaxf(rg.b[i], 0.f) : rg.b[i]);
+    const uint32_t o = off0 + (uint32_t)(i * N_PROD_WARPS * 128);
+    st_elem<PASSES>(sB_hi + o, sB_lo + o, rl ? fmaxf(rg.b[i], 0.f) : rg.b[i]);
   }
 }
 
@@ -350,7 +360,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
       lbase = (int)ll * prm.p.d.l_mul + prm.p.d.off;
     }
     using Regs = typename std::conditional<MODE == 0, ConvRegs<BN>, WgradRegs<BN>>::type;
-    Regs cur, nxt;
     WgradRows<BN> rows;
     if constexpr (MODE == 1) {
       const vqs_wgrad_desc& d = prm.p.d;
@@ -368,23 +377,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
       if constexpr (MODE == 0) load_conv<BN>(prm.p, kb, rg, m0, ptid, n_ok, xb, lbase, bk0);
       else load_wgrad<BN>(prm.p, kb, rg, rows, m0, warp, lane);
     };
-    if (nkb > 0) load(kb_begin, cur);
-    for (int i = 0; i < nkb; ++i) {
+    // Register ring of depth 3: while k-block i is stored, the loads of i+1 and i+2 are in flight.  With ~1.2k cycles of
+    // loaded-L2 latency and 32 KB of operands per k-block, one block in flight caps the SM at ~27 B/clk (measured: 2.8k
+    // cycles per k-block); two blocks in flight cover the 768-cycle MMA time of a 3xTF32 k-block.
+    const uint32_t smem_base = smem_u32(smem);
+    uint32_t offA = 0, off0 = 0;
+    uint32_t offB[ConvRegs<BN>::CH];
+    if constexpr (MODE == 0) {
+      const int r0a = ptid >> 3, ca = ptid & 7;
+      offA = (uint32_t)(r0a * 128 + ((ca ^ (r0a & 7)) << 4));
+#pragma unroll
+      for (int ci = 0; ci < ConvRegs<BN>::CH; ++ci) offB[ci] = (uint32_t)(brow * 128 + (((bk0 + ci) ^ (brow & 7)) << 4));
+    } else {
+      off0 = sw128_off(warp, lane);
+#pragma unroll
+      for (int ci = 0; ci < ConvRegs<BN>::CH; ++ci) offB[ci] = 0;
+    }
+    auto stage = [&](int i, const Regs& rg) {
       const int s = i % Cfg::STAGES;
       const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
-      if (i + 1 < nkb) load(kb_begin + i + 1, nxt);      // next k-block's loads fly during this block's wait + stores
       mbar_wait(&sh->empty[s], ph ^ 1u);
-      uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-      uint8_t* sA_hi = st;
-      uint8_t* sB_hi = st + Cfg::A_BYTES;
-      uint8_t* sA_lo = st + Cfg::A_BYTES + Cfg::B_BYTES;
-      uint8_t* sB_lo = sA_lo + Cfg::A_BYTES;
-      if constexpr (MODE == 0) store_conv<BN, PASSES>(prm.p, cur, sA_hi, sA_lo, sB_hi, sB_lo, ptid, brow, bk0);
-      else store_wgrad<BN, PASSES>(prm.p, cur, sA_hi, sA_lo, sB_hi, sB_lo, warp, lane);
+      const uint32_t sA_hi = smem_base + (uint32_t)(s * Cfg::STAGE_BYTES);
+      const uint32_t sB_hi = sA_hi + Cfg::A_BYTES;
+      const uint32_t sA_lo = sA_hi + Cfg::A_BYTES + Cfg::B_BYTES;
+      const uint32_t sB_lo = sA_lo + Cfg::A_BYTES;
+      if constexpr (MODE == 0) store_conv<BN, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, offA, offB);
+      else store_wgrad<BN, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, off0);
       fence_proxy_async();  // this thread's generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->full[s]);          // one arrival per producer warp
-      cur = nxt;
+    };
+    Regs r0, r1, r2;
+    if (nkb > 0) load(kb_begin, r0);
+    if (nkb > 1) load(kb_begin + 1, r1);
+    for (int i = 0; i < nkb; i += 3) {
+      if (i + 2 < nkb) load(kb_begin + i + 2, r2);
+      stage(i, r0);
+      if (i + 1 >= nkb) break;
+      if (i + 3 < nkb) load(kb_begin + i + 3, r0);
+      stage(i + 1, r1);
+      if (i + 2 >= nkb) break;
+      if (i + 4 < nkb) load(kb_begin + i + 4, r1);
+      stage(i + 2, r2);
     }
   } else {
     // ================= MMA issuer (one thread) =================
