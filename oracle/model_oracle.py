@@ -211,7 +211,7 @@ def model_forward(p, x_btf, cfg, jitter_src=None, training=True, dtype=np.float6
         ema = dict(cluster_size=g('_vq._ema_cluster_size'), ema_w=g('_vq._ema_w'),
                    decay=cfg['decay'], eps=cfg.get('epsilon', 1e-5))
     vq = vqo.vq_forward(z, np.asarray(p['_vq._embedding.weight'], np.float32), cfg['commitment_cost'],
-                        ema=ema, training=training, dtype=dtype)
+                        ema=ema, training=training, dtype=dtype, stats_allreduce=cfg.get('stats_allreduce'))
     c['vq'] = vq
     q = vq['quantized']
     if jitter_src is not None:

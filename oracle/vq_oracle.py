@@ -123,7 +123,7 @@ def ema_update(cluster_size, ema_w, counts, dw, decay, eps, dtype=np.float32):
 # ----------------------------------------------------------------------------------------------
 # full forward / backward
 # ----------------------------------------------------------------------------------------------
-def vq_forward(z, W, commitment_cost, ema=None, training=True, dtype=np.float64):
+def vq_forward(z, W, commitment_cost, ema=None, training=True, dtype=np.float64, stats_allreduce=None):
     """Forward of VectorQuantizer (ema=None) or VectorQuantizerEMA (ema=dict).
 
     z: (B, D, T).  W: (K, D) codebook (`_embedding.weight`).
@@ -131,6 +131,10 @@ def vq_forward(z, W, commitment_cost, ema=None, training=True, dtype=np.float64)
     Index search is always fp32 (that is what the reference computes); every
     other quantity is evaluated in `dtype` (float64 = high-accuracy truth used
     for the 1e-5 relative parity bound, float32 = like-for-like).
+
+    stats_allreduce: optional callable (counts, dw, n_rows) -> (counts, dw, n_rows_total) that sums the per-code
+    statistics over data-parallel shards: the EMA update and the perplexity then use the global
+    statistics, everything else (indices, quantisation, loss) stays per shard.
 
     Returns a dict: idx, near_tie, gap_rel, counts, dw, W_used (codebook used
     for quantisation: updated one in EMA training mode, ema.py:156-159),
@@ -148,8 +152,11 @@ def vq_forward(z, W, commitment_cost, ema=None, training=True, dtype=np.float64)
     counts, dw = code_stats(flat, idx, K, dtype)
     out = dict(idx=idx, near_tie=near, gap_rel=gap, counts=counts, dw=dw, N=N)
     Wq = np.asarray(W, dtype)
+    g_counts, g_dw, n_total = counts, dw, N
+    if stats_allreduce is not None and ema is not None and training:
+        g_counts, g_dw, n_total = stats_allreduce(counts, dw, N)
     if ema is not None and training:
-        cs, ew, Wq = ema_update(ema['cluster_size'], ema['ema_w'], counts, dw, ema['decay'], ema['eps'], dtype)
+        cs, ew, Wq = ema_update(ema['cluster_size'], ema['ema_w'], g_counts, g_dw, ema['decay'], ema['eps'], dtype)
         out.update(cluster_size=cs, ema_w=ew)
     out['W_used'] = Wq
     q_rows = Wq[idx]                                   # matmul(encodings, W) (ema.py:159)
@@ -164,7 +171,7 @@ def vq_forward(z, W, commitment_cost, ema=None, training=True, dtype=np.float64)
     ste_rows = flat + (q_rows - flat)                  # inputs + (quantized - inputs).detach() (ema.py:169)
     out['quantized'] = bdt_from_rows(ste_rows, B, D, T)
     out['q_rows'] = q_rows
-    out['perplexity'] = perplexity(counts, N, dtype)
+    out['perplexity'] = perplexity(g_counts, n_total, dtype)
     out['encodings'] = one_hot(idx, K).reshape(B, T, K)          # .view(batch_size, time, -1) of an (N, K) buffer
     out['distances'] = distances_fp32(flat32, W).reshape(B, T, K)
     return out

@@ -1,0 +1,67 @@
+"""Data-parallel plumbing of the training step: one process per GPU, torch.distributed (NCCL on B200, gloo in the CPU
+tests).  The reference has no working multi-GPU path (its nn.DataParallel wrap is dead code, pipeline_factory.py:56-61);
+the contract implemented here is SURVEY.md 8e:
+
+  * the batch is sharded over ranks; every rank holds the full (bit-identical) weights, codebook and EMA state;
+  * EMA statistics [counts | dw] are SUM-allreduced between the assignment and the EMA update, so every rank applies
+    the same update and codebooks stay identical;
+  * gradients are SUM-allreduced in two buckets (decoder first: its backward finishes first, so its allreduce overlaps
+    the encoder's backward) and divided by world_size inside the fused AMSGrad kernel (g_scale).
+
+Nothing here touches CUDA directly, so the same class runs under gloo on CPU tensors (tests/test_parallel_cpu.py).
+"""
+import torch
+import torch.distributed as dist
+
+
+class DataParallelComm(object):
+    def __init__(self, process_group=None):
+        self.pg = process_group
+        self.enabled = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if self.enabled else 1
+        self.rank = dist.get_rank(process_group) if self.enabled else 0
+        self._works = []
+
+    @property
+    def grad_scale(self):
+        """Factor the optimizer applies to the summed gradient: the average over ranks."""
+        return 1.0 / self.world
+
+    def allreduce_stats(self, stats):
+        """In-place SUM of the packed [counts (K) | dw (K*D)] vector (blocking: the EMA update needs it)."""
+        if self.world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.pg)
+        return stats
+
+    def total_rows(self, local_rows):
+        """Rows the (allreduced) counts were taken over: every rank contributes the same number of rows."""
+        return local_rows * self.world
+
+    def start_bucket(self, flat_grad, lo, hi):
+        """Launches the asynchronous SUM-allreduce of flat_grad[lo:hi]."""
+        if self.world > 1 and hi > lo:
+            self._works.append(dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def wait_buckets(self):
+        for w in self._works:
+            w.wait()
+        self._works = []
+
+    def shard(self, global_batch):
+        """This rank's contiguous slice [r*B/W, (r+1)*B/W) of a global batch (first dim)."""
+        n = global_batch.shape[0]
+        if n % self.world != 0:
+            raise ValueError('global batch %d is not divisible by world size %d' % (n, self.world))
+        per = n // self.world
+        return global_batch[self.rank * per:(self.rank + 1) * per]
+
+    def assert_replicated(self, tensor, what='tensor'):
+        """Debug helper: raises unless `tensor` is bit-identical on every rank."""
+        if self.world == 1:
+            return
+        lo = tensor.detach().clone()
+        hi = tensor.detach().clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.pg)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.pg)
+        if not torch.equal(lo, hi):
+            raise RuntimeError('%s differs across data-parallel ranks' % what)

@@ -19,6 +19,7 @@ from . import functional as F
 from . import ops
 from ._lib import LAYOUT_BDT_AS_DTB
 from .modules import jitter_plan
+from .parallel import DataParallelComm
 from .ops import MASK_FLOAT, MASK_U8
 from .vector_quantizer import VectorQuantizerEMA
 
@@ -38,10 +39,8 @@ class FusedTrainStep(object):
         self.precision = precision
         self.B, self.T = int(batch_size), int(num_frames)
         self.lr, self.betas, self.eps = float(learning_rate), betas, float(eps)
-        self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
+        self.comm = DataParallelComm(process_group)
+        self.world = self.comm.world
         self.dev = next(model.parameters()).device
         if self.dev.type != 'cuda':
             raise RuntimeError('FusedTrainStep needs the model on a CUDA device (no CPU path)')
@@ -199,15 +198,13 @@ class FusedTrainStep(object):
         return self.buf[name].view(-1)[:self.B * C * L].view(self.B, C, L)
 
     def _allreduce_stats(self):
-        torch.distributed.all_reduce(self.buf['stats'], group=self.pg)
+        self.comm.allreduce_stats(self.buf['stats'])
 
     def _allreduce_bucket(self, lo, hi):
-        self._works.append(torch.distributed.all_reduce(self.flat_g[lo:hi], group=self.pg, async_op=True))
+        self.comm.start_bucket(self.flat_g, lo, hi)
 
     def _wait_buckets(self):
-        for w in self._works:
-            w.wait()
-        self._works = []
+        self.comm.wait_buckets()
 
     def _emit_step(self):
         m, b, d = self.model, self.buf, self.dims
@@ -216,8 +213,6 @@ class FusedTrainStep(object):
         RS1, RS2 = '_residual_stack._layers.0._block.1.weight', '_residual_stack._layers.0._block.3.weight'
         P, G, WP, ws = self._p, self.grads, self.wperm, self.ws_wgrad
         nl = self.nl
-        self._works = []
-
         # ---- 0. weight re-arrangements for this step's dgrad / transposed-conv GEMMs ----
         for (name, role), (buf, tap, mode) in WP.items():
             if buf is not None:
@@ -273,7 +268,7 @@ class FusedTrainStep(object):
         if self.is_ema:
             if self.world > 1:
                 ops.record_callable(self._allreduce_stats)
-                n_rows_total = B * Tq * self.world
+                n_rows_total = self.comm.total_rows(B * Tq)
             ops.vq_ema_update(vq._ema_cluster_size, vq._ema_w.data, cb, b['stats'], vq._decay, vq._epsilon)
         beta = float(vq._commitment_cost)
         ops.vq_quantize(b['z'], b['idx'], cb, LAYOUT_BDT_AS_DTB, self.ws_vq, b['stats'][:K], n_rows_total, beta,
@@ -399,7 +394,7 @@ class FusedTrainStep(object):
         if self.world > 1:
             ops.record_callable(lambda: self._allreduce_bucket(0, self.bucket_split))
             ops.record_callable(self._wait_buckets)
-            g_scale = 1.0 / self.world
+            g_scale = self.comm.grad_scale
         ops.amsgrad_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, self.opt_step, self.lr,
                          self.betas[0], self.betas[1], self.eps, g_scale=g_scale)
 
