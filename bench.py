@@ -169,7 +169,7 @@ def run_reference(args):
         'e2e': {'value': r['value'], 'unit': 'utterances/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world, batch_override=None):
@@ -393,13 +393,30 @@ def run_b200(args):
         'ms_per_step_cuda_graph': graph_ms, 'kernel_breakdown': breakdown, 'vq': vq,
         'params': eng.n_params, 'flops_per_step': sum(flops_of(e) for e in eng.schedule if e[0] is not None),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (e.g. NCCL's version banner) was
+    redirected to stderr at start-up."""
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 if __name__ == '__main__':
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the duration of the run
     if a.impl == 'reference':
         run_reference(a)
     else:

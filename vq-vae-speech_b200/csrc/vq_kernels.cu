@@ -425,43 +425,93 @@ struct EwParams {
   FastDiv divD, divT;
 };
 
-template <bool BWD, bool SMEM_CB>
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Element-wise pass in the caller's memory order.  VEC = 4: each thread owns 4 consecutive floats (flat: 4 columns of one
+// row, one index load; (B, D, T): 4 consecutive t of one (b, d) run = 4 different rows).  The codebook sits in shared
+// memory with a row stride chosen per layout so that the gather is bank-conflict-free: D + 4 (16-byte aligned float4
+// reads) for flat rows, D + 1 for (B, D, T), where the lanes of a warp hit the same column of different codes (the
+// first build used stride D there: 32-way conflicts, 37 M conflict cycles per launch, profiles/r01c).
+template <bool BWD, bool SMEM_CB, bool FLAT, int VEC>
 __global__ void __launch_bounds__(256) vq_elementwise_kernel(const EwParams p) {
   extern __shared__ __align__(16) float cbs[];
   __shared__ double wred[8];
   const int D = p.D;
+  const int Dp = SMEM_CB ? (FLAT ? D + 4 : D + 1) : D;
   if (SMEM_CB) {
-    for (int i = threadIdx.x; i < p.K * D; i += 256) cbs[i] = __ldg(p.cb + i);
+    for (int i = threadIdx.x; i < p.K * D; i += 256) {
+      uint32_t k, j;
+      p.divD.divmod((uint32_t)i, k, j);
+      cbs[k * Dp + j] = __ldg(p.cb + i);
+    }
     __syncthreads();
   }
   const float* cb = SMEM_CB ? cbs : p.cb;
   float c = 0.f;
   if (BWD) c = p.gl[0] * p.coef;
   float sse = 0.f;
+  const long long nvec = p.total / VEC;
   const long long stride = (long long)gridDim.x * 256;
-  const bool flat = p.layout == VQS_LAYOUT_FLAT_ND;
   const int TB = p.T * p.B;
-  for (long long o = blockIdx.x * 256ll + threadIdx.x; o < p.total; o += stride) {
-    uint32_t row, j;
-    if (flat) {
+  for (long long iv = blockIdx.x * 256ll + threadIdx.x; iv < nvec; iv += stride) {
+    const long long o = iv * VEC;
+    float x[VEC], g[VEC], q[VEC], r[VEC];
+    if (VEC == 4) {
+      float4 xv = ldg_stream4(p.z + o);
+      x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
+      if (BWD) {
+        float4 gv = ldg_stream4(p.g + o);
+        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+      }
+    } else {
+      x[0] = __ldg(p.z + o);
+      if (BWD) g[0] = __ldg(p.g + o);
+    }
+    if (FLAT) {
+      uint32_t row, j;
       p.divD.divmod((uint32_t)o, row, j);
+      const int k = (int)__ldg(p.idx + row);
+      if (VEC == 4 && SMEM_CB) {
+        float4 qv = *reinterpret_cast<const float4*>(&cb[k * Dp + j]);
+        q[0] = qv.x; q[1] = qv.y; q[2] = qv.z; q[3] = qv.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) q[e] = SMEM_CB ? cb[k * Dp + j + e] : __ldg(cb + (size_t)k * D + j + e);
+      }
     } else {
       uint32_t bd, t, b, d;
       p.divT.divmod((uint32_t)o, bd, t);
       p.divD.divmod(bd, b, d);
-      uint32_t f = d * TB + t * p.B + b;
-      p.divD.divmod(f, row, j);
+      const uint32_t f0 = d * TB + t * p.B + b;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        uint32_t row, j;
+        p.divD.divmod(f0 + e * p.B, row, j);
+        const int k = (int)__ldg(p.idx + row);
+        q[e] = SMEM_CB ? cb[k * Dp + j] : __ldg(cb + (size_t)k * D + j);
+      }
     }
-    int k = (int)p.idx[row];
-    float q = SMEM_CB ? cb[k * D + j] : __ldg(cb + (size_t)k * D + j);
-    float x = p.z[o];
-    if (BWD) {
-      p.out[o] = fmaf(c, __fsub_rn(x, q), p.g[o]);
-    } else {
-      float df = __fsub_rn(q, x);
-      p.out[o] = __fadd_rn(x, df);  // inputs + (quantized - inputs).detach()  (ema.py:169)
-      sse = fmaf(df, df, sse);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      if (BWD) {
+        r[e] = fmaf(c, __fsub_rn(x[e], q[e]), g[e]);
+      } else {
+        float df = __fsub_rn(q[e], x[e]);
+        r[e] = __fadd_rn(x[e], df);  // inputs + (quantized - inputs).detach()  (ema.py:169)
+        sse = fmaf(df, df, sse);
+      }
     }
+    if (VEC == 4) stg_stream4(p.out + o, make_float4(r[0], r[1], r[2], r[3]));
+    else p.out[o] = r[0];
   }
   if (!BWD) {
     double s = warp_sum((double)sse);
@@ -681,27 +731,37 @@ extern "C" int vqs_vq_ema_update(float* cluster_size, float* ema_w, float* embed
   return 0;
 }
 
+template <bool BWD, bool SM, bool FLAT, int VEC>
+static int launch_ew_t(const EwParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kern = vq_elementwise_kernel<BWD, SM, FLAT, VEC>;
+  if (smem > 48 * 1024) VQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, 256, smem, st>>>(p);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool BWD, bool SM>
+static int launch_ew_2(const EwParams& p, bool flat, bool vec, int grid, size_t smem, cudaStream_t st) {
+  if (flat) return vec ? launch_ew_t<BWD, SM, true, 4>(p, grid, smem, st) : launch_ew_t<BWD, SM, true, 1>(p, grid, smem, st);
+  return vec ? launch_ew_t<BWD, SM, false, 4>(p, grid, smem, st) : launch_ew_t<BWD, SM, false, 1>(p, grid, smem, st);
+}
+
 static int launch_elementwise(bool bwd, EwParams& p, size_t cb_bytes, int& grid_out, cudaStream_t st) {
-  long long blocks = (p.total + 256 * 4 - 1) / (256 * 4);
+  const bool flat = p.layout == VQS_LAYOUT_FLAT_ND;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  // float4 path: 4 consecutive floats never leave a row (flat) or a (b, d) run (B, D, T)
+  const bool vec = al16(p.z) && al16(p.out) && (!bwd || al16(p.g)) && (flat ? (p.D % 4 == 0) : (p.T % 4 == 0));
+  const long long nvec = p.total / (vec ? 4 : 1);
+  long long blocks = (nvec + 256 * 4 - 1) / (256 * 4);
   int grid = (int)(blocks < EW_MAX_BLOCKS ? blocks : EW_MAX_BLOCKS);
   if (grid < 1) grid = 1;
   grid_out = grid;
-  const bool smem_cb = cb_bytes <= 96 * 1024;
-  size_t smem = smem_cb ? cb_bytes : 0;
-#define VQS_EW(BW, SM)                                                                                        \
-  {                                                                                                           \
-    auto kern = vq_elementwise_kernel<BW, SM>;                                                                \
-    if (smem > 48 * 1024) VQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, 256, smem, st>>>(p);                                                                         \
-  }
-  if (bwd) {
-    if (smem_cb) VQS_EW(true, true) else VQS_EW(true, false)
-  } else {
-    if (smem_cb) VQS_EW(false, true) else VQS_EW(false, false)
-  }
-#undef VQS_EW
-  VQS_LAUNCH_CHECK();
-  return 0;
+  const size_t padded = (size_t)p.K * (p.D + (flat ? 4 : 1)) * sizeof(float);
+  const bool sm = padded <= 96 * 1024;
+  const size_t smem = sm ? padded : 0;
+  (void)cb_bytes;
+  if (bwd) return sm ? launch_ew_2<true, true>(p, flat, vec, grid, smem, st) : launch_ew_2<true, false>(p, flat, vec, grid, smem, st);
+  return sm ? launch_ew_2<false, true>(p, flat, vec, grid, smem, st) : launch_ew_2<false, false>(p, flat, vec, grid, smem, st);
 }
 
 extern "C" int vqs_vq_quantize(const float* z, int layout, int B, int D, int T, const int64_t* idx,
