@@ -72,6 +72,13 @@ int vqs_vq_assign(const float* z, int layout, int B, int D, int T, const float* 
                   int64_t* idx, float* stats, float* dmin2, float* distances,
                   void* workspace, size_t workspace_bytes, vqs_stream_t stream);
 
+/* Search engine of vqs_vq_assign (process-wide): 1 = CUDA cores (default), 0 = tcgen05 tensor-core dot products (3xTF32)
+ * + exact fp32 re-check of near-ties when D is 32 or 64, the codebook fits shared memory and no distance outputs are
+ * requested (CUDA cores otherwise).  Both engines return identical indices and counts (tests/test_vq_gpu.py); on the
+ * B200 the tensor-core engine is currently the slower one at K = 44 (1.37 vs 1.24 ms for 2^22 rows: its per-code
+ * statistics pass, not the search, is the bottleneck -- DESIGN.md section 7), hence not the default. */
+int vqs_vq_set_engine(int engine);
+
 /* encodings = zeros(N, K).scatter_(1, idx, 1)  (vector_quantizer_ema.py:118-119). */
 int vqs_vq_one_hot(const int64_t* idx, long long N, int K, float* encodings, vqs_stream_t stream);
 

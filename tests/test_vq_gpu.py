@@ -261,3 +261,59 @@ def test_cpu_tensor_raises():
     vq = VectorQuantizerEMA(44, 64, 0.25, 0.99, 'cpu')
     with pytest.raises(RuntimeError):
         vq(torch.randn(2, 64, 24))
+
+
+TC_CASES = [  # (K, D, B, T, layout, data)
+    (44, 64, 2, 24, 'bdt', 'randn'), (44, 64, 64, 96, 'bdt', 'randn'), (44, 64, 256, 96, 'bdt', 'trained'),
+    (44, 64, 3, 17, 'bdt', 'randn'), (29, 64, 7, 33, 'bdt', 'trained'), (44, 64, 1, 100000, 'flat', 'randn'),
+    (256, 64, 16, 96, 'bdt', 'randn'), (100, 32, 9, 50, 'bdt', 'randn'), (64, 32, 4, 24, 'flat', 'trained'),
+    (44, 64, 8, 96, 'bdt', 'near_dup'), (1, 64, 2, 24, 'bdt', 'randn'), (44, 64, 1, 777, 'flat', 'near_dup'),
+]
+
+
+@pytest.mark.parametrize('K,D,B,T,lay,data', TC_CASES)
+def test_vq_tensor_core_engine_matches_cuda_core_engine(K, D, B, T, lay, data):
+    """The tcgen05 search (3xTF32 scores + exact fp32 re-check of near-ties) must return the SAME indices and counts as
+    the exact-fp32 CUDA-core search, including true ties and rows whose two best codes are almost equidistant, and both
+    must match the oracle outside fp64 near-ties."""
+    dev = _dev()
+    from vq_vae_speech_b200 import ops, LAYOUT_BDT_AS_DTB, LAYOUT_FLAT_ND
+    rng = np.random.RandomState(K + D + B + T)
+    W = rng.randn(K, D).astype(np.float32)
+    N = B * T
+    if data == 'near_dup' and K > 4:
+        W[K // 2] = W[1]                              # exact duplicate: lowest index must win
+        W[K - 1] = W[2] * (1 + 1e-7)                  # almost-duplicate: gap far below the TF32 score error
+        W[3] = W[2] + 1e-6 * rng.randn(D).astype(np.float32)
+    if data == 'randn':
+        rows = rng.randn(N, D).astype(np.float32)
+    else:
+        rows = (W[rng.randint(0, K, N)] + 0.1 * rng.randn(N, D)).astype(np.float32)
+    if lay == 'flat':
+        z, layout = _t(rows, dev), LAYOUT_FLAT_ND
+    else:
+        z, layout = _t(vqo.bdt_from_rows(rows, B, D, T), dev), LAYOUT_BDT_AS_DTB
+    Wd = _t(W, dev)
+    ws = ops.vq_workspace(K, D, dev)
+    try:
+        ops.vq_set_engine('cuda_core')
+        idx_cc, st_cc = ops.vq_assign(z, Wd, layout, ws)
+        idx_cc, st_cc = idx_cc.clone(), st_cc.clone()
+        ops.vq_set_engine('tensor_core')
+        idx_tc, st_tc = ops.vq_assign(z, Wd, layout, ws)
+    finally:
+        ops.vq_set_engine('cuda_core')
+    assert torch.equal(idx_tc, idx_cc), '%d rows differ between the engines' % int((idx_tc != idx_cc).sum())
+    assert torch.equal(st_tc[:K], st_cc[:K])
+    assert rel_err(st_tc[K:].cpu().numpy(), st_cc[K:].cpu().numpy()) < TOL
+    # vs the oracle: an fp32 evaluation of (|x|^2 + |e|^2) - 2 x.e resolves gaps down to ~1e-6 of its OPERANDS
+    # (|x|^2 + |e|^2), not of the (possibly tiny) distance -- the near-duplicate codes built above sit below that, so the
+    # near-tie exclusion is taken relative to the operand scale here
+    idx_o, near, gap_rel = vqo.assign(rows, W)
+    d64 = vqo.distances_fp64(rows, W)
+    part = np.partition(d64, 1, axis=1) if K > 1 else np.concatenate([d64, d64 + 1e9], 1)
+    scale = (rows.astype(np.float64) ** 2).sum(1) + (W.astype(np.float64) ** 2).sum(1).max()
+    near_fp32 = (part[:, 1] - part[:, 0]) < 1e-6 * scale
+    mism = idx_tc.cpu().numpy() != idx_o
+    assert not np.any(mism & ~(near | near_fp32))
+    assert float(st_tc[:K].sum()) == N

@@ -51,6 +51,7 @@ PROTOTYPES = {
     'vqs_vq_workspace_bytes': (c_size_t, [c_int, c_int]),
     'vqs_vq_assign': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_size_t, c_void_p]),
+    'vqs_vq_set_engine': (c_int, [c_int]),
     'vqs_vq_one_hot': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     'vqs_vq_ema_update': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int,
                                   c_int, c_void_p]),

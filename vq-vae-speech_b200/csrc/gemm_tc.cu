@@ -60,14 +60,6 @@ struct TcShared {
 // ---------------------------------------------------------------------------------------------------
 // producers
 // ---------------------------------------------------------------------------------------------------
-// Explicit shared-space stores on 32-bit addresses (generic-pointer stores compile to ST + 64-bit address arithmetic:
-// 128 generic ST and 420 IMAD in the first build's producer loop).
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 template <int PASSES>
 __device__ __forceinline__ void st_elem(uint32_t hi, uint32_t lo, float v) {
   if (PASSES == 3) {

@@ -648,11 +648,26 @@ int launch_assign(const AssignParams& p, const AssignPlan& pl, int& grid, cudaSt
 }  // namespace
 }  // namespace vqs
 
+namespace vqs {
+// vq_assign_tc.cu
+bool assign_tc_supported(int K, int D);
+int launch_assign_tc(const float* z, int layout, int B, int D, int T, const float* cb, int K, int64_t* idx,
+                     float* partials, int max_grid, int* grid_out, cudaStream_t st);
+static int g_vq_engine = 1;   // 1: CUDA-core search (default), 0: tensor-core search when supported
+}  // namespace vqs
+
 using namespace vqs;
+
+extern "C" int vqs_vq_set_engine(int engine) {
+  VQS_CHECK_ARG(engine == 0 || engine == 1, "vqs_vq_set_engine: engine must be 0 (auto) or 1 (CUDA cores)");
+  g_vq_engine = engine;
+  return 0;
+}
 
 static size_t partials_bytes(int K, int D) {
   AssignPlan pl;
-  if (!plan_assign(K, D, pl) || !pl.smem_stats) return 0;
+  const bool v1 = plan_assign(K, D, pl) && pl.smem_stats;
+  if (!v1 && !assign_tc_supported(K, D)) return 0;
   return align_up((size_t)4 * num_sms() * K * (D + 1) * sizeof(float), 256);  // <= 4 CTAs per SM
 }
 
@@ -678,6 +693,17 @@ extern "C" int vqs_vq_assign(const float* z, int layout, int B, int D, int T, co
   if (workspace_bytes < vqs_vq_workspace_bytes(K, D)) {
     set_error("vqs_vq_assign: workspace %zu < %zu", workspace_bytes, vqs_vq_workspace_bytes(K, D));
     return VQS_ERR_WORKSPACE;
+  }
+  if (g_vq_engine == 0 && dmin2 == nullptr && distances == nullptr && assign_tc_supported(K, D) &&
+      (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
+    // tensor-core search (tcgen05) + exact fp32 re-check: same indices and statistics as the CUDA-core search
+    int grid = 0;
+    if (int e = launch_assign_tc(z, layout, B, D, T, codebook, K, idx, (float*)workspace, 4 * num_sms(), &grid, st))
+      return e;
+    const int S = K * (D + 1);
+    stats_reduce_kernel<<<(S + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, S, stats);
+    VQS_LAUNCH_CHECK();
+    return 0;
   }
   AssignPlan pl;
   VQS_CHECK_ARG(plan_assign(K, D, pl), "vqs_vq_assign: embedding_dim %d too large for the shared-memory path", D);

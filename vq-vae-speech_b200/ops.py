@@ -111,6 +111,11 @@ def _pany(t):
 # ------------------------------------------------------------------------------------------------
 # VQ bottleneck
 # ------------------------------------------------------------------------------------------------
+def vq_set_engine(name):
+    """'cuda_core' (default) or 'tensor_core' / 'auto' (tcgen05 search + exact re-check where supported)."""
+    _lib.check(_lib.load().vqs_vq_set_engine({'auto': 0, 'tensor_core': 0, 'cuda_core': 1}[name]))
+
+
 def vq_workspace_bytes(K, D):
     return int(_lib.load().vqs_vq_workspace_bytes(K, D))
 
