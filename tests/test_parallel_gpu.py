@@ -35,7 +35,8 @@ def _worker(rank, world, port, ret):
         model, cfg = _build(g, dev)
         x = torch.from_numpy(np.concatenate([g['x0'], g['x1']], 0))
         eng = FusedTrainStep(model, x.shape[0] // world, x.shape[1], cfg['learning_rate'], precision='fp32')
-        assert eng.world == world and not eng.use_graph
+        assert eng.world == world
+        eng.use_graph = False          # gloo over CUDA tensors is not graph-capturable; NCCL (bench.py) is
         eng.step(eng.comm.shard(x))
         out = eng.losses()
         grads = {k: (v * eng.comm.grad_scale).cpu().numpy() for k, v in eng.gradients().items()}

@@ -362,8 +362,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
     __syncwarp();
   }
 
-  // ================= epilogue: warps 0-3, TMEM lane quarter = warp id =================
-  if (warp < 4) {
+  // ================= epilogue: every producer warp takes part =================
+  // TMEM lane quarter = warp % 4 (hardware rule); the BN/32 column blocks are spread over warp / 4, so the 16 producer
+  // warps drain a 128 x 128 tile four times faster than 4 warps could (the epilogue with residual / mask operands was a
+  // third of the dgrad kernels' time: 0.158 vs 0.103 ms for the same GEMM, profiles/r01j).
+  if (warp < N_PROD_WARPS && (warp >> 2) < BN / 32) {
+    const int q = warp & 3;                 // TMEM lane quarter -> rows m0 + 32 q .. + 31
     float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 33);  // stage buffers are idle by now
     if (nkb > 0) {
       mbar_wait(&sh->tmem_full, 0);
@@ -372,11 +376,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
     int Ncols;
     if constexpr (MODE == 0) Ncols = prm.p.Ntot;
     else Ncols = prm.p.Nw;
+    constexpr int BLK_STEP = N_PROD_WARPS / 4;
 #pragma unroll 1
-    for (int blk = 0; blk < BN / 32; ++blk) {
+    for (int blk = warp >> 2; blk < BN / 32; blk += BLK_STEP) {
       float v[32];
       if (nkb > 0) {
-        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(blk * 32);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 32);
         if (Cfg::NACC == 4) {
           float t1[32];
           tmem_ld32(ta + 1 * BN, v);
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
         const float bias_on = d.bias ? 1.f : 0.f;
 #pragma unroll 1
         for (int rb = 0; rb < 32; rb += 8) {
-          const int mb = m0 + warp * 32 + rb;
+          const int mb = m0 + q * 32 + rb;
           if (mb >= d.M) break;
           float x[8], pre[8], post[8];
           bool k1[8], k2[8];
@@ -446,7 +451,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
         float* out = prm.p.partial ? prm.p.partial + (size_t)blockIdx.z * d.M * prm.p.Nw : d.dW;
         const bool accum = (prm.p.partial == nullptr) && d.accumulate;
         for (int r = 0; r < 32; ++r) {
-          const int m = m0 + warp * 32 + r;
+          const int m = m0 + q * 32 + r;
           if (m >= d.M) break;
           if (!n_ok) continue;
           const size_t o = (size_t)m * prm.p.Nw + n;
@@ -512,8 +517,13 @@ int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
   TcParams<0> prm;
   prm.p = p;
   const int mt = (p.d.M + BM - 1) / BM;
-  // BN = 128 when that still gives every SM a tile, else 64 (twice the tiles)
-  int bn = ((long long)mt * ((p.Ntot + 127) / 128) >= num_sms() * 3 / 4) ? 128 : 64;
+  // BN in {128, 64}: one CTA per SM, so the launch costs ceil(tiles / SMs) waves; a 128 x 64 tile costs ~0.6 of a
+  // 128 x 128 one (same A operand, half the B operand and MMA work).  E.g. N = 3200: 150 tiles = 2 waves at BN = 128
+  // but 3 cheaper waves at BN = 64.
+  const long long sms = num_sms();
+  const long long t128 = (long long)mt * ((p.Ntot + 127) / 128), t64 = (long long)mt * ((p.Ntot + 63) / 64);
+  const double c128 = (double)((t128 + sms - 1) / sms), c64 = 0.6 * (double)((t64 + sms - 1) / sms);
+  int bn = (c128 <= c64) ? 128 : 64;
   dim3 grid((p.Ntot + bn - 1) / bn, mt, 1);
   return launch_tc<0>(prm, p.d.ksz, bn, precision, grid, st);
 }

@@ -66,7 +66,10 @@ class FusedTrainStep(object):
             ops.set_precision(prev_prec)
         self.n_launch_calls = sum(1 for f, _, _ in self.schedule if f is not None)
         self.graph = None
-        self.use_graph = bool(use_graph) and self.world == 1
+        # data parallel: the NCCL allreduces are captured into the graph too (torch.distributed supports capture); set
+        # VQS_DP_GRAPH=0 to replay launch by launch instead
+        import os
+        self.use_graph = bool(use_graph) and (self.world == 1 or os.environ.get('VQS_DP_GRAPH', '1') != '0')
         self.steps_done = 0
 
     # ------------------------------------------------------------------------------------------------
@@ -420,7 +423,17 @@ class FusedTrainStep(object):
             self._run_schedule()       # the first step always runs launch by launch (loads every kernel before capture)
         else:
             if self.graph is None:
-                self._capture()
+                try:
+                    self._capture()
+                except Exception as exc:       # e.g. a collective that cannot be captured: stay on launch-by-launch replay
+                    import warnings
+                    warnings.warn('CUDA-graph capture of the training step failed (%s); replaying launch by launch' % exc)
+                    self.use_graph = False
+                    self.graph = None
+                    torch.cuda.synchronize()
+                    self._run_schedule()
+                    self.steps_done += 1
+                    return
             self.graph.replay()
         self.steps_done += 1
 
