@@ -72,11 +72,13 @@ int vqs_vq_assign(const float* z, int layout, int B, int D, int T, const float* 
                   int64_t* idx, float* stats, float* dmin2, float* distances,
                   void* workspace, size_t workspace_bytes, vqs_stream_t stream);
 
-/* Search engine of vqs_vq_assign (process-wide): 1 = CUDA cores (default), 0 = tcgen05 tensor-core dot products (3xTF32)
- * + exact fp32 re-check of near-ties when D is 32 or 64, the codebook fits shared memory and no distance outputs are
- * requested (CUDA cores otherwise).  Both engines return identical indices and counts (tests/test_vq_gpu.py); on the
- * B200 the tensor-core engine is currently the slower one at K = 44 (1.37 vs 1.24 ms for 2^22 rows: its per-code
- * statistics pass, not the search, is the bottleneck -- DESIGN.md section 7), hence not the default. */
+/* Search engine of vqs_vq_assign (process-wide).  All engines return identical indices and counts (tests/test_vq_gpu.py).
+ *   1 = automatic (default): exact-fp32 CUDA-core search while the codebook is shared-memory resident (K = 10/29/44...:
+ *       HBM/FMA-bound, the tensor-core variant is not faster there: 0.96 vs 1.08 ms at 2^20 rows but slower at 2^22),
+ *       streamed tcgen05 distance GEMM (3xTF32 scores + exact fp32 settlement of near-ties) for large codebooks
+ *       (D = 32/64; K = 512: 1.9x, K = 4096: 4x faster than the CUDA-core search);
+ *   0 = tensor cores wherever a tensor-core kernel exists (also the resident-codebook one);
+ *   2 = CUDA cores only. */
 int vqs_vq_set_engine(int engine);
 
 /* encodings = zeros(N, K).scatter_(1, idx, 1)  (vector_quantizer_ema.py:118-119). */

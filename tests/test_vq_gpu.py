@@ -268,6 +268,12 @@ TC_CASES = [  # (K, D, B, T, layout, data)
     (44, 64, 3, 17, 'bdt', 'randn'), (29, 64, 7, 33, 'bdt', 'trained'), (44, 64, 1, 100000, 'flat', 'randn'),
     (256, 64, 16, 96, 'bdt', 'randn'), (100, 32, 9, 50, 'bdt', 'randn'), (64, 32, 4, 24, 'flat', 'trained'),
     (44, 64, 8, 96, 'bdt', 'near_dup'), (1, 64, 2, 24, 'bdt', 'randn'), (44, 64, 1, 777, 'flat', 'near_dup'),
+    # large codebooks: streamed tensor-core distance GEMM (vq_search_large_kernel)
+    (512, 64, 32, 96, 'bdt', 'randn'), (1000, 64, 8, 24, 'bdt', 'trained'), (4096, 64, 16, 96, 'bdt', 'randn'),
+    (4096, 64, 1, 5000, 'flat', 'near_dup'), (300, 32, 3, 50, 'bdt', 'randn'), (513, 64, 1, 129, 'flat', 'trained'),
+    # a few enormous codes (what the first EMA steps do to never-used codes): the per-code error bound must not
+    # push every row into the exact path, and indices must still agree
+    (44, 64, 8, 96, 'bdt', 'huge'), (4096, 64, 8, 96, 'bdt', 'huge'),
 ]
 
 
@@ -285,7 +291,9 @@ def test_vq_tensor_core_engine_matches_cuda_core_engine(K, D, B, T, lay, data):
         W[K // 2] = W[1]                              # exact duplicate: lowest index must win
         W[K - 1] = W[2] * (1 + 1e-7)                  # almost-duplicate: gap far below the TF32 score error
         W[3] = W[2] + 1e-6 * rng.randn(D).astype(np.float32)
-    if data == 'randn':
+    if data == 'huge':
+        W[K // 3: K // 3 + max(K // 8, 2)] *= 3e4
+    if data in ('randn', 'huge'):
         rows = rng.randn(N, D).astype(np.float32)
     else:
         rows = (W[rng.randint(0, K, N)] + 0.1 * rng.randn(N, D)).astype(np.float32)
@@ -302,7 +310,7 @@ def test_vq_tensor_core_engine_matches_cuda_core_engine(K, D, B, T, lay, data):
         ops.vq_set_engine('tensor_core')
         idx_tc, st_tc = ops.vq_assign(z, Wd, layout, ws)
     finally:
-        ops.vq_set_engine('cuda_core')
+        ops.vq_set_engine('auto')
     assert torch.equal(idx_tc, idx_cc), '%d rows differ between the engines' % int((idx_tc != idx_cc).sum())
     assert torch.equal(st_tc[:K], st_cc[:K])
     assert rel_err(st_tc[K:].cpu().numpy(), st_cc[K:].cpu().numpy()) < TOL

@@ -374,28 +374,44 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
   if (threadIdx.x == 0) db[m] = accumulate ? db[m] + red[0] : red[0];
 }
 
-__global__ void permute_weight_kernel(const float* __restrict__ w, int d0, int d1, int k, int mode,
-                                      float* __restrict__ out) {
-  const long long n = (long long)d0 * d1 * k;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int a, b, j;  // source element w[a][b][j]
-    if (mode == 0) {          // i indexes out[b][a][j]
-      j = (int)(i % k);
-      long long t = i / k;
-      a = (int)(t % d0);
-      b = (int)(t / d0);
-    } else if (mode == 1) {   // i indexes out[a][j][b]
-      b = (int)(i % d1);
-      long long t = i / d1;
-      j = (int)(t % k);
-      a = (int)(t / k);
-    } else {                  // i indexes out[b][j][a]
-      a = (int)(i % d0);
-      long long t = i / d0;
-      j = (int)(t % k);
-      b = (int)(t / k);
+// Weight re-arrangement through a 32 x 32 x k shared-memory tile: global reads and writes are both contiguous runs
+// (the first version read with stride d1*k in modes 0/2: 13.7 us per 7 MB weight, 8 % of the training step).
+//   w[a][b][j]  ->  mode 0: out[b][a][j]   mode 1: out[a][j][b]   mode 2: out[b][j][a]
+template <int KS>
+__global__ void __launch_bounds__(256) permute_weight_kernel(const float* __restrict__ w, int d0, int d1, int mode,
+                                                             float* __restrict__ out) {
+  constexpr int ROW = 32 * KS + 1;
+  __shared__ float tile[32 * ROW];
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  // load: for each a, the 32*KS contiguous floats w[a][b0 .. b0+31][*]
+  for (int i = tid; i < 32 * 32 * KS; i += 256) {
+    const int ar = i / (32 * KS), rem = i - ar * (32 * KS);
+    const int a = a0 + ar, b = b0 + rem / KS;
+    tile[ar * ROW + rem] = (a < d0 && b < d1) ? w[((size_t)a * d1 + b0) * KS + rem] : 0.f;
+  }
+  __syncthreads();
+  if (mode == 0) {          // out[b][a][j]: for each b, 32*KS contiguous floats over (a, j)
+    for (int i = tid; i < 32 * 32 * KS; i += 256) {
+      const int br = i / (32 * KS), rem = i - br * (32 * KS);
+      const int ar = rem / KS, j = rem - ar * KS;
+      const int a = a0 + ar, b = b0 + br;
+      if (a < d0 && b < d1) out[((size_t)b * d0 + a0) * KS + rem] = tile[ar * ROW + br * KS + j];
     }
-    out[i] = w[((size_t)a * d1 + b) * k + j];
+  } else if (mode == 1) {   // out[a][j][b]: for each (a, j), 32 contiguous b
+    for (int i = tid; i < 32 * 32 * KS; i += 256) {
+      const int br = i & 31, t = i >> 5;
+      const int j = t % KS, ar = t / KS;
+      const int a = a0 + ar, b = b0 + br;
+      if (a < d0 && b < d1) out[((size_t)a * KS + j) * d1 + b] = tile[ar * ROW + br * KS + j];
+    }
+  } else {                  // out[b][j][a]: for each (b, j), 32 contiguous a
+    for (int i = tid; i < 32 * 32 * KS; i += 256) {
+      const int ar = i & 31, t = i >> 5;
+      const int j = t % KS, br = t / KS;
+      const int a = a0 + ar, b = b0 + br;
+      if (a < d0 && b < d1) out[((size_t)b * KS + j) * d0 + a] = tile[ar * ROW + br * KS + j];
+    }
   }
 }
 
@@ -484,11 +500,16 @@ extern "C" int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int
 }
 
 extern "C" int vqs_permute_weight(const float* w, int d0, int d1, int k, int mode, float* out, vqs_stream_t stream) {
-  VQS_CHECK_ARG(w && out && d0 > 0 && d1 > 0 && k > 0 && mode >= 0 && mode <= 2, "vqs_permute_weight: bad arguments");
-  long long n = (long long)d0 * d1 * k;
-  long long blocks = (n + 255) / 256;
-  permute_weight_kernel<<<(int)(blocks < 8 * num_sms() ? blocks : 8 * num_sms()), 256, 0, (cudaStream_t)stream>>>(
-      w, d0, d1, k, mode, out);
+  VQS_CHECK_ARG(w && out && d0 > 0 && d1 > 0 && k >= 1 && k <= 4 && mode >= 0 && mode <= 2,
+                "vqs_permute_weight: bad arguments (kernel size 1..4, mode 0..2)");
+  dim3 grid((d1 + 31) / 32, (d0 + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (k) {
+    case 1: permute_weight_kernel<1><<<grid, 256, 0, st>>>(w, d0, d1, mode, out); break;
+    case 2: permute_weight_kernel<2><<<grid, 256, 0, st>>>(w, d0, d1, mode, out); break;
+    case 3: permute_weight_kernel<3><<<grid, 256, 0, st>>>(w, d0, d1, mode, out); break;
+    default: permute_weight_kernel<4><<<grid, 256, 0, st>>>(w, d0, d1, mode, out); break;
+  }
   VQS_LAUNCH_CHECK();
   return 0;
 }

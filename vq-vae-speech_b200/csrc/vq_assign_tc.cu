@@ -42,6 +42,14 @@ struct AssignTcParams {
 namespace {
 
 constexpr int TROWS = 128;
+// Score error bound.  With tau_k = EPS_SCORE * (|x|^2 + |e_k|^2) the tensor-core score s_k = |e_k|^2 - 2 x.e_k satisfies
+// |s_k + |x|^2 - d_k| <= tau_k, d_k being the fp32 distance of the exact path: 3xTF32 operand error 2 * 3 * 2^-20 |x||e_k|
+// plus truncating accumulation over 24 MMAs 2 * 24 * 2^-23 |x||e_k| (together < 1.2e-5 |x||e_k| <= 0.6e-5 (|x|^2+|e_k|^2))
+// plus the rounding of the fp32 formula itself (~66 * 2^-24 (|x|^2 + |e_k|^2) < 0.4e-5 ...), with margin.  The scan ranks
+// the LOWER bounds adj_k = s_k - EPS_SCORE |e_k|^2; the best code b is certainly the fp32 argmin when
+// adj_second - adj_b > 2 EPS_SCORE (|x|^2 + |e_b|^2).  The bound is per code, so a few huge (e.g. never-used EMA) codes
+// do not inflate it for everybody.
+constexpr float EPS_SCORE = 1.6e-5f;
 constexpr int XT_BYTES = TROWS * 128;     // one [128 rows x 32 floats] k-block tile
 constexpr int STAGES = 2;
 constexpr int PROD_WARPS = 8;
@@ -171,7 +179,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_assign_tc_kernel(const AssignT
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
-  const float emax = sh->emax;
 
   const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -406,8 +413,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_assign_tc_kernel(const AssignT
         tmem_ld16(ta + (uint32_t)c0, v);
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float sa = fmaf(-2.f, v[j], se[c0 + j]);
-          const float sb = fmaf(-2.f, v[j + 1], se[c0 + j + 1]);
+          const float sa = fmaf(-2.f, v[j], se[c0 + j] * (1.f - EPS_SCORE));
+          const float sb = fmaf(-2.f, v[j + 1], se[c0 + j + 1] * (1.f - EPS_SCORE));
           if (sa < b0) { s0 = b0; b0 = sa; k0 = c0 + j; } else if (sa < s0) { s0 = sa; }
           if (sb < b1) { s1 = b1; b1 = sb; k1 = c0 + j + 1; } else if (sb < s1) { s1 = sb; }
         }
@@ -436,11 +443,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_assign_tc_kernel(const AssignT
         }
       }
       sx *= 1.01f;
-      // ---- bound on |score - fp32 distance|:  3xTF32 operand error 2 * 3 * 2^-20 |x||e| + truncating accumulation over
-      // 24 MMAs 2 * 24 * 2^-23 |x||e|  (together < 1.2e-5 |x||e|), plus the rounding of the fp32 formula itself
-      // (~66 * 2^-24 (|x|^2 + |e|^2)); both with margin.  Scores closer than 2*tol are re-checked exactly. ----
-      const float tol = sqrtf(sx) * emax * 1.5e-5f + (sx + emax * emax) * 6e-6f;
-      const bool flagged = (p.debug & 2) ? false : !((second - best) > 2.f * tol);
+      const bool flagged = (p.debug & 2) ? false : !((second - best) > 2.f * EPS_SCORE * (sx + se[bkm]));
       // ---- exact re-check by the whole warp, same fp32 formula and order as the CUDA-core kernel ----
       unsigned m = __ballot_sync(0xffffffffu, flagged);
       while (m) {
@@ -539,6 +542,485 @@ int launch_assign_tc(const float* z, int layout, int B, int D, int T, const floa
   *grid_out = grid;
   vq_assign_tc_kernel<<<grid, NTHREADS, smem, st>>>(p);
   VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vqs
+
+// =====================================================================================================================
+// Large codebooks (K > what fits shared memory, e.g. the 512 / 4096-code sweep): the distance search is a real GEMM
+// N x 64 . 64 x K.  One CTA = one 128-row tile that stays resident in shared memory (hi/lo split) while the codebook is
+// streamed past it in 128-code chunks (pre-split hi/lo copies in global memory, cp.async into a 2-stage ring), 24 tf32
+// MMAs per chunk into one of two TMEM accumulators; 8 scan warps keep a running top-3 of the scores per row.  Rows whose
+// best and second-best scores are closer than 2*tol are settled exactly in fp32 (top-2 when the third is far, a full
+// scan otherwise), so indices equal the fp32 search.  Statistics go straight to global memory with atomics (contention
+// is low at large K), as in the CUDA-core kernel.
+// =====================================================================================================================
+namespace vqs {
+
+struct SearchLargeParams {
+  const float* z;
+  const float* cb;      // exact codebook (K, D)
+  const float* img;     // per-chunk shared-memory images of the split codebook (cb_prep_kernel)
+  const float* se;      // |e|^2, nchunks*128 entries (+inf beyond K)
+  int64_t* idx;
+  float* stats;         // [counts | dw], zeroed by the launcher
+  long long N;
+  int layout, B, D, T, K;
+  int nkb, nchunks, ntiles;
+  int debug;            // profiling aid (env VQS_TC_DEBUG): bit 3 skips the score scan, bit 4 the TMEM loads as well
+  float* dbg;           // [2] debug counters: rows settled by the top-2 check / by a full exact scan
+  FastDiv divD;
+};
+
+namespace {
+
+constexpr int L_SCAN_WARPS = 8, L_PROD_WARPS = 8;
+constexpr int L_PROD_THREADS = L_PROD_WARPS * 32;
+constexpr int L_MMA_WARP = L_SCAN_WARPS + L_PROD_WARPS;
+constexpr int L_THREADS = (L_MMA_WARP + 1) * 32;
+constexpr int CHUNK = 128;    // codes per streamed chunk (UMMA N)
+constexpr int BSTAGES = 2;    // chunk ring depth
+constexpr int TBUF = 2;       // TMEM accumulators (CHUNK columns each)
+#ifndef VQS_LARGE_CLUSTER
+#define VQS_LARGE_CLUSTER 1
+#endif
+constexpr int CLUSTER = VQS_LARGE_CLUSTER;   // CTAs that share every codebook chunk through a multicast bulk copy (L2 reads / CLUSTER)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// tcgen05.commit that arrives on the barrier at the same shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+struct LShared {
+  uint64_t a_full, b_full[BSTAGES], b_empty[BSTAGES], tmem_full[TBUF], tmem_empty[TBUF];
+  uint32_t tmem_base;
+};
+
+// Pre-splits the codebook and lays every 128-code chunk out as the exact shared-memory image the MMAs read
+// ([hi | lo] x [k-block] x [128 rows x 128 B, SWIZZLE_128B]), so that a chunk is ONE contiguous block in global memory
+// and a single thread can stream it with cp.async.bulk (TMA bulk copy, completion on an mbarrier) -- 4096 16-byte
+// cp.async per chunk gave 10 B/clk/SM.  Also |e_k|^2 (fp32, sequential order = the exact path's) and +inf padding.
+__global__ void cb_prep_kernel(const float* __restrict__ cb, int K, int D, int Kpad, float* __restrict__ img,
+                               float* __restrict__ se) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kpad) return;
+  const int nkb = D / 32;
+  const int copy_floats = nkb * CHUNK * 32;            // floats per copy of one chunk
+  float* chunk = img + (size_t)(k / CHUNK) * 2 * copy_floats;
+  const int row = k % CHUNK;
+  float s = 0.f;
+  for (int j = 0; j < D; ++j) {
+    const float v = (k < K) ? cb[(size_t)k * D + j] : 0.f;
+    const float h = tf32_hi(v);
+    const uint32_t off = elem_off(row, j, CHUNK) >> 2;
+    chunk[off] = h;
+    chunk[copy_floats + off] = v - h;
+    s = fmaf(v, v, s);
+  }
+  se[k] = (k < K) ? s : INFINITY;
+}
+
+struct Top3 {
+  float b, s, t;
+  int kb, ks;
+};
+// Almost every score is NOT among the three smallest seen so far (after 1000 codes fewer than 1 in 300 is), so the common
+// path is one compare and a branch the whole warp skips; the update itself is branch-free selects.
+__device__ __forceinline__ void top3_push(Top3& a, float sc, int k) {
+  if (sc < a.t) {
+    const bool lb = sc < a.b, ls = sc < a.s;
+    a.t = ls ? a.s : sc;
+    a.s = lb ? a.b : (ls ? sc : a.s);
+    a.ks = lb ? a.kb : (ls ? k : a.ks);
+    a.b = lb ? sc : a.b;
+    a.kb = lb ? k : a.kb;
+  }
+}
+
+__device__ __forceinline__ float exact_dist(const uint8_t* xh, const uint8_t* xl, int R, const float* __restrict__ e,
+                                            float sx, float sek, int D) {
+  float dot = 0.f;
+  for (int j = 0; j < D; ++j) dot = fmaf(ld_exact(xh, xl, elem_off(R, j, TROWS)), __ldg(e + j), dot);
+  return __fsub_rn(__fadd_rn(sx, sek), __fmul_rn(2.0f, dot));
+}
+
+__global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const SearchLargeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = p.D, K = p.K, nkb = p.nkb;
+  const int a_copy = nkb * XT_BYTES;                 // one copy (hi or lo) of the row tile / of a code chunk
+  uint8_t* xa = smem;                                 // [hi | lo]
+  uint8_t* bring = smem + 2 * a_copy;                 // BSTAGES x [hi | lo] chunk images
+  const int b_copy = nkb * CHUNK * 128;
+  const int b_stage = 2 * b_copy;
+  float* se_s = reinterpret_cast<float*>(bring + BSTAGES * b_stage);   // [nchunks*CHUNK]
+  float* mrg = se_s + p.nchunks * CHUNK;                          // [128][6] merge buffer of the upper column half
+  int* sidx = reinterpret_cast<int*>(mrg + TROWS * 6);           // [128]
+  LShared* sh = reinterpret_cast<LShared*>(sidx + TROWS);
+
+  if (tid == 0) {
+    mbar_init(&sh->a_full, L_PROD_WARPS);
+    for (int s = 0; s < BSTAGES; ++s) {
+      mbar_init(&sh->b_full[s], 1);
+      mbar_init(&sh->b_empty[s], CLUSTER);          // every CTA of the cluster has consumed the stage
+    }
+    for (int s = 0; s < TBUF; ++s) {
+      mbar_init(&sh->tmem_full[s], 1);
+      mbar_init(&sh->tmem_empty[s], L_SCAN_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == L_MMA_WARP) tmem_alloc(&sh->tmem_base, TBUF * CHUNK);
+  for (int i = tid; i < p.nchunks * CHUNK; i += L_THREADS) se_s[i] = __ldg(p.se + i);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // remote CTAs multicast into this CTA's ring and arrive on its barriers: all must be initialised
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+  const int tile = blockIdx.x;
+  const long long r0 = (long long)tile * TROWS;
+  const long long left = p.N - r0;
+  const int rows = left < 0 ? 0 : (left < TROWS ? (int)left : TROWS);   // padding CTAs of the last cluster own no rows
+  const uint8_t* xh = xa;
+  const uint8_t* xl = xa + a_copy;
+
+  if (warp >= L_SCAN_WARPS && warp < L_MMA_WARP) {
+    // ================= producers =================
+    const int ptid = tid - L_SCAN_WARPS * 32;
+    const uint32_t xh_a = smem_u32(xa), xl_a = xh_a + (uint32_t)a_copy;
+    // ---- the row tile (once) ----
+    for (int e = ptid; e < (TROWS - rows) * D; e += L_PROD_THREADS) {   // zero tail rows
+      uint32_t r, j;
+      p.divD.divmod((uint32_t)e, r, j);
+      const uint32_t off = elem_off(rows + (int)r, (int)j, TROWS);
+      sts_f32(xh_a + off, 0.f);
+      sts_f32(xl_a + off, 0.f);
+    }
+    if (p.layout == VQS_LAYOUT_FLAT_ND) {
+      const int cpr = D >> 2;
+      const float4* src = reinterpret_cast<const float4*>(p.z + r0 * D);
+      const int total = rows * cpr;
+      for (int c0 = ptid; c0 < total; c0 += L_PROD_THREADS * 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * L_PROD_THREADS;
+          v[u] = (c < total) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * L_PROD_THREADS;
+          if (c < total) {
+            const uint32_t row = p.divD.div((uint32_t)c << 2);
+            const int c16 = c - (int)row * cpr;
+            const uint32_t off = (uint32_t)((c16 >> 3) * XT_BYTES + row * 128 + (((c16 & 7) ^ (row & 7)) << 4));
+            const float4 h = make_float4(tf32_hi(v[u].x), tf32_hi(v[u].y), tf32_hi(v[u].z), tf32_hi(v[u].w));
+            sts_v4(xh_a + off, h);
+            sts_v4(xl_a + off, make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w));
+          }
+        }
+      }
+    } else if (rows > 0) {
+      const int B = p.B, T = p.T;
+      const long long P = (long long)T * B;
+      const long long f0 = r0 * D;
+      const long long f1 = f0 + (long long)rows * D;
+      const long long d_first = f0 / P, d_last = (f1 - 1) / P;
+      for (long long d = d_first; d <= d_last; ++d) {
+        const long long base = d * P;
+        const int p0 = (int)((f0 > base ? f0 : base) - base);
+        const int p1 = (int)((f1 < base + P ? f1 : base + P) - base);
+        const int t0 = p0 / B, t1 = (p1 + B - 1) / B;
+        const int span = t1 - t0, count = span * B;
+        const int qs = L_PROD_THREADS / span, rs = L_PROD_THREADS - qs * span;
+        int b = ptid / span, tt = ptid - b * span;
+        const int foff = (int)(base - f0);
+        const float* zd = p.z + (size_t)d * T;
+        for (int e = ptid; e < count; e += L_PROD_THREADS * 8) {
+          float v[8];
+          uint32_t off[8];
+          bool ok[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int t = t0 + tt;
+            const int pp = t * B + b;
+            ok[u] = (e + u * L_PROD_THREADS < count) && pp >= p0 && pp < p1;
+            v[u] = ok[u] ? __ldg(zd + (size_t)b * D * T + t) : 0.f;
+            uint32_t row, j;
+            p.divD.divmod((uint32_t)(foff + pp), row, j);
+            off[u] = elem_off((int)row, (int)j, TROWS);
+            tt += rs;
+            b += qs;
+            if (tt >= span) {
+              tt -= span;
+              ++b;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (ok[u]) {
+              const float h = tf32_hi(v[u]);
+              sts_f32(xh_a + off[u], h);
+              sts_f32(xl_a + off[u], v[u] - h);
+            }
+          }
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sh->a_full);
+    // ---- code chunks: one thread streams the pre-built chunk images with TMA bulk copies, two chunks in flight ----
+    if (ptid == 0) {
+      const uint32_t ring_a = smem_u32(bring);
+      const uint32_t chunk_bytes = (uint32_t)b_stage;
+      const uint32_t crank = cluster_ctarank();
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int s = c % BSTAGES;
+        mbar_wait(&sh->b_empty[s], ((uint32_t)(c / BSTAGES) & 1u) ^ 1u);
+        const uint32_t bar = smem_u32(&sh->b_full[s]);
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
+                     "r"(chunk_bytes)
+                     : "memory");
+        // this CTA fetches 1/CLUSTER of the chunk and multicasts it to every CTA of the cluster (same smem offset, each
+        // CTA's own b_full barrier at the same offset receives the complete_tx)
+        const uint32_t share = chunk_bytes / CLUSTER;
+        const uint32_t o0 = crank * share;
+        const char* src = reinterpret_cast<const char*>(p.img) + (size_t)c * chunk_bytes + o0;
+        const uint32_t dst = ring_a + (uint32_t)(s * b_stage) + o0;
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+            ::"r"(dst), "l"(src), "r"(share), "r"(bar), "h"((uint16_t)((1u << CLUSTER) - 1))
+            : "memory");
+      }
+    }
+  } else if (warp == L_MMA_WARP) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(CHUNK);
+      const uint32_t xh_a = smem_u32(xa), xl_a = xh_a + (uint32_t)a_copy;
+      mbar_wait(&sh->a_full, 0);
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int s = c % BSTAGES, a = c % TBUF;
+        mbar_wait(&sh->b_full[s], (uint32_t)(c / BSTAGES) & 1u);
+        mbar_wait(&sh->tmem_empty[a], ((uint32_t)(c / TBUF) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t bh_a = smem_u32(bring) + (uint32_t)(s * b_stage), bl_a = bh_a + (uint32_t)b_copy;
+        const uint32_t dst = tmem_base + (uint32_t)(a * CHUNK);
+        uint32_t acc = 0u;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint64_t ah = make_desc_sw128(xh_a + kb * XT_BYTES), al = make_desc_sw128(xl_a + kb * XT_BYTES);
+          const uint64_t bh = make_desc_sw128(bh_a + kb * CHUNK * 128), bl = make_desc_sw128(bl_a + kb * CHUNK * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            umma_tf32(dst, al + adv, bh + adv, idesc, acc);
+            umma_tf32(dst, ah + adv, bl + adv, idesc, 1u);
+            umma_tf32(dst, ah + adv, bh + adv, idesc, 1u);
+            acc = 1u;
+          }
+        }
+        umma_commit_multicast(&sh->b_empty[s], (uint16_t)((1u << CLUSTER) - 1));   // stage consumed, tell every CTA
+        umma_commit(&sh->tmem_full[a]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= scan warps: running top-3 per row over the chunks =================
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+    Top3 top;
+    top.b = top.s = top.t = INFINITY;
+    top.kb = top.ks = 0;
+    for (int c = 0; c < p.nchunks; ++c) {
+      const int a = c % TBUF;
+      mbar_wait(&sh->tmem_full[a], (uint32_t)(c / TBUF) & 1u);
+      tc_fence_after();
+      // this warp's share of the chunk: lane quarter q, columns [half * CHUNK/2, (half + 1) * CHUNK/2)
+      float v[CHUNK / 2];
+#pragma unroll
+      for (int h2 = 0; h2 < CHUNK / 64; ++h2) {
+        float t[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * CHUNK + half * (CHUNK / 2) + h2 * 32), t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[h2 * 32 + j] = t[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->tmem_empty[a]);      // scores are in registers: the accumulator is free again
+      const int kbase = c * CHUNK + half * (CHUNK / 2);
+#pragma unroll
+      for (int j = 0; j < CHUNK / 2; ++j)
+        top3_push(top, fmaf(-2.f, v[j], se_s[kbase + j] * (1.f - EPS_SCORE)), kbase + j);
+    }
+    // ---- merge the two column halves (ties need no care here: equal scores are re-checked exactly) ----
+    if (half == 1) {
+      float* m = mrg + r * 6;
+      m[0] = top.b; m[1] = top.s; m[2] = top.t;
+      m[3] = __int_as_float(top.kb); m[4] = __int_as_float(top.ks);
+    }
+    named_bar_sync(1, L_SCAN_WARPS * 32);
+    if (half == 0) {
+      const float* m = mrg + r * 6;
+      top3_push(top, m[0], __float_as_int(m[3]));
+      top3_push(top, m[1], __float_as_int(m[4]));
+      top3_push(top, m[2], 0);   // only its value matters (third place)
+      // ---- |x|^2 for the bound (hi copy, rotated conflict-free read) ----
+      float sx = 0.f;
+      for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pc = (r + i) & 7;
+          const float4 h = *reinterpret_cast<const float4*>(xh + kb * XT_BYTES + r * 128 + (pc << 4));
+          sx = fmaf(h.x, h.x, sx);
+          sx = fmaf(h.y, h.y, sx);
+          sx = fmaf(h.z, h.z, sx);
+          sx = fmaf(h.w, h.w, sx);
+        }
+      }
+      sx *= 1.01f;
+      const float tol2 = 2.f * EPS_SCORE * (sx + se_s[top.kb]);
+      int bk = top.kb;
+      const bool close2 = !((top.s - top.b) > tol2);
+      const bool close3 = !((top.t - top.b) > tol2);
+      if (close2 && !close3) {        // exactly two candidates: settle them in fp32 (lowest index on a tie)
+        atomicAdd(p.dbg, 1.f);
+        const float sxr = row_sumsq(xh, xl, r, D);
+        const float d1 = exact_dist(xh, xl, r, p.cb + (size_t)top.kb * D, sxr, se_s[top.kb], D);
+        const float d2 = exact_dist(xh, xl, r, p.cb + (size_t)top.ks * D, sxr, se_s[top.ks], D);
+        if (d2 < d1 || (d2 == d1 && top.ks < top.kb)) bk = top.ks;
+      }
+      // three or more candidates: exact scan over the whole codebook by the warp
+      unsigned mk = __ballot_sync(0xffffffffu, close2 && close3);
+      while (mk) {
+        const int rr = __ffs(mk) - 1;
+        mk &= mk - 1;
+        const int R = q * 32 + rr;
+        if (lane == 0) atomicAdd(p.dbg + 1, 1.f);
+        const float sxr = row_sumsq(xh, xl, R, D);
+        float bd = INFINITY;
+        int bkk = 0x7fffffff;
+        for (int k = lane; k < K; k += 32) {
+          const float dd = exact_dist(xh, xl, R, p.cb + (size_t)k * D, sxr, se_s[k], D);
+          if (dd < bd) {
+            bd = dd;
+            bkk = k;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+          const int ok = __shfl_xor_sync(0xffffffffu, bkk, o);
+          if (od < bd || (od == bd && ok < bkk)) {
+            bd = od;
+            bkk = ok;
+          }
+        }
+        if (lane == rr) bk = bkk < K ? bkk : K - 1;
+      }
+      sidx[r] = bk;
+      if (r < rows) p.idx[r0 + r] = (int64_t)bk;
+    }
+    named_bar_sync(1, L_SCAN_WARPS * 32);
+    // ---- statistics: global atomics (low contention at large K) ----
+    const int st = tid;   // 256 scan threads
+    for (int e = st; e < rows * D; e += L_SCAN_WARPS * 32) {
+      uint32_t R, j;
+      p.divD.divmod((uint32_t)e, R, j);
+      atomicAdd(p.stats + K + (size_t)sidx[R] * D + j, ld_exact(xh, xl, elem_off((int)R, (int)j, TROWS)));
+    }
+    for (int R = st; R < rows; R += L_SCAN_WARPS * 32) atomicAdd(p.stats + sidx[R], 1.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA may exit while a sibling can still multicast into it or arrive on its barriers
+  if (warp == L_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TBUF * CHUNK);
+  }
+}
+
+}  // namespace
+
+bool search_large_supported(int K, int D) { return (D == 32 || D == 64) && K >= 1 && K <= 8192; }
+
+size_t search_large_workspace_bytes(int K, int D) {
+  const int nchunks = (K + CHUNK - 1) / CHUNK;
+  return ((size_t)nchunks * 2 * CHUNK * D + (size_t)nchunks * CHUNK + 8) * sizeof(float);
+}
+
+int launch_search_large(const float* z, int layout, int B, int D, int T, const float* cb, int K, int64_t* idx,
+                        float* stats, void* workspace, cudaStream_t st) {
+  SearchLargeParams p;
+  const int nchunks = (K + CHUNK - 1) / CHUNK;
+  float* img = (float*)workspace;
+  float* se = img + (size_t)nchunks * 2 * CHUNK * D;
+  p.z = z; p.cb = cb; p.img = img; p.se = se; p.idx = idx; p.stats = stats;
+  p.N = (long long)B * T;
+  p.layout = layout; p.B = B; p.D = D; p.T = T; p.K = K;
+  p.nkb = D / 32;
+  p.nchunks = nchunks;
+  p.ntiles = (int)((p.N + TROWS - 1) / TROWS);
+  p.divD = FastDiv((uint32_t)D);
+  p.dbg = se + (size_t)nchunks * CHUNK + 2;
+  {
+    const char* dbg = getenv("VQS_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  VQS_CUDA(cudaMemsetAsync(se + (size_t)nchunks * CHUNK, 0, 8 * sizeof(float), st));
+  VQS_CUDA(cudaMemsetAsync(stats, 0, (size_t)K * (D + 1) * sizeof(float), st));
+  cb_prep_kernel<<<(nchunks * CHUNK + 127) / 128, 128, 0, st>>>(cb, K, D, nchunks * CHUNK, img, se);
+  VQS_LAUNCH_CHECK();
+  const int a_copy = p.nkb * XT_BYTES;
+  const size_t smem = (size_t)2 * a_copy + (size_t)BSTAGES * 2 * p.nkb * CHUNK * 128 +
+                      ((size_t)nchunks * CHUNK + TROWS * 6 + TROWS) * 4 + sizeof(LShared) + 1024 + 64;
+  if (smem > 226 * 1024) {
+    set_error("vq_search_large: codebook of %d codes needs %zu bytes of shared memory", K, smem);
+    return VQS_ERR_ARG;
+  }
+  static size_t configured = 0;
+  if (smem > configured) {
+    VQS_CUDA(cudaFuncSetAttribute(vq_search_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((p.ntiles + CLUSTER - 1) / CLUSTER * CLUSTER));
+    cfg.blockDim = dim3(L_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VQS_CUDA(cudaLaunchKernelEx(&cfg, vq_search_large_kernel, p));
+  }
+  VQS_LAUNCH_CHECK();
+  {
+    const char* dbg = getenv("VQS_TC_DEBUG");
+    if (dbg && (atoi(dbg) & 4)) {   // profiling aid: how many rows needed the exact paths (synchronises!)
+      float h[2] = {0.f, 0.f};
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[vq_search_large] N=%lld K=%d: top-2 settlements %.0f, full exact scans %.0f\n", p.N, K, h[0], h[1]);
+    }
+  }
   return 0;
 }
 

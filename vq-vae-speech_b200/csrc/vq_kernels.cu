@@ -653,13 +653,17 @@ namespace vqs {
 bool assign_tc_supported(int K, int D);
 int launch_assign_tc(const float* z, int layout, int B, int D, int T, const float* cb, int K, int64_t* idx,
                      float* partials, int max_grid, int* grid_out, cudaStream_t st);
-static int g_vq_engine = 1;   // 1: CUDA-core search (default), 0: tensor-core search when supported
+bool search_large_supported(int K, int D);
+size_t search_large_workspace_bytes(int K, int D);
+int launch_search_large(const float* z, int layout, int B, int D, int T, const float* cb, int K, int64_t* idx,
+                        float* stats, void* workspace, cudaStream_t st);
+static int g_vq_engine = 1;   // 0: tensor cores wherever supported, 1: auto (default), 2: CUDA cores only
 }  // namespace vqs
 
 using namespace vqs;
 
 extern "C" int vqs_vq_set_engine(int engine) {
-  VQS_CHECK_ARG(engine == 0 || engine == 1, "vqs_vq_set_engine: engine must be 0 (auto) or 1 (CUDA cores)");
+  VQS_CHECK_ARG(engine >= 0 && engine <= 2, "vqs_vq_set_engine: engine must be 0 (tensor cores), 1 (auto) or 2 (CUDA cores)");
   g_vq_engine = engine;
   return 0;
 }
@@ -673,7 +677,12 @@ static size_t partials_bytes(int K, int D) {
 
 extern "C" size_t vqs_vq_workspace_bytes(int K, int D) {
   if (K <= 0 || D <= 0) return 0;
-  return partials_bytes(K, D) + align_up((size_t)EW_MAX_BLOCKS * sizeof(double), 256) + 256;
+  size_t front = partials_bytes(K, D);
+  if (search_large_supported(K, D)) {
+    size_t l = align_up(search_large_workspace_bytes(K, D), 256);
+    if (l > front) front = l;
+  }
+  return front + align_up((size_t)EW_MAX_BLOCKS * sizeof(double), 256) + 256;
 }
 
 static int check_vq_shape(int layout, int B, int D, int T, int K) {
@@ -704,6 +713,11 @@ extern "C" int vqs_vq_assign(const float* z, int layout, int B, int D, int T, co
     stats_reduce_kernel<<<(S + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, S, stats);
     VQS_LAUNCH_CHECK();
     return 0;
+  }
+  if (g_vq_engine <= 1 && dmin2 == nullptr && distances == nullptr && !assign_tc_supported(K, D) &&
+      search_large_supported(K, D) && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
+    // large codebooks: streamed tensor-core distance GEMM + exact fp32 settlement of near-ties
+    return launch_search_large(z, layout, B, D, T, codebook, K, idx, stats, workspace, st);
   }
   AssignPlan pl;
   VQS_CHECK_ARG(plan_assign(K, D, pl), "vqs_vq_assign: embedding_dim %d too large for the shared-memory path", D);
@@ -801,7 +815,12 @@ extern "C" int vqs_vq_quantize(const float* z, int layout, int B, int D, int T, 
     set_error("vqs_vq_quantize: workspace too small");
     return VQS_ERR_WORKSPACE;
   }
-  double* sse_part = (double*)((char*)workspace + partials_bytes(K, D));
+  size_t front = partials_bytes(K, D);
+  if (search_large_supported(K, D)) {
+    size_t l = align_up(search_large_workspace_bytes(K, D), 256);
+    if (l > front) front = l;
+  }
+  double* sse_part = (double*)((char*)workspace + front);
   EwParams p;
   p.z = z; p.g = nullptr; p.gl = nullptr; p.idx = idx; p.cb = codebook; p.out = out; p.sse_partials = sse_part;
   p.coef = 0.f;

@@ -112,8 +112,9 @@ def _pany(t):
 # VQ bottleneck
 # ------------------------------------------------------------------------------------------------
 def vq_set_engine(name):
-    """'cuda_core' (default) or 'tensor_core' / 'auto' (tcgen05 search + exact re-check where supported)."""
-    _lib.check(_lib.load().vqs_vq_set_engine({'auto': 0, 'tensor_core': 0, 'cuda_core': 1}[name]))
+    """'auto' (default: CUDA cores for resident codebooks, tcgen05 distance GEMM for large ones), 'tensor_core' (tcgen05
+    wherever a kernel exists) or 'cuda_core'."""
+    _lib.check(_lib.load().vqs_vq_set_engine({'tensor_core': 0, 'auto': 1, 'cuda_core': 2}[name]))
 
 
 def vq_workspace_bytes(K, D):
