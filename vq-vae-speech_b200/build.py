@@ -25,7 +25,7 @@ def sources():
 def _digest():
     h = hashlib.sha256()
     for p in sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + sorted(glob.glob(os.path.join(ROOT, 'include', '*.h'))):
-        h.update(p.encode())
+        h.update(os.path.relpath(p, ROOT).encode())     # relative: the repo lives at a different path on the GPU box
         with open(p, 'rb') as f:
             h.update(f.read())
     h.update(' '.join(ARCH + FLAGS).encode())
@@ -35,8 +35,26 @@ def _digest():
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ for sm_100a and link libvqs_b200.so.  Returns the library path."""
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig
+
+    if not force and fresh():
         return LIB
+    # one builder at a time (several ranks import the package concurrently under torch.distributed.run)
+    import fcntl
+    lock = open(os.path.join(CSRC, '.build.lock'), 'w')
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and fresh():
+            return LIB
+        return _build_locked(dig, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(dig, verbose):
     if not os.path.exists(NVCC):
         if os.path.exists(LIB):      # GPU box without a toolkit: use the prebuilt library that travelled with the snapshot
             return LIB
@@ -56,10 +74,12 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed on %s:\n%s' % (src, out))
         if verbose or out.strip():
             sys.stderr.write(out)
-    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs + ['-lcuda']
+    tmp = LIB + '.tmp.%d' % os.getpid()
+    cmd = [NVCC] + ARCH + ['-shared', '-o', tmp] + objs + ['-lcuda']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout)
+    os.replace(tmp, LIB)          # atomic: a concurrent loader never sees a half-written library
     with open(STAMP, 'w') as f:
         f.write(dig)
     return LIB
