@@ -389,8 +389,7 @@ def run_b200(args):
            'last_losses': last}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     vq = None
     if not args.skip_vq and world == 1:
@@ -412,11 +411,23 @@ def run_b200(args):
         'params': eng.n_params, 'flops_per_step': sum(flops_of(e) for e in eng.schedule if e[0] is not None),
     }
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 _REAL_STDOUT = None
+
+
+def finish(world):
+    """Multi-rank runs leave through os._exit once every rank is done: tearing down a process group whose collectives
+    were captured into a CUDA graph can block in destroy_process_group (seen on 2 GPUs: the result was printed, then the
+    processes hung until the launcher's timeout)."""
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def emit(line):
