@@ -132,7 +132,9 @@ int vqs_vq_grad_codebook(const float* stats, const float* codebook, const float*
  * A is a row-major (M, Cred*ksz) matrix: the nn.Conv1d weight (Cout, Cin, k) as is for a forward conv and
  * the nn.ConvTranspose1d weight (Cin, Cout, k) as is for its dgrad; vqs_permute_weight produces the
  * (d1, d0, k) arrangement the other two cases need.  With a_tap_major != 0, A is instead (M, ksz, Cred) -- reduction
- * index j*Cred + c -- the arrangement the tensor-core engines require (vqs_permute_weight modes 1 and 2).
+ * index j*Cred + c -- the arrangement the tensor-core engines require (vqs_permute_weight modes 1 and 2).  With
+ * a_tap_major == 2, A is the pre-split, pre-swizzled tensor-core operand IMAGE of that matrix (vqs_permute_weight
+ * modes 3 and 4; Cred % 32 == 0): the GEMM fetches its A tiles with TMA bulk copies.
  *
  * Epilogue, per output element (b, m, l), out tensors are NCL (B, M, Lout):
  *   v = acc + bias[m]                       (bias may be NULL)
@@ -197,7 +199,9 @@ int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int accumulate
 /* Re-arrangements of a conv weight w[d0][d1][k]:
  *   mode 0: out[d1][d0][k]   (swap the channel dims)
  *   mode 1: out[d0][k][d1]   (tap-major, same orientation)
- *   mode 2: out[d1][k][d0]   (tap-major, channel dims swapped) */
+ *   mode 2: out[d1][k][d0]   (tap-major, channel dims swapped)
+ *   mode 3 / 4: tensor-core operand image of the mode-1 / mode-2 matrix: ceil(M/128) * (k*Cred/32) blocks of 8192 floats
+ *               ([hi | lo] x 128 rows x 32 floats, SWIZZLE_128B), M = d0 / d1, Cred = d1 / d0 */
 int vqs_permute_weight(const float* w, int d0, int d1, int k, int mode, float* out, vqs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ */

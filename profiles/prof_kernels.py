@@ -23,10 +23,10 @@ if what in ('conv', 'all'):
     ws = F._wgrad_ws(C, C, 3, B, L, dev)
     for prec in ('3xtf32', 'tf32', 'fp32'):
         ops.set_precision(prec)
-        A, tap = F.gemm_weight(w, 'conv_fwd')
+        A = F.gemm_weight(w, 'conv_fwd')
         for _ in range(2):
-            F.conv1d_forward(x, A, b, 1, 1, out=out, tap=tap, relu=True, mask_out=mask_out, add_post=res)  # enc conv_2
-            F.conv1d_forward(x, A, b, 1, 1, out=out, tap=tap)                                             # plain epilogue
+            F.conv1d_forward(x, A, b, 1, 1, out=out, relu=True, mask_out=mask_out, add_post=res)  # enc conv_2
+            F.conv1d_forward(x, A, b, 1, 1, out=out)                                             # plain epilogue
             F.conv1d_wgrad(out, x, dW, 1, 1, ws)
     torch.cuda.synchronize()
 if what in ('vq', 'all'):

@@ -50,14 +50,12 @@ def test_conv1d_fwd_dgrad_wgrad(B, Cin, Cout, L, k, stride, pad, prec):
     b = rng.randn(Cout)
     y_o = mo.conv1d_fwd(x, w, b, stride, pad)
     xd, wd, bd = _t(x, dev), _t(w, dev), _t(b, dev)
-    A, tap = F.gemm_weight(wd, 'conv_fwd')      # tap-major (Cout, k, Cin) for the tensor-core engines when Cin % 32 == 0
-    y = F.conv1d_forward(xd, A, bd, stride, pad, tap=tap)
+    y = F.conv1d_forward(xd, F.gemm_weight(wd, 'conv_fwd'), bd, stride, pad)   # operand image when Cin % 32 == 0
     assert tuple(y.shape) == y_o.shape
     assert rel_err(y.cpu().numpy(), y_o) < TOL
     gy = rng.randn(*y_o.shape)
     gyd = _t(gy, dev)
-    A, tap = F.gemm_weight(wd, 'conv_dgrad')
-    dx = F.conv1d_dgrad(gyd, A, L, stride, pad, tap=tap)
+    dx = F.conv1d_dgrad(gyd, F.gemm_weight(wd, 'conv_dgrad'), L, stride, pad)
     assert rel_err(dx.cpu().numpy(), mo.conv1d_dgrad(gy, w, L, stride, pad)) < TOL
     dW = torch.empty_like(wd)
     F.conv1d_wgrad(gyd, xd, dW, stride, pad, F._wgrad_ws(Cout, Cin, k, B, y.shape[2], dev))
@@ -86,21 +84,20 @@ def test_conv_transpose1d_fwd_dgrad_wgrad(B, Cin, Cout, L, k, pad, prec):
     b = rng.randn(Cout)
     y_o = mo.convT1d_fwd(x, w, b, pad)
     xd, wd, bd = _t(x, dev), _t(w, dev), _t(b, dev)
-    A, tap = F.gemm_weight(wd, 'convT_fwd')
-    y = F.convT1d_forward(xd, A, bd, pad, tap=tap)
+    A = F.gemm_weight(wd, 'convT_fwd')
+    y = F.convT1d_forward(xd, A, bd, pad)
     assert tuple(y.shape) == y_o.shape
     assert rel_err(y.cpu().numpy(), y_o) < TOL
     # trimmed output (convolutional_vq_vae.py:133-137 drops the tail): only the first `keep` positions are computed,
     # and the backward sees zero gradient beyond them
     keep = y_o.shape[2] - 3
-    yt = F.convT1d_forward(xd, A, bd, pad, out_len=keep, tap=tap)
+    yt = F.convT1d_forward(xd, A, bd, pad, out_len=keep)
     assert rel_err(yt.cpu().numpy(), y_o[:, :, :keep]) < TOL
     gy = rng.randn(B, Cout, keep)
     gfull = np.zeros_like(y_o)
     gfull[:, :, :keep] = gy
     gyd = _t(gy, dev)
-    A, tap = F.gemm_weight(wd, 'convT_dgrad')
-    dx = F.convT1d_dgrad(gyd, A, L, pad, tap=tap)
+    dx = F.convT1d_dgrad(gyd, F.gemm_weight(wd, 'convT_dgrad'), L, pad)
     assert rel_err(dx.cpu().numpy(), mo.convT1d_dgrad(gfull, w, L, pad)) < TOL
     dW = torch.empty_like(wd)
     F.convT1d_wgrad(gyd, xd, dW, pad, F._wgrad_ws(Cin, Cout, k, B, L, dev))
@@ -122,7 +119,8 @@ def test_fused_epilogue_and_strided_input(prec):
     pre = rng.randn(B, Cout, L)
     xd = _t(x_blc, dev)
     mask_out = torch.empty(B, Cout, L, dtype=torch.uint8, device=dev)
-    y = F.conv1d_forward(xd, _t(w, dev), _t(b, dev), 1, 1, x_strides=(L * Cin, 1, Cin), x_shape=(B, Cin, L),
+    y = F.conv1d_forward(xd, F.gemm_weight(_t(w, dev), 'conv_fwd'), _t(b, dev), 1, 1, x_strides=(L * Cin, 1, Cin),
+                         x_shape=(B, Cin, L),
                          add_pre=_t(pre, dev), add_pre_relu=True, relu=True, mask_out=mask_out, add_post=_t(res, dev))
     p = mo.conv1d_fwd(x_blc.transpose(0, 2, 1), w, b, 1, 1) + np.maximum(pre, 0)
     r = np.maximum(p, 0)
@@ -135,8 +133,7 @@ def test_fused_epilogue_and_strided_input(prec):
     w2 = rng.randn(Cout, Cout, 3) / 10
     act = rng.randn(B, Cout, L)
     out2 = torch.empty(B, Cout, L, device=dev)
-    A2, tap2 = F.gemm_weight(_t(w2, dev), 'conv_fwd')
-    y2 = F.conv1d_forward(_t(x, dev), A2, None, 1, 1, tap=tap2, x_relu=True, mask=_t(act, dev), mask_kind=ops.MASK_FLOAT,
+    y2 = F.conv1d_forward(_t(x, dev), F.gemm_weight(_t(w2, dev), 'conv_fwd'), None, 1, 1, x_relu=True, mask=_t(act, dev), mask_kind=ops.MASK_FLOAT,
                           add_post=_t(res, dev), out2=out2, mask2=mask_out, mask2_kind=ops.MASK_U8)
     v = mo.conv1d_fwd(np.maximum(x, 0), w2, None, 1, 1) * (act > 0) + res
     assert rel_err(y2.cpu().numpy(), v) < TOL

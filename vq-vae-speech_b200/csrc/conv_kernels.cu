@@ -377,6 +377,10 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
 // Weight re-arrangement through a 32 x 32 x k shared-memory tile: global reads and writes are both contiguous runs
 // (the first version read with stride d1*k in modes 0/2: 13.7 us per 7 MB weight, 8 % of the training step).
 //   w[a][b][j]  ->  mode 0: out[b][a][j]   mode 1: out[a][j][b]   mode 2: out[b][j][a]
+//   modes 3 / 4: tensor-core operand IMAGE of the tap-major matrix A[m][j*Cred + c] (mode 3: m = a, c = b; mode 4: m = b,
+//   c = a): for every (128-row tile mt, 32-wide k-block kb) one contiguous 32 KB block [hi 16 KB | lo 16 KB], each
+//   copy laid out exactly as the MMA reads it (128 rows x 128 B, SWIZZLE_128B), values pre-split x = hi + lo.  The GEMM
+//   kernel then fetches its A operand with ONE cp.async.bulk per k-block instead of 512 thread loads + splits.
 template <int KS>
 __global__ void __launch_bounds__(256) permute_weight_kernel(const float* __restrict__ w, int d0, int d1, int mode,
                                                              float* __restrict__ out) {
@@ -405,12 +409,37 @@ __global__ void __launch_bounds__(256) permute_weight_kernel(const float* __rest
       const int a = a0 + ar, b = b0 + br;
       if (a < d0 && b < d1) out[((size_t)a * KS + j) * d1 + b] = tile[ar * ROW + br * KS + j];
     }
-  } else {                  // out[b][j][a]: for each (b, j), 32 contiguous a
+  } else if (mode == 2) {   // out[b][j][a]: for each (b, j), 32 contiguous a
     for (int i = tid; i < 32 * 32 * KS; i += 256) {
       const int ar = i & 31, t = i >> 5;
       const int j = t % KS, br = t / KS;
       const int a = a0 + ar, b = b0 + br;
       if (a < d0 && b < d1) out[((size_t)b * KS + j) * d0 + a] = tile[ar * ROW + br * KS + j];
+    }
+  } else {                  // operand image: 32 consecutive c of one (m, j) = one swizzled 128-byte row of a k-block
+    const int Cred = (mode == 3) ? d1 : d0;
+    const int nkb = KS * Cred / 32;
+    for (int i = tid; i < 32 * 32 * KS; i += 256) {
+      const int cr = i & 31, t = i >> 5;        // cr: position along c (the fast index of the image row)
+      const int j = t % KS, mr = t / KS;
+      int m, c;
+      float v;
+      if (mode == 3) {
+        m = a0 + mr; c = b0 + cr;
+        v = tile[mr * ROW + cr * KS + j];
+        if (m >= d0 || c >= d1) continue;
+      } else {
+        m = b0 + mr; c = a0 + cr;
+        v = tile[cr * ROW + mr * KS + j];
+        if (m >= d1 || c >= d0) continue;
+      }
+      const int kk = j * Cred + c;
+      const int kb = kk >> 5, kcol = kk & 31, r = m & 127, mt = m >> 7;
+      const size_t base = ((size_t)mt * nkb + kb) * 8192;   // floats: 2 copies x 4096
+      const int off = r * 32 + ((((kcol >> 2) ^ (r & 7)) << 2) | (kcol & 3));
+      const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      out[base + off] = h;
+      out[base + 4096 + off] = v - h;
     }
   }
 }
@@ -438,6 +467,11 @@ extern "C" int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream) {
   p.divCpb = FastDiv((uint32_t)p.cpb);
   p.divCred = FastDiv((uint32_t)d->Cred);
   cudaStream_t st = (cudaStream_t)stream;
+  if (d->a_tap_major == 2) {
+    VQS_CHECK_ARG(d->precision != VQS_PREC_FP32 && conv_tc_supported(p),
+                  "vqs_conv_gemm: an operand image (a_tap_major = 2) needs a tensor-core precision and Cred %% 32 == 0");
+    return launch_conv_tc(p, d->precision, st);
+  }
   if (d->precision != VQS_PREC_FP32 && conv_tc_supported(p)) return launch_conv_tc(p, d->precision, st);
   // tile choice: big tiles once they fill the machine, small tiles otherwise
   long long big = (long long)((d->M + 127) / 128) * ((p.Ntot + 127) / 128);
@@ -500,8 +534,15 @@ extern "C" int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int
 }
 
 extern "C" int vqs_permute_weight(const float* w, int d0, int d1, int k, int mode, float* out, vqs_stream_t stream) {
-  VQS_CHECK_ARG(w && out && d0 > 0 && d1 > 0 && k >= 1 && k <= 4 && mode >= 0 && mode <= 2,
-                "vqs_permute_weight: bad arguments (kernel size 1..4, mode 0..2)");
+  VQS_CHECK_ARG(w && out && d0 > 0 && d1 > 0 && k >= 1 && k <= 4 && mode >= 0 && mode <= 4,
+                "vqs_permute_weight: bad arguments (kernel size 1..4, mode 0..4)");
+  if (mode >= 3) {
+    const int M = mode == 3 ? d0 : d1, Cred = mode == 3 ? d1 : d0;
+    VQS_CHECK_ARG(Cred % 32 == 0, "vqs_permute_weight: operand images need Cred %% 32 == 0 (got %d)", Cred);
+    if (M % 128 != 0)   // rows beyond M stay zero
+      VQS_CUDA(cudaMemsetAsync(out, 0, (size_t)((M + 127) / 128) * (k * Cred / 32) * 8192 * sizeof(float),
+                               (cudaStream_t)stream));
+  }
   dim3 grid((d1 + 31) / 32, (d0 + 31) / 32);
   cudaStream_t st = (cudaStream_t)stream;
   switch (k) {

@@ -112,13 +112,15 @@ __device__ __forceinline__ void load_conv(const ConvParams& p, int kb, ConvRegs<
   // tap-major K: k-block kb = tap j, channels [c0, c0 + 32)
   const uint32_t j = p.divCpb.div((uint32_t)kb);
   const int c0 = (kb - (int)j * p.cpb) * BKF;
-  const int c = ptid & 7;  // A: float4 along k; 8 consecutive threads cover one 128-byte row
-  const float* arow = d.A + (size_t)kb * BKF + c * 4;
+  if (d.a_tap_major != 2) {   // (with an operand image the A tile arrives by cp.async.bulk, see the stage code)
+    const int c = ptid & 7;  // A: float4 along k; 8 consecutive threads cover one 128-byte row
+    const float* arow = d.A + (size_t)kb * BKF + c * 4;
 #pragma unroll
-  for (int i = 0; i < ConvRegs<BN>::AI; ++i) {
-    const int m = m0 + (ptid >> 3) + i * (N_PROD / 8);
-    rg.a[i] = (m < d.M) ? __ldg(reinterpret_cast<const float4*>(arow + (size_t)m * p.Ktot))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < ConvRegs<BN>::AI; ++i) {
+      const int m = m0 + (ptid >> 3) + i * (N_PROD / 8);
+      rg.a[i] = (m < d.M) ? __ldg(reinterpret_cast<const float4*>(arow + (size_t)m * p.Ktot))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   // B: thread = column n (fixed (b, l)); one bounds decision per k-block, then a constant channel stride
   int pn = lbase + (int)j * d.j_mul;
@@ -138,10 +140,12 @@ template <int BN, int PASSES>
 __device__ __forceinline__ void store_conv(const ConvParams& p, const ConvRegs<BN>& rg, uint32_t sA_hi, uint32_t sA_lo,
                                            uint32_t sB_hi, uint32_t sB_lo, uint32_t offA,
                                            const uint32_t (&offB)[ConvRegs<BN>::CH]) {
+  if (p.d.a_tap_major != 2) {
 #pragma unroll
-  for (int i = 0; i < ConvRegs<BN>::AI; ++i) {
-    const uint32_t o = offA + (uint32_t)(i * (N_PROD / 8) * 128);   // rows step by 64: (r & 7) unchanged
-    st_vec4<PASSES>(sA_hi + o, sA_lo + o, rg.a[i]);
+    for (int i = 0; i < ConvRegs<BN>::AI; ++i) {
+      const uint32_t o = offA + (uint32_t)(i * (N_PROD / 8) * 128);   // rows step by 64: (r & 7) unchanged
+      st_vec4<PASSES>(sA_hi + o, sA_lo + o, rg.a[i]);
+    }
   }
   const bool rl = p.d.x_relu != 0;
 #pragma unroll
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
 
+  bool a_image = false;
+  if constexpr (MODE == 0) a_image = prm.p.d.a_tap_major == 2;
   int nkb, kb_begin;
   if constexpr (MODE == 0) {
     nkb = (prm.p.Ktot + BKF - 1) / BKF;
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&sh->full[s], N_PROD_WARPS);
+      mbar_init(&sh->full[s], N_PROD_WARPS + (a_image ? 1 : 0));
       mbar_init(&sh->empty[s], 1);
     }
     mbar_init(&sh->tmem_full, 1);
@@ -308,8 +314,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
       const uint32_t sB_hi = sA_hi + Cfg::A_BYTES;
       const uint32_t sA_lo = sA_hi + Cfg::A_BYTES + Cfg::B_BYTES;
       const uint32_t sB_lo = sA_lo + Cfg::A_BYTES;
-      if constexpr (MODE == 0) store_conv<BN, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, offA, offB);
-      else store_wgrad<BN, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, off0);
+      if constexpr (MODE == 0) {
+        if (a_image && tid == 0) {
+          // A operand: one bulk copy per copy (hi, lo) of the pre-built 128 x 32 image block of this k-block; the copy
+          // engine signals full[s] with complete_tx (async proxy: no fence needed), this thread adds the extra arrival
+          const int nkb_all = prm.p.Ktot / BKF;
+          const float* blk = prm.p.d.A + ((size_t)blockIdx.y * nkb_all + (kb_begin + i)) * 8192;
+          const uint32_t bar = smem_u32(&sh->full[s]);
+          constexpr uint32_t bytes = (PASSES == 3) ? 2u * Cfg::A_BYTES : (uint32_t)Cfg::A_BYTES;
+          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
+                       "r"(bytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           sA_hi),
+                       "l"(blk), "r"((uint32_t)Cfg::A_BYTES), "r"(bar)
+                       : "memory");
+          if (PASSES == 3)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             sA_lo),
+                         "l"(blk + 4096), "r"((uint32_t)Cfg::A_BYTES), "r"(bar)
+                         : "memory");
+        }
+        store_conv<BN, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, offA, offB);
+      } else {
+        store_wgrad<BN, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, off0);
+      }
       fence_proxy_async();  // this thread's generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->full[s]);          // one arrival per producer warp
@@ -509,7 +538,8 @@ int launch_tc(const TcParams<MODE>& prm, int ksz, int bn, int precision, dim3 gr
 }  // namespace
 
 bool conv_tc_supported(const ConvParams& p) {
-  return p.a_vec && p.d.a_tap_major && p.d.Cred % BKF == 0 && p.d.ksz >= 1;
+  if (p.d.a_tap_major == 2) return p.d.Cred % BKF == 0 && p.d.ksz >= 1;       // pre-built operand image
+  return p.a_vec && p.d.a_tap_major == 1 && p.d.Cred % BKF == 0 && p.d.ksz >= 1;
 }
 bool wgrad_tc_supported(const WgradParams& p) { return p.d.ksz >= 1 && p.d.ksz <= 4 && p.Kred >= 32; }
 

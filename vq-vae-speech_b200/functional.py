@@ -20,55 +20,59 @@ def convT_out_len(Lin, k, pad):
     return Lin - 1 + k - 2 * pad
 
 
-# GEMM-ready weight arrangements.  role -> (permute mode when tap-major, permute mode otherwise [None = as is]).
-# The tensor-core engines need the tap-major form (reduction index j*Cred + c) and Cred % 32 == 0; everything else runs
-# the canonical form on the exact-fp32 CUDA-core engine.
-_ROLES = {'conv_fwd': (1, None), 'conv_dgrad': (2, 0), 'convT_fwd': (2, 0), 'convT_dgrad': (1, None)}
+# GEMM-ready weight arrangements.  role -> permute mode for (operand image, tap-major matrix, canonical [None = as is]).
+# The tensor-core engines take the pre-split, pre-swizzled operand IMAGE (vqs_permute_weight modes 3 / 4; needs
+# Cred % 32 == 0); everything else runs the canonical arrangement on the exact-fp32 CUDA-core engine.
+import collections
+
+GemmW = collections.namedtuple('GemmW', 'A tap M Cred ksz')   # tap: 0 canonical, 1 tap-major matrix, 2 operand image
+_ROLES = {'conv_fwd': (3, None), 'conv_dgrad': (4, 0), 'convT_fwd': (4, 0), 'convT_dgrad': (3, None)}
+
+
+def _role_dims(w_shape, role):
+    d0, d1, k = w_shape
+    return (d0, d1, k) if role in ('conv_fwd', 'convT_dgrad') else (d1, d0, k)     # (M, Cred, ksz)
 
 
 def gemm_weight_layout(w_shape, role, precision=None):
-    """(tap_major, mode) the GEMM of `role` should use for a weight of shape w_shape under the given engine."""
+    """(tap, permute mode or None, number of floats of the GEMM operand buffer) for a weight of shape w_shape."""
     prec = ops.get_precision() if precision is None else precision
-    cred = w_shape[1] if role in ('conv_fwd', 'convT_dgrad') else w_shape[0]
-    tap = prec != 'fp32' and cred % 32 == 0
-    return tap, _ROLES[role][0 if tap else 1]
+    M, Cred, k = _role_dims(w_shape, role)
+    if prec != 'fp32' and Cred % 32 == 0:
+        return 2, _ROLES[role][0], ((M + 127) // 128) * (k * Cred // 32) * 8192
+    return 0, _ROLES[role][1], M * Cred * k
 
 
-def gemm_weight(w, role, out=None):
-    """Returns (A, tap_major): the dense GEMM operand for `role`, re-arranged by vqs_permute_weight when needed."""
-    tap, mode = gemm_weight_layout(tuple(w.shape), role)
+def gemm_weight(w, role, out=None, precision=None):
+    """The dense GEMM operand of `role` for weight w: a GemmW (re-arranged by vqs_permute_weight when needed)."""
+    tap, mode, numel = gemm_weight_layout(tuple(w.shape), role, precision)
+    M, Cred, k = _role_dims(tuple(w.shape), role)
     if mode is None:
-        return w, tap
-    return ops.permute_weight(w, out=out, mode=mode), tap
+        return GemmW(w, tap, M, Cred, k)
+    if out is None:
+        out = torch.empty(numel, dtype=torch.float32, device=w.device)
+    ops.permute_weight(w, out=out, mode=mode)
+    return GemmW(out, tap, M, Cred, k)
 
 
-def _a_dims(A, tap):
-    """(M, Cred, ksz) of a GEMM-ready weight."""
-    if tap:
-        return A.shape[0], A.shape[2], A.shape[1]
-    return A.shape[0], A.shape[1], A.shape[2]
-
-
-def conv1d_forward(x, A, b, stride, pad, out=None, x_strides=None, x_shape=None, tap=False, **epi):
-    """nn.Conv1d forward: y[b,o,l] = bias[o] + sum_{c,j} w[o,c,j] x[b,c,l*stride + j - pad].
-    A = w (Cout, Cin, k), or its tap-major form (Cout, k, Cin) with tap=True."""
-    Cout, Cin, k = _a_dims(A, tap)
+def conv1d_forward(x, A, b, stride, pad, out=None, x_strides=None, x_shape=None, **epi):
+    """nn.Conv1d forward: y[b,o,l] = bias[o] + sum_{c,j} w[o,c,j] x[b,c,l*stride + j - pad].   A = gemm_weight(w, 'conv_fwd')."""
+    Cout, Cin, k = A.M, A.Cred, A.ksz
     B, _, Lin = x_shape if x_shape is not None else x.shape
     Lout = conv_out_len(Lin, k, stride, pad)
     if out is None:
-        out = torch.empty(B, Cout, Lout, dtype=torch.float32, device=A.device)
-    return ops.conv_gemm(A, x, out, Cout, Cin, k, B, Lin, Lout, stride, 1, -pad, 1, x_strides=x_strides, bias=b,
-                         a_tap_major=tap, **epi)
+        out = torch.empty(B, Cout, Lout, dtype=torch.float32, device=A.A.device)
+    return ops.conv_gemm(A.A, x, out, Cout, Cin, k, B, Lin, Lout, stride, 1, -pad, 1, x_strides=x_strides, bias=b,
+                         a_tap_major=A.tap, **epi)
 
 
-def conv1d_dgrad(gy, A, Lx, stride, pad, out=None, tap=False, **epi):
-    """dx[b,c,i] = sum_{o,j} w[o,c,j] gy[b,o,(i + pad - j)/stride].
-    A = permute_weight(w, mode 0) = (Cin, Cout, k), or mode 2 = (Cin, k, Cout) with tap=True."""
-    Cin, Cout, k = _a_dims(A, tap)
+def conv1d_dgrad(gy, A, Lx, stride, pad, out=None, **epi):
+    """dx[b,c,i] = sum_{o,j} w[o,c,j] gy[b,o,(i + pad - j)/stride].   A = gemm_weight(w, 'conv_dgrad')."""
+    Cin, Cout, k = A.M, A.Cred, A.ksz
     B, _, Ly = gy.shape
     if out is None:
         out = torch.empty(B, Cin, Lx, dtype=torch.float32, device=gy.device)
-    return ops.conv_gemm(A, gy, out, Cin, Cout, k, B, Ly, Lx, 1, -1, pad, stride, a_tap_major=tap, **epi)
+    return ops.conv_gemm(A.A, gy, out, Cin, Cout, k, B, Ly, Lx, 1, -1, pad, stride, a_tap_major=A.tap, **epi)
 
 
 def conv1d_wgrad(gy, x, dW, stride, pad, ws, x_relu=False, accumulate=False):
@@ -79,26 +83,25 @@ def conv1d_wgrad(gy, x, dW, stride, pad, ws, x_relu=False, accumulate=False):
                           accumulate=accumulate)
 
 
-def convT1d_forward(x, A, b, pad, out_len=None, out=None, tap=False, **epi):
+def convT1d_forward(x, A, b, pad, out_len=None, out=None, **epi):
     """nn.ConvTranspose1d (stride 1) forward: y[b,o,i] = bias[o] + sum_{c,j} x[b,c,i - j + pad] w[c,o,j].
-    A = permute_weight(w, mode 0) = (Cout, Cin, k), or mode 2 = (Cout, k, Cin) with tap=True.
-    out_len < full length computes only the first out_len positions."""
-    Cout, Cin, k = _a_dims(A, tap)
+    A = gemm_weight(w, 'convT_fwd').  out_len < full length computes only the first out_len positions."""
+    Cout, Cin, k = A.M, A.Cred, A.ksz
     B, _, Lin = x.shape
     Lout = convT_out_len(Lin, k, pad) if out_len is None else out_len
     if out is None:
         out = torch.empty(B, Cout, Lout, dtype=torch.float32, device=x.device)
-    return ops.conv_gemm(A, x, out, Cout, Cin, k, B, Lin, Lout, 1, -1, pad, 1, bias=b, a_tap_major=tap, **epi)
+    return ops.conv_gemm(A.A, x, out, Cout, Cin, k, B, Lin, Lout, 1, -1, pad, 1, bias=b, a_tap_major=A.tap, **epi)
 
 
-def convT1d_dgrad(gy, A, Lx, pad, out=None, tap=False, **epi):
+def convT1d_dgrad(gy, A, Lx, pad, out=None, **epi):
     """dx[b,c,l] = sum_{o,j} gy[b,o,l + j - pad] w[c,o,j]  (gy may be the trimmed tensor: positions beyond it are 0).
-    A = w (Cin, Cout, k), or its tap-major form (Cin, k, Cout) with tap=True."""
-    Cin, Cout, k = _a_dims(A, tap)
+    A = gemm_weight(w, 'convT_dgrad')."""
+    Cin, Cout, k = A.M, A.Cred, A.ksz
     B, _, Ly = gy.shape
     if out is None:
         out = torch.empty(B, Cin, Lx, dtype=torch.float32, device=gy.device)
-    return ops.conv_gemm(A, gy, out, Cin, Cout, k, B, Ly, Lx, 1, 1, -pad, 1, a_tap_major=tap, **epi)
+    return ops.conv_gemm(A.A, gy, out, Cin, Cout, k, B, Ly, Lx, 1, 1, -pad, 1, a_tap_major=A.tap, **epi)
 
 
 def convT1d_wgrad(gy, x, dW, pad, ws, accumulate=False):
@@ -122,8 +125,8 @@ class Conv1dFn(Function):
     @staticmethod
     def forward(ctx, x, w, b, stride, pad, relu):
         x = x.contiguous()
-        A, tap = gemm_weight(w.contiguous(), 'conv_fwd')
-        out = conv1d_forward(x, A, None if b is None else b.contiguous(), stride, pad, relu=relu, tap=tap)
+        out = conv1d_forward(x, gemm_weight(w.contiguous(), 'conv_fwd'), None if b is None else b.contiguous(), stride,
+                             pad, relu=relu)
         ctx.save_for_backward(x, w, out if relu else None)
         ctx.cfg = (stride, pad, relu, b is not None)
         return out
@@ -139,8 +142,7 @@ class Conv1dFn(Function):
         B = x.shape[0]
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            A, tap = gemm_weight(w.contiguous(), 'conv_dgrad')
-            dx = conv1d_dgrad(g, A, x.shape[2], stride, pad, tap=tap)
+            dx = conv1d_dgrad(g, gemm_weight(w.contiguous(), 'conv_dgrad'), x.shape[2], stride, pad)
         if ctx.needs_input_grad[1]:
             dW = torch.empty_like(w)
             conv1d_wgrad(g, x, dW, stride, pad, _wgrad_ws(Cout, Cin, k, B, g.shape[2], g.device))
@@ -155,8 +157,8 @@ class ConvTranspose1dFn(Function):
     @staticmethod
     def forward(ctx, x, w, b, pad, relu, out_len):
         x = x.contiguous()
-        A, tap = gemm_weight(w.contiguous(), 'convT_fwd')
-        out = convT1d_forward(x, A, None if b is None else b.contiguous(), pad, out_len=out_len, relu=relu, tap=tap)
+        out = convT1d_forward(x, gemm_weight(w.contiguous(), 'convT_fwd'), None if b is None else b.contiguous(), pad,
+                              out_len=out_len, relu=relu)
         ctx.save_for_backward(x, w, out if relu else None)
         ctx.cfg = (pad, relu, b is not None)
         return out
@@ -172,8 +174,7 @@ class ConvTranspose1dFn(Function):
         B = x.shape[0]
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            A, tap = gemm_weight(w.contiguous(), 'convT_dgrad')
-            dx = convT1d_dgrad(g, A, x.shape[2], pad, tap=tap)
+            dx = convT1d_dgrad(g, gemm_weight(w.contiguous(), 'convT_dgrad'), x.shape[2], pad)
         if ctx.needs_input_grad[1]:
             dW = torch.empty_like(w)
             convT1d_wgrad(g, x, dW, pad, _wgrad_ws(Cin, Cout, k, B, x.shape[2], g.device))

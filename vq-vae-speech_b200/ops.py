@@ -206,7 +206,7 @@ def conv_gemm(A, X, out, M, Cred, ksz, B, Lin, Lout, l_mul, j_mul, off, l_div=1,
     d = ConvGemmDesc()
     d.A = _p(A)
     d.X = X.data_ptr() if x_strides is not None else _p(X)
-    d.a_tap_major = int(a_tap_major)
+    d.a_tap_major = int(a_tap_major)          # 0 canonical, 1 tap-major matrix, 2 tensor-core operand image
     d.M, d.Cred, d.ksz = M, Cred, ksz
     d.B, d.Lin, d.Lout = B, Lin, Lout
     if x_strides is None:
@@ -258,10 +258,12 @@ def bias_grad(g, db, accumulate=False):
 
 
 def permute_weight(w, out=None, mode=0):
-    """w[d0][d1][k] -> mode 0: [d1][d0][k]; mode 1: [d0][k][d1] (tap-major); mode 2: [d1][k][d0] (tap-major, swapped)."""
+    """w[d0][d1][k] -> mode 0: [d1][d0][k]; mode 1: [d0][k][d1] (tap-major); mode 2: [d1][k][d0] (tap-major, swapped);
+    modes 3 / 4: tensor-core operand image of the mode-1 / mode-2 matrix (see include/vqs_b200.h)."""
     d0, d1, k = w.shape
     if out is None:
-        shape = {0: (d1, d0, k), 1: (d0, k, d1), 2: (d1, k, d0)}[mode]
+        shape = {0: (d1, d0, k), 1: (d0, k, d1), 2: (d1, k, d0),
+                 3: (((d0 + 127) // 128) * (k * d1 // 32) * 8192,), 4: (((d1 + 127) // 128) * (k * d0 // 32) * 8192,)}[mode]
         out = torch.empty(*shape, dtype=torch.float32, device=w.device)
     _call('vqs_permute_weight', (_p(w), d0, d1, k, mode, _p(out)))
     return out

@@ -164,8 +164,8 @@ class FusedTrainStep(object):
         b['gH1'] = f(B, max(R_enc, C), Tq)
         b['gT_a'], b['gT_b'] = f(B, C, T), f(B, C, T)
         b['gq'], b['gqj'], b['gz'] = f(B, D, Tq), f(B, D, Tq), f(B, D, Tq)
-        # GEMM-ready weight arrangements, rebuilt at the top of every step by vqs_permute_weight: (name, role) ->
-        # (buffer or None when the parameter is used as is, tap_major, permute mode)
+        # GEMM-ready weight operands, rebuilt at the top of every step by vqs_permute_weight: (name, role) ->
+        # (buffer or None when the parameter is used as is, tap flag, permute mode)
         self.wperm = {}
         for name in self.param_names:
             if not name.endswith('weight') or name.startswith('_vq.'):
@@ -175,13 +175,8 @@ class FusedTrainStep(object):
             for role in roles:
                 if name == '_encoder._conv_1.weight' and role == 'conv_dgrad':
                     continue                       # the input features need no gradient
-                tap, mode = F.gemm_weight_layout(tuple(p.shape), role, self.precision)
-                buf = None
-                if mode is not None:
-                    shape = {0: (p.shape[1], p.shape[0], p.shape[2]), 1: (p.shape[0], p.shape[2], p.shape[1]),
-                             2: (p.shape[1], p.shape[2], p.shape[0])}[mode]
-                    buf = f(*shape)
-                self.wperm[(name, role)] = (buf, tap, mode)
+                tap, mode, numel = F.gemm_weight_layout(tuple(p.shape), role, self.precision)
+                self.wperm[(name, role)] = (f(numel) if mode is not None else None, tap, mode)
         ws_bytes = 16
         for (M, Cr, k, La) in [(C, Fi, 3, T), (C, C, 3, T), (C, C, 4, Tq), (C, C, 3, Tq), (R_enc, C, 3, Tq),
                                (C, R_enc, 1, Tq), (D, C, 3, Tq), (C, D, 3, Tq), (R_dec, C, 3, L2), (C, R_dec, 1, L2),
@@ -223,23 +218,20 @@ class FusedTrainStep(object):
 
         def A(name, role):
             buf, tap, mode = WP[(name, role)]
-            return (buf if buf is not None else P(name)), tap
+            M, Cred, k = F._role_dims(tuple(P(name).shape), role)
+            return F.GemmW(buf if buf is not None else P(name), tap, M, Cred, k)
 
         def cfwd(xin, name, bias, stride, pad, **kw):
-            a, tap = A(name, 'conv_fwd')
-            return F.conv1d_forward(xin, a, bias, stride, pad, tap=tap, **kw)
+            return F.conv1d_forward(xin, A(name, 'conv_fwd'), bias, stride, pad, **kw)
 
         def cdgrad(gy, name, Lx, stride, pad, **kw):
-            a, tap = A(name, 'conv_dgrad')
-            return F.conv1d_dgrad(gy, a, Lx, stride, pad, tap=tap, **kw)
+            return F.conv1d_dgrad(gy, A(name, 'conv_dgrad'), Lx, stride, pad, **kw)
 
         def tfwd(xin, name, bias, pad, **kw):
-            a, tap = A(name, 'convT_fwd')
-            return F.convT1d_forward(xin, a, bias, pad, tap=tap, **kw)
+            return F.convT1d_forward(xin, A(name, 'convT_fwd'), bias, pad, **kw)
 
         def tdgrad(gy, name, Lx, pad, **kw):
-            a, tap = A(name, 'convT_dgrad')
-            return F.convT1d_dgrad(gy, a, Lx, pad, tap=tap, **kw)
+            return F.convT1d_dgrad(gy, A(name, 'convT_dgrad'), Lx, pad, **kw)
 
         # ---- 1. encoder forward (convolutional_encoder.py:118-146) ----
         ops.blc_to_ncl(b['x_in'], b['x'])                                            # vq_vae.py:118
