@@ -57,7 +57,7 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -65,7 +65,7 @@ class ClockSampler(object):
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -96,6 +96,15 @@ class ClockSampler(object):
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
                 'samples': len(sm)}
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f)[kernel]['dram_bytes_per_launch']
+    except Exception:
+        return None
 
 
 def model_config(args):
@@ -348,7 +357,9 @@ def run_b200(args):
     dname, (dms, dflops, dn) = dom
     achieved = dflops / (dms * 1e-3) / 1e12
     roofline = {'bound': 'tensor', 'kernel': dname, 'achieved': achieved, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['tensor'], 'traffic': None, 'peak_source': pk['src'] + ' bf16 sustained',
+                'frac': achieved / pk['tensor'], 'traffic': measured_traffic(dname),
+                'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)',
+                'peak_source': pk['src'] + ' bf16 sustained',
                 'launches_per_step': dn // args.steps, 'avg_launch_ms': dms / dn,
                 'share_of_step_kernel_time': dms / kern_ms, 'measured_in': 'instrumented replay of the same %d steps '
                 '(%.3f ms/step with per-launch events vs %.3f ms/step in the timed region)' % (args.steps, instr_ms,

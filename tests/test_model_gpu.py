@@ -176,3 +176,32 @@ def test_fused_step_tf32_stated_tolerance(case):
     assert rel_err(out['vq_loss'], g['vq_loss0']) < 5e-2
     agree = np.mean(eng.encoding_indices().cpu().numpy().reshape(-1) == g['idx0'].reshape(-1))
     assert agree >= 0.9, agree
+
+
+def test_checkpoint_roundtrip_and_torch_adam_compat(tmp_path):
+    """the checkpoint dict has the reference's keys (convolutional_trainer.py:76-86); its 'optimizer' entry
+    loads into torch.optim.Adam(amsgrad=True) (how the reference resumes, pipeline_factory.py:118-120); and a step after
+    save -> load reproduces the step of the uninterrupted run bit for bit."""
+    dev = _dev()
+    from vq_vae_speech_b200 import trainer as tr
+    g = load_golden('model_ema_k44')
+    model, cfg = _build(g, dev)
+    eng = tr.FusedTrainStep(model, int(g['B']), int(g['T']), cfg['learning_rate'], use_graph=False)
+    eng.step(torch.from_numpy(g['x0']))
+    path = str(tmp_path / 'exp_1_checkpoint.pth')
+    tr.save_checkpoint(eng, path, 'exp', 0)
+    ck = torch.load(path, weights_only=False)
+    assert sorted(ck.keys()) == sorted(['experiment_name', 'epoch', 'model', 'optimizer', 'train_res_recon_error',
+                                        'train_res_perplexity'])
+    assert ck['epoch'] == 1
+    ref_opt = torch.optim.Adam(model.parameters(), lr=cfg['learning_rate'], amsgrad=True)
+    ref_opt.load_state_dict(ck['optimizer'])                      # torch accepts the format
+    assert len(ref_opt.state_dict()['state']) == len(eng.grads)
+    eng.step(torch.from_numpy(g['x1']))                            # uninterrupted run: step 2
+    want = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model2, _ = _build(g, dev)
+    eng2 = tr.FusedTrainStep(model2, int(g['B']), int(g['T']), cfg['learning_rate'], use_graph=False)
+    tr.load_checkpoint(eng2, path)
+    eng2.step(torch.from_numpy(g['x1']))
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v, want[k]), k

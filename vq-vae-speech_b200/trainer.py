@@ -458,6 +458,81 @@ class FusedTrainStep(object):
         return dict(self.grads)
 
 
+# ------------------------------------------------------------------------------------------------
+# checkpoint wire format of the reference (convolutional_trainer.py:76-86, pipeline_factory.py:108-126)
+# ------------------------------------------------------------------------------------------------
+def optimizer_state_dict(step):
+    """torch.optim.Adam(amsgrad=True)-compatible state_dict of a FusedTrainStep: the flat AMSGrad buffers are sliced back
+    into per-parameter exp_avg / exp_avg_sq / max_exp_avg_sq, indexed in model.parameters() order like torch does, so
+    `torch.optim.Adam(model.parameters(), lr, amsgrad=True).load_state_dict(...)` accepts it (the reference resumes
+    exactly that way, pipeline_factory.py:118-120).  Parameters Adam never stepped (EMA codebook) have no state."""
+    order = []
+    seen = set()
+    for name, p in step.model.named_parameters():
+        if id(p) not in seen:
+            seen.add(id(p))
+            order.append(name)
+    state = {}
+    nstep = int(step.opt_step.item())
+    for name, g in step.grads.items():
+        off = g.storage_offset()
+        n = g.numel()
+        if nstep == 0:
+            continue
+        state[order.index(name)] = {
+            'step': torch.tensor(float(nstep)),
+            'exp_avg': step.flat_m[off:off + n].view_as(g).clone(),
+            'exp_avg_sq': step.flat_v[off:off + n].view_as(g).clone(),
+            'max_exp_avg_sq': step.flat_vmax[off:off + n].view_as(g).clone(),
+        }
+    group = dict(lr=step.lr, betas=tuple(step.betas), eps=step.eps, weight_decay=0, amsgrad=True, maximize=False,
+                 foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False,
+                 params=list(range(len(order))))
+    return {'state': state, 'param_groups': [group]}
+
+
+def load_optimizer_state_dict(step, sd):
+    """Inverse of optimizer_state_dict: accepts a torch Adam(amsgrad=True) state_dict (e.g. from a reference checkpoint)."""
+    order = []
+    seen = set()
+    for name, p in step.model.named_parameters():
+        if id(p) not in seen:
+            seen.add(id(p))
+            order.append(name)
+    nstep = 0
+    for idx, st in sd['state'].items():
+        name = order[int(idx)]
+        if name not in step.grads:
+            continue
+        g = step.grads[name]
+        off, n = g.storage_offset(), g.numel()
+        step.flat_m[off:off + n].copy_(st['exp_avg'].reshape(-1))
+        step.flat_v[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+        step.flat_vmax[off:off + n].copy_(st['max_exp_avg_sq'].reshape(-1))
+        nstep = max(nstep, int(float(st['step'])))
+    step.opt_step.fill_(nstep)
+
+
+def save_checkpoint(step, path, experiment_name, epoch, train_res_recon_error=-1, train_res_perplexity=-1):
+    """Writes the reference's per-epoch checkpoint dict (convolutional_trainer.py:76-86): same keys, same state_dict
+    names, so either implementation can resume from the other's file."""
+    torch.save({'experiment_name': experiment_name, 'epoch': epoch + 1,
+                'model': {k: v.detach().clone() for k, v in step.model.state_dict().items()},
+                'optimizer': optimizer_state_dict(step),
+                'train_res_recon_error': train_res_recon_error, 'train_res_perplexity': train_res_perplexity}, path)
+
+
+def load_checkpoint(step, path, map_location=None):
+    """Restores model + optimizer state from a checkpoint written by save_checkpoint or by the reference trainer."""
+    ck = torch.load(path, map_location=map_location, weights_only=False)
+    with torch.no_grad():
+        sd = step.model.state_dict()
+        for k, v in ck['model'].items():
+            sd[k].copy_(v)                 # in place: parameters are views of the flat buffer
+    load_optimizer_state_dict(step, ck['optimizer'])
+    return ck
+
+
 def reference_config(**over):
     """The hot-path keys of configurations/vctk_features.yaml (:36-85) with the vq44-mfcc39 experiment's values."""
     cfg = dict(output_features_filters=13, augment_output_features=True, output_features_dim=47, verbose=False,
