@@ -5,8 +5,8 @@ the contract implemented here is SURVEY.md 8e:
   * the batch is sharded over ranks; every rank holds the full (bit-identical) weights, codebook and EMA state;
   * EMA statistics [counts | dw] are SUM-allreduced between the assignment and the EMA update, so every rank applies
     the same update and codebooks stay identical;
-  * gradients are SUM-allreduced in two buckets (decoder first: its backward finishes first, so its allreduce overlaps
-    the encoder's backward) and divided by world_size inside the fused AMSGrad kernel (g_scale).
+  * gradients are SUM-allreduced in buckets launched as the backward pass completes them (decoder first, so its
+    allreduces overlap the encoder's backward) and divided by world_size inside the fused AMSGrad kernel (g_scale).
 
 Nothing here touches CUDA directly, so the same class runs under gloo on CPU tensors (tests/test_parallel_cpu.py).
 """

@@ -7,7 +7,8 @@ buffers (activations, one flat parameter buffer, one flat gradient buffer, flat 
 once (ops.set_recorder) and then either replayed launch by launch or captured into a CUDA graph, so a training step costs
 one graph launch on the host.  Under data parallelism (one process per GPU, torch.distributed / NCCL) each rank runs the
 step on its batch shard; the EMA statistics [counts | dw] are sum-allreduced between the assignment and the EMA update,
-and the flat gradient buffer is allreduced in two buckets (decoder first, overlapping the encoder's backward).
+and the flat gradient buffer is allreduced in four buckets launched as the backward pass completes them (only the
+last, smallest one -- encoder conv_1..3, 14 MB -- is not hidden under backward compute).
 
 Parity contract: per rank, the step equals the reference step on that rank's shard with the same
 codebook; EMA statistics are the sum over shards; gradients are the average over shards.
@@ -109,6 +110,13 @@ class FusedTrainStep(object):
                 if first_decoder is None and name.startswith('_decoder.'):
                     first_decoder = off
         self.bucket_split = first_decoder if first_decoder is not None else total
+        # gradient allreduce buckets, in the order the backward pass completes them (flat order is encoder, pre_vq, [vq],
+        # decoder): decoder transposed convs | rest of the decoder | encoder conv_4 .. pre_vq (+ codebook) | conv_1 .. conv_3
+        offs_by_name = dict((n, o) for (n, _), o in zip(params, offs))
+        cut_t = offs_by_name.get('_decoder._conv_trans_1.weight', total)
+        cut_e = offs_by_name.get('_encoder._conv_4.weight', 0)
+        self.buckets = {'dec_convT': (cut_t, total), 'dec_rest': (self.bucket_split, cut_t),
+                        'enc_hi': (cut_e, self.bucket_split), 'enc_lo': (0, cut_e)}
         self.n_params = sum(p.numel() for _, p in params)
 
     def _p(self, name):
@@ -306,6 +314,8 @@ class FusedTrainStep(object):
         F.convT1d_wgrad(gq1, b['s'], G[DEC + '_conv_trans_1.weight'], 1, ws)
         ops.bias_grad(gq1, G[DEC + '_conv_trans_1.bias'])
         tdgrad(gq1, DEC + '_conv_trans_1.weight', L2, 1, out=g, mask=b['s'], mask_kind=MASK_FLOAT)
+        if self.world > 1:       # the three transposed convs are done: their gradients start travelling now
+            ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_convT']))
         other = self._view('gB2', C, L2)
         R_dec = d['R_dec']
         gh = self._view('gH2', R_dec, L2)
@@ -326,8 +336,8 @@ class FusedTrainStep(object):
             ops.jitter_bwd(b['gqj'], b['jitter_src'], gq)
         else:
             cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=gq)
-        if self.world > 1:       # decoder gradients are complete: start their allreduce under the encoder's backward
-            ops.record_callable(lambda: self._allreduce_bucket(self.bucket_split, self.flat_g.numel()))
+        if self.world > 1:       # decoder gradients are complete: allreduce the rest of them under the encoder's backward
+            ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_rest']))
 
         # ---- 6. VQ backward (autograd of ema.py:165-169 / vector_quantizer.py:136-141), upstream d(loss)/d(vq_loss) = 1
         n_local = B * Tq
@@ -370,6 +380,8 @@ class FusedTrainStep(object):
         gp3 = b['gA1']
         cdgrad(gp4, E + '_conv_4.weight', Tq, 1, 1, out=gp3, add_pre=gh4, mask=b['a3'],
                        mask_kind=MASK_FLOAT)
+        if self.world > 1:       # conv_4 .. pre_vq (and the codebook gradient) are final
+            ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_hi']))
         # conv_3 (k4 s2 p2): a3 = relu(conv3(h2))
         F.conv1d_wgrad(gp3, b['h2'], G[E + '_conv_3.weight'], 2, 2, ws)
         ops.bias_grad(gp3, G[E + '_conv_3.bias'])
@@ -387,7 +399,7 @@ class FusedTrainStep(object):
         # ---- 8. gradient allreduce (average) + fused AMSGrad over the flat buffers (trainer.py:41-42,68) ----
         g_scale = 1.0
         if self.world > 1:
-            ops.record_callable(lambda: self._allreduce_bucket(0, self.bucket_split))
+            ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_lo']))
             ops.record_callable(self._wait_buckets)
             g_scale = self.comm.grad_scale
         ops.amsgrad_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, self.opt_step, self.lr,
