@@ -232,6 +232,12 @@ int vqs_add(const float* a, const float* b, long long n, float* out, vqs_stream_
 /* strided (B, L, C) -> NCL (B, C, L) copy: the `.permute(0, 2, 1).contiguous().float()` of convolutional_vq_vae.py:118. */
 int vqs_blc_to_ncl(const float* in, int B, int L, int C, float* out, vqs_stream_t stream);
 
+/* Feature normalisation of the data feed, on the GPU (reference: `(dic['input_features'] - train_mean) / train_std` in
+ * numpy float64, src/dataset/vctk_features_dataset.py:56-58, then `.float()` in convolutional_vq_vae.py:118):
+ *   out[i] = (float)((in[i] - mean[i % F]) / std[i % F])      in float64 -> bit-identical to the reference's values. */
+int vqs_normalize_features(const double* in, const double* mean, const double* stdev, long long n, int F, float* out,
+                           vqs_stream_t stream);
+
 /* torch.optim.Adam(amsgrad=True, weight_decay=0) over one flat fp32 buffer, one launch:
  *   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; vmax <- max(vmax, v)
  *   p <- p - (lr / bc1) * m / (sqrt(vmax) / sqrt(bc2) + eps),  bc1 = 1 - b1^step, bc2 = 1 - b2^step

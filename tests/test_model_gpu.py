@@ -205,3 +205,20 @@ def test_checkpoint_roundtrip_and_torch_adam_compat(tmp_path):
     eng2.step(torch.from_numpy(g['x1']))
     for k, v in model2.state_dict().items():
         assert torch.equal(v, want[k]), k
+
+
+def test_feature_batcher_matches_reference_normalisation():
+    """on-GPU normalisation == the reference's numpy float64 `(x - mean) / std` followed by .float()."""
+    dev = _dev()
+    from vq_vae_speech_b200.data import FeatureBatcher
+    rng = np.random.RandomState(3)
+    mean, std = rng.randn(39) * 10, np.abs(rng.randn(39)) * 5 + 0.5
+    items = [{'input_features': rng.randn(47, 39) * 12 + 3, 'speaker_id': i} for i in range(8)]
+    fb = FeatureBatcher(4, 47, dev, {'train_mean': mean, 'train_std': std}, rank=1, world_size=2)
+    mine = fb.shard(items)
+    assert [m['speaker_id'] for m in mine] == [4, 5, 6, 7]
+    got = fb.collate(mine).cpu().numpy()
+    ref = np.stack([((m['input_features'] - mean) / std) for m in mine]).astype(np.float32)
+    assert np.array_equal(got, ref)
+    with pytest.raises(ValueError):
+        fb.collate(mine[:2])

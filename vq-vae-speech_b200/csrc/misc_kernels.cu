@@ -146,6 +146,15 @@ __global__ void mse_finalize_kernel(const double* __restrict__ partials, int G, 
   if (threadIdx.x == 0) loss[0] = (float)(red[0] / numel);
 }
 
+__global__ void normalize_features_kernel(const double* __restrict__ in, const double* __restrict__ mean,
+                                          const double* __restrict__ stdev, long long n, int F,
+                                          float* __restrict__ out) {
+  GRID_STRIDE(i, n) {
+    const int f = (int)(i % F);
+    out[i] = (float)((in[i] - mean[f]) / stdev[f]);
+  }
+}
+
 __global__ void step_inc_kernel(long long* step) { step[0] += 1; }
 
 // torch.optim.Adam(amsgrad=True) single-tensor formulation (torch/optim/adam.py::_single_tensor_adam):
@@ -254,6 +263,14 @@ extern "C" int vqs_blc_to_ncl(const float* in, int B, int L, int C, float* out, 
   VQS_CHECK_ARG(in && out && B > 0 && L > 0 && C > 0 && B <= 65535, "vqs_blc_to_ncl: bad arguments");
   dim3 grid((L + 31) / 32, (C + 31) / 32, B), block(32, 8);
   blc_to_ncl_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, B, L, C, out);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vqs_normalize_features(const double* in, const double* mean, const double* stdev, long long n, int F,
+                                      float* out, vqs_stream_t stream) {
+  VQS_CHECK_ARG(in && mean && stdev && out && n > 0 && F > 0, "vqs_normalize_features: bad arguments");
+  normalize_features_kernel<<<ew_grid(n), EW_T, 0, (cudaStream_t)stream>>>(in, mean, stdev, n, F, out);
   VQS_LAUNCH_CHECK();
   return 0;
 }

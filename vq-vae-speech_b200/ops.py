@@ -354,3 +354,14 @@ def amsgrad_step(p, g, m, v, vmax, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, g
     _call('vqs_amsgrad_step', (_p(p), _p(g), _p(m), _p(v), _p(vmax), p.numel(), _p(step, torch.int64),
                                             int(inc_step), float(lr), float(beta1), float(beta2), float(eps),
                                             float(g_scale)))
+
+
+def normalize_features(x64, mean64, std64, out=None):
+    """(x - mean) / std in float64 on the device, stored as float32 (the reference normalises in numpy float64 and casts
+    with .float()): x64 (..., F) float64, mean64 / std64 (F,) float64."""
+    F = x64.shape[-1]
+    if out is None:
+        out = torch.empty(x64.shape, dtype=torch.float32, device=x64.device)
+    _call('vqs_normalize_features', (_p(x64, torch.float64), _p(mean64, torch.float64), _p(std64, torch.float64),
+                                     x64.numel(), F, _p(out)))
+    return out
