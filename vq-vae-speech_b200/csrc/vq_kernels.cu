@@ -653,6 +653,10 @@ namespace vqs {
 bool assign_tc_supported(int K, int D);
 int launch_assign_tc(const float* z, int layout, int B, int D, int T, const float* cb, int K, int64_t* idx,
                      float* partials, int max_grid, int* grid_out, cudaStream_t st);
+// vq_assign_tma.cu
+bool assign_tma_supported(int layout, int K, int D, long long N);
+int launch_assign_tma(const float* z, long long N, const float* cb, int K, int64_t* idx, float* partials, int max_grid,
+                      int* grid_out, cudaStream_t st);
 bool search_large_supported(int K, int D);
 size_t search_large_workspace_bytes(int K, int D);
 int launch_search_large(const float* z, int layout, int B, int D, int T, const float* cb, int K, int64_t* idx,
@@ -702,6 +706,17 @@ extern "C" int vqs_vq_assign(const float* z, int layout, int B, int D, int T, co
   if (workspace_bytes < vqs_vq_workspace_bytes(K, D)) {
     set_error("vqs_vq_assign: workspace %zu < %zu", workspace_bytes, vqs_vq_workspace_bytes(K, D));
     return VQS_ERR_WORKSPACE;
+  }
+  const long long Nrows = (long long)B * T;
+  if (g_vq_engine <= 1 && dmin2 == nullptr && distances == nullptr && assign_tma_supported(layout, K, D, Nrows) &&
+      (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (g_vq_engine == 0 || Nrows >= 4096)) {
+    // streaming engine for flat rows: TMA-fed raw tf32 filter on tcgen05 + exact fp32 settlement (same indices)
+    int grid = 0;
+    if (int e = launch_assign_tma(z, Nrows, codebook, K, idx, (float*)workspace, 4 * num_sms(), &grid, st)) return e;
+    const int S = K * (D + 1);
+    stats_reduce_kernel<<<(S + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, S, stats);
+    VQS_LAUNCH_CHECK();
+    return 0;
   }
   if (g_vq_engine == 0 && dmin2 == nullptr && distances == nullptr && assign_tc_supported(K, D) &&
       (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
