@@ -11,14 +11,15 @@
 //     random rows) its two candidates are re-scored in fp32 by the whole warp; only if those land within 4e-5 of each
 //     other (or a third candidate is close) the row is settled with the CUDA-core kernel's own formula and summation
 //     order -- so the indices are IDENTICAL to the fp32 search (torch.argmin semantics, lowest index on ties);
-//   * per-code statistics (counts, dw = encodings^T x) without atomics: the tile's rows are counting-sorted by code
-//     (ranks from match.any in the scan warps, offsets from one warp scan), eight warps sum runs of equal codes in
-//     registers from the same shared-memory tile and add each run to the CTA's private bins in a fixed order
-//     (run continuations across warp ranges go through a carry slot) -> deterministic.
-// Warp roles (576 threads, one persistent CTA per SM): warps 0-7 scan (two groups alternating tiles, TMEM lane quarter =
-// warp % 4), warps 8-15 statistics, warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer.
+//   * per-code statistics (dw = encodings^T x) without floating-point atomics and without barriers: each of the four
+//     statistics warps owns 32 rows of every tile and a PRIVATE copy of the bins in shared memory (lane = column pair),
+//     so its read-add-write sequences are ordered and the final sum over warps / CTAs is fixed -> deterministic.  Counts
+//     are integers (match.any + one shared-memory atomic per distinct code and warp).
+// Warp roles (448 threads, one persistent CTA per SM): warps 0-7 scan (two groups alternating tiles, TMEM lane quarter =
+// warp % 4), warps 8-11 statistics, warp 12 TMA producer, warp 13 TMEM allocator + MMA issuer.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -30,6 +31,7 @@ struct AssignTmaParams {
   float* partials;  // [grid][K*65]
   long long N;
   int K, Kpad, ntiles;
+  int debug;   // profiling aid (env VQS_TMA_DEBUG): bit 0 skips the statistics pass, bit 1 the settlement, bit 2 the scan
 };
 
 namespace {
@@ -37,11 +39,12 @@ namespace {
 constexpr int TR = 128;                  // rows per tile
 constexpr int XT = TR * 128;             // bytes of one k-block image (32 columns)
 constexpr int TILE_BYTES = 2 * XT;       // 32 KB
-constexpr int NSTAGE = 4;
-constexpr int SCAN_WARPS = 8, STAT_WARPS = 8;
+constexpr int NSTAGE = 5;
+constexpr int SCAN_WARPS = 8, STAT_WARPS = 4;
+constexpr int SROWS = TR / STAT_WARPS;   // rows of a tile per statistics warp
 constexpr int TMA_WARP = SCAN_WARPS + STAT_WARPS, MMA_WARP = TMA_WARP + 1;
 constexpr int NT = (MMA_WARP + 1) * 32;
-constexpr int KMAX = 64;
+constexpr int KMAX = 48;              // four private bin copies of K x 64 floats must fit beside the tile ring
 // Tensor-core filter.  kind::tf32 drops the low 13 mantissa bits of both operands: |x_j e_j - tf32(x_j) tf32(e_j)| <
 // (2 * 2^-10 + 2^-20) |x_j e_j|, so the score error is < 2 * 1.955e-3 |x||e_k| <= 1.955e-3 (|x|^2 + |e_k|^2); packing the
 // code index into 6 mantissa bits adds < 1.6e-5, the fp32 rounding of the formula itself < 1e-5 of the same scale.
@@ -130,18 +133,12 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
   const int K = p.K, Kpad = p.Kpad;
   uint8_t* xs = smem;                                               // [NSTAGE][2 k-blocks][128 rows][128 B], raw fp32
   uint8_t* cbs = xs + NSTAGE * TILE_BYTES;                          // [2 k-blocks][Kpad codes][128 B], raw fp32
-  float* dw_s = reinterpret_cast<float*>(cbs + 2 * Kpad * 128);     // [Kpad][64] this CTA's dw bins
-  float* se = dw_s + Kpad * 64;                                     // [64]  |e_k|^2
-  float* sea = se + KMAX;                                           // [64]  |e_k|^2 (1 - EPS1), BIG beyond K
-  int* cnt_s = reinterpret_cast<int*>(sea + KMAX);                  // [64]  this CTA's counts
-  int* cw = cnt_s + KMAX;                                           // [2][4][64] rows per (tile parity, scan warp, code)
-  int* qoff = cw + 2 * 4 * KMAX;                                    // [4][64] first sorted position of (scan warp, code)
-  int* start = qoff + 4 * KMAX;                                     // [64] first sorted position of a code
-  int* sidx = start + KMAX;                                         // [2][128] code | rank << 8 (-1: no row)
-  int* order = sidx + 2 * TR;                                       // [128] sorted: row * 128 | code << 16
-  float* carry = reinterpret_cast<float*>(order + TR);              // [8][64] run continuations
-  int* carryk = reinterpret_cast<int*>(carry + STAT_WARPS * 64);    // [8]
-  Sh* sh = reinterpret_cast<Sh*>(carryk + STAT_WARPS);
+  float* bins = reinterpret_cast<float*>(cbs + 2 * Kpad * 128);     // [STAT_WARPS][K][64] private dw bins
+  float* se = bins + STAT_WARPS * K * 64;                           // [KMAX]  |e_k|^2
+  float* sea = se + KMAX;                                           // [KMAX]  |e_k|^2 (1 - EPS1), BIG beyond K
+  int* cnt_s = reinterpret_cast<int*>(sea + KMAX);                  // [KMAX]  this CTA's counts
+  int* sidx = cnt_s + KMAX;                                         // [2][128] code of every row of a tile
+  Sh* sh = reinterpret_cast<Sh*>(sidx + 2 * TR);
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -163,8 +160,8 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
     const int k = e >> 6, j = e & 63;
     const float v = (k < K) ? __ldg(p.cb + (size_t)k * 64 + j) : 0.f;
     *reinterpret_cast<float*>(cbs + elem_off64(k, j, Kpad)) = v;
-    dw_s[e] = 0.f;
   }
+  for (int e = tid; e < STAT_WARPS * K * 64; e += NT) bins[e] = 0.f;
   for (int k = tid; k < KMAX; k += NT) {
     float s = 0.f;
     if (k < K)
@@ -176,8 +173,6 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
     sea[k] = (k < K) ? s * (1.f - EPS1) : BIG;
     cnt_s[k] = 0;
   }
-  for (int i = tid; i < 2 * 4 * KMAX; i += NT) cw[i] = 0;
-  if (tid < STAT_WARPS) carryk[tid] = -1;
   fence_proxy_async();   // the codebook image was written through the generic proxy
   tc_fence_before();
   __syncthreads();
@@ -227,9 +222,10 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
     }
     __syncwarp();
   } else if (warp < SCAN_WARPS) {
-    // ================= scan warps: scores -> index, rank of the row inside its code =================
+    // ================= scan warps: scores -> index =================
     const int g = warp >> 2, q = warp & 3;
     const int r = q * 32 + lane;
+    const int sub = lane >> 3, u8 = lane & 7;          // settlement: 8 lanes per row, lane = 8 columns
     for (int it = g; it < my_tiles; it += 2) {
       const int s = it % NSTAGE;
       const uint32_t ph2 = (uint32_t)(it >> 1) & 1u;
@@ -238,75 +234,171 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
       const int rows = left < TR ? (int)left : TR;
       const uint8_t* xt = xs + s * TILE_BYTES;
       mbar_wait(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);   // acquire the TMA writes for this thread's own reads
+      // |x|^2 (any order: it only scales the bounds) while the MMAs run; lanes walk the 16-byte chunks of their row in a
+      // rotated order so that every quarter-warp touches 8 distinct bank groups; four independent chains
+      float sx;
+      {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < ((p.debug & 2) ? 0 : 2); ++kb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int pc = (r + i) & 7;
+            const float4 h = *reinterpret_cast<const float4*>(xt + kb * XT + r * 128 + (pc << 4));
+            a0 = fmaf(h.x, h.x, a0);
+            a1 = fmaf(h.y, h.y, a1);
+            a2 = fmaf(h.z, h.z, a2);
+            a3 = fmaf(h.w, h.w, a3);
+          }
+        }
+        sx = ((a0 + a1) + (a2 + a3)) * 1.0001f;
+      }
       mbar_wait(&sh->tmem_full[g], ph2);
       tc_fence_after();
-      // ---- lower bounds adj_k = |e_k|^2 (1 - EPS1) - 2 x.e_k with k in the low 6 mantissa bits: three smallest ----
-      float b = INFINITY, s2 = INFINITY, t3 = INFINITY;
+      // ---- lower bounds adj_k = |e_k|^2 (1 - EPS1) - 2 x.e_k with k in the low 6 mantissa bits: three smallest, kept by
+      //      two independent min/max chains (even / odd codes) ----
+      float b = INFINITY, s2 = INFINITY, t3 = INFINITY, b1 = INFINITY, s21 = INFINITY, t31 = INFINITY;
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * Kpad);
-      for (int c0 = 0; c0 < Kpad; c0 += 16) {
+      for (int c0 = 0; c0 < ((p.debug & 4) ? 16 : Kpad); c0 += 16) {
         float v[16];
         tmem_ld16(ta + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float adj = fmaf(-2.f, v[j], sea[c0 + j]);
-          const float key = __uint_as_float((__float_as_uint(adj) & 0xFFFFFFC0u) | (uint32_t)(c0 + j));
-          const float hi1 = fmaxf(b, key);
-          b = fminf(b, key);
-          const float hi2 = fmaxf(s2, hi1);
-          s2 = fminf(s2, hi1);
-          t3 = fminf(t3, hi2);
+        for (int j = 0; j < 16; j += 2) {
+          const float adj0 = fmaf(-2.f, v[j], sea[c0 + j]), adj1 = fmaf(-2.f, v[j + 1], sea[c0 + j + 1]);
+          const float key0 = __uint_as_float((__float_as_uint(adj0) & 0xFFFFFFC0u) | (uint32_t)(c0 + j));
+          const float key1 = __uint_as_float((__float_as_uint(adj1) & 0xFFFFFFC0u) | (uint32_t)(c0 + j + 1));
+          const float h0 = fmaxf(b, key0), h1 = fmaxf(b1, key1);
+          b = fminf(b, key0);
+          b1 = fminf(b1, key1);
+          const float g0 = fmaxf(s2, h0), g1 = fmaxf(s21, h1);
+          s2 = fminf(s2, h0);
+          s21 = fminf(s21, h1);
+          t3 = fminf(t3, g0);
+          t31 = fminf(t31, g1);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->tmem_empty[g]);   // the accumulator can be overwritten
+      // merge the chains: push (b1, s21, t31) into (b, s2, t3)
+      {
+        float h = fmaxf(b, b1);
+        b = fminf(b, b1);
+        float gg = fmaxf(s2, h);
+        s2 = fminf(s2, h);
+        t3 = fminf(t3, gg);
+        h = fmaxf(b, s21);       // s21 >= b1 >= new b: only second / third place
+        gg = fmaxf(s2, h);
+        s2 = fminf(s2, h);
+        t3 = fminf(t3, gg);
+        t3 = fminf(t3, fmaxf(s2, t31));
+      }
       const int k1 = (int)(__float_as_uint(b) & 63u);
       const int k2 = (int)(__float_as_uint(s2) & 63u);
       int bk = k1;
-      // |x|^2 (any order: it only scales the bounds); lanes walk the 16-byte chunks of their row in a rotated order so
-      // that every quarter-warp touches 8 distinct bank groups
-      float sx = 0.f;
-#pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int pc = (r + i) & 7;
-          const float4 h = *reinterpret_cast<const float4*>(xt + kb * XT + r * 128 + (pc << 4));
-          sx = fmaf(h.x, h.x, sx);
-          sx = fmaf(h.y, h.y, sx);
-          sx = fmaf(h.z, h.z, sx);
-          sx = fmaf(h.w, h.w, sx);
-        }
-      }
-      sx *= 1.0001f;
       const float tol2 = 2.f * EPS1 * (sx + se[k1]);
-      const bool close2 = !((s2 - b) > tol2);
+      const bool close2 = (p.debug & 2) ? false : !((s2 - b) > tol2);
       const bool close3 = !((t3 - b) > tol2);
-      // ---- exactly two candidates: fp32 re-score by the whole warp (lane = column pair) ----
+      // ---- exactly two candidates: fp32 re-score, four rows per pass (8 lanes per row, lane = 8 columns) ----
       unsigned m2 = __ballot_sync(0xffffffffu, close2 && !close3);
       unsigned canon = __ballot_sync(0xffffffffu, close2 && close3);
       while (m2) {
-        const int rr = __ffs(m2) - 1;
-        m2 &= m2 - 1;
-        const int R = q * 32 + rr;
-        const int c1 = __shfl_sync(0xffffffffu, k1, rr), c2 = __shfl_sync(0xffffffffu, k2, rr);
-        const float sxr = __shfl_sync(0xffffffffu, sx, rr);
-        const float2 xv = *reinterpret_cast<const float2*>(xt + elem_off64(R, 2 * lane, TR));
-        const float2 e1 = *reinterpret_cast<const float2*>(cbs + elem_off64(c1, 2 * lane, Kpad));
-        const float2 e2 = *reinterpret_cast<const float2*>(cbs + elem_off64(c2, 2 * lane, Kpad));
-        float d1 = fmaf(xv.y, e1.y, xv.x * e1.x), d2 = fmaf(xv.y, e2.y, xv.x * e2.x);
+        int rsel = -1;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int i = 0; i < 4; ++i) {
+          const int f = m2 ? __ffs(m2) - 1 : -1;
+          if (i == sub) rsel = f;
+          m2 &= m2 - 1;                                 // (0 & 0xffffffff stays 0)
+        }
+        const bool have = rsel >= 0;
+        const int src = have ? rsel : lane;
+        const int c1 = __shfl_sync(0xffffffffu, k1, src), c2 = __shfl_sync(0xffffffffu, k2, src);
+        const float sxr = __shfl_sync(0xffffffffu, sx, src);
+        const int R = q * 32 + src;
+        const int kbo = u8 >> 2, ch = (u8 & 3) * 2;     // k-block image, first of two 16-byte chunks
+        const uint8_t* xr = xt + kbo * XT + R * 128;
+        const uint8_t* e1r = cbs + kbo * Kpad * 128 + c1 * 128;
+        const uint8_t* e2r = cbs + kbo * Kpad * 128 + c2 * 128;
+        const float4 xa = *reinterpret_cast<const float4*>(xr + ((ch ^ (R & 7)) << 4));
+        const float4 xb = *reinterpret_cast<const float4*>(xr + (((ch + 1) ^ (R & 7)) << 4));
+        const float4 ea = *reinterpret_cast<const float4*>(e1r + ((ch ^ (c1 & 7)) << 4));
+        const float4 eb = *reinterpret_cast<const float4*>(e1r + (((ch + 1) ^ (c1 & 7)) << 4));
+        const float4 fa = *reinterpret_cast<const float4*>(e2r + ((ch ^ (c2 & 7)) << 4));
+        const float4 fb = *reinterpret_cast<const float4*>(e2r + (((ch + 1) ^ (c2 & 7)) << 4));
+        float d1 = fmaf(xa.w, ea.w, fmaf(xa.z, ea.z, fmaf(xa.y, ea.y, xa.x * ea.x))) +
+                   fmaf(xb.w, eb.w, fmaf(xb.z, eb.z, fmaf(xb.y, eb.y, xb.x * eb.x)));
+        float d2 = fmaf(xa.w, fa.w, fmaf(xa.z, fa.z, fmaf(xa.y, fa.y, xa.x * fa.x))) +
+                   fmaf(xb.w, fb.w, fmaf(xb.z, fb.z, fmaf(xb.y, fb.y, xb.x * fb.x)));
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
           d1 += __shfl_xor_sync(0xffffffffu, d1, o);
           d2 += __shfl_xor_sync(0xffffffffu, d2, o);
         }
         const float se1 = se[c1], se2 = se[c2];
         const float dd1 = (sxr + se1) - 2.f * d1, dd2 = (sxr + se2) - 2.f * d2;
         const float diff = dd1 - dd2;
-        if (fabsf(diff) > 2.f * EPS2 * (sxr + fmaxf(se1, se2))) {
-          if (lane == rr) bk = diff < 0.f ? c1 : c2;
-        } else {
-          canon |= 1u << rr;   // too close for an order-independent decision
+        const bool safe = fabsf(diff) > 2.f * EPS2 * (sxr + fmaxf(se1, se2));
+        const int win = diff < 0.f ? c1 : c2;
+        canon |= __reduce_or_sync(0xffffffffu, (have && !safe && u8 == 0) ? (1u << rsel) : 0u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int wr = __shfl_sync(0xffffffffu, (have && safe) ? rsel : -1, i * 8);
+          const int ww = __shfl_sync(0xffffffffu, win, i * 8);
+          if (lane == wr) bk = ww;
+        }
+      }
+      // ---- three or more candidates: fp32 re-score of ALL codes (lanes = codes lane, lane + 32), best two ----
+      {
+        unsigned m3 = canon;
+        canon = 0u;
+        while (m3) {
+          const int rr = __ffs(m3) - 1;
+          m3 &= m3 - 1;
+          const int R = q * 32 + rr;
+          const float sxr = __shfl_sync(0xffffffffu, sx, rr);
+          const int kA = lane, kB = lane + 32 < Kpad ? lane + 32 : lane;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll 2
+          for (int c = 0; c < 16; ++c) {
+            const int kbo = c >> 3, ch = c & 7;
+            const float4 xv = *reinterpret_cast<const float4*>(xt + kbo * XT + R * 128 + ((ch ^ (R & 7)) << 4));
+            const float4 ea = *reinterpret_cast<const float4*>(cbs + kbo * Kpad * 128 + kA * 128 + ((ch ^ (kA & 7)) << 4));
+            const float4 eb = *reinterpret_cast<const float4*>(cbs + kbo * Kpad * 128 + kB * 128 + ((ch ^ (kB & 7)) << 4));
+            a0 = fmaf(xv.x, ea.x, a0);
+            a1 = fmaf(xv.y, ea.y, a1);
+            a2 = fmaf(xv.z, ea.z, a2);
+            a3 = fmaf(xv.w, ea.w, a3);
+            c0 = fmaf(xv.x, eb.x, c0);
+            c1 = fmaf(xv.y, eb.y, c1);
+            c2 = fmaf(xv.z, eb.z, c2);
+            c3 = fmaf(xv.w, eb.w, c3);
+          }
+          const float dA = kA < K ? (sxr + se[kA]) - 2.f * ((a0 + a1) + (a2 + a3)) : BIG;
+          const float dB = lane + 32 < K ? (sxr + se[kB]) - 2.f * ((c0 + c1) + (c2 + c3)) : BIG;
+          // (best, its code, second best, its code) of this lane, then a butterfly merge
+          float m1 = dA, n1 = dB;
+          int i1 = kA, j1 = lane + 32;
+          if (n1 < m1) {
+            const float tf = m1; m1 = n1; n1 = tf;
+            const int ti = i1; i1 = j1; j1 = ti;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m1, o), on = __shfl_xor_sync(0xffffffffu, n1, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i1, o), oj = __shfl_xor_sync(0xffffffffu, j1, o);
+            if (om < m1 || (om == m1 && oi < i1)) {      // partner's best wins: second = min(my best, partner's second)
+              if (m1 < on || (m1 == on && i1 < oj)) { n1 = m1; j1 = i1; } else { n1 = on; j1 = oj; }
+              m1 = om; i1 = oi;
+            } else {                                      // mine wins: second = min(my second, partner's best)
+              if (om < n1 || (om == n1 && oi < j1)) { n1 = om; j1 = oi; }
+            }
+          }
+          const float sc2 = sxr + fmaxf(se[i1 < K ? i1 : 0], se[j1 < K ? j1 : 0]);
+          if ((n1 - m1) > 2.f * EPS2 * sc2) {
+            if (lane == rr) bk = i1;
+          } else {
+            canon |= 1u << rr;
+          }
         }
       }
       // ---- canonical settlement: same fp32 formula and summation order as the CUDA-core kernel, lanes = codes ----
@@ -341,13 +433,12 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
       }
       const bool valid = r < rows;
       if (valid) p.idx[r0 + r] = (int64_t)bk;
-      // ---- rank of this row among the rows of its scan warp with the same code (stable counting sort, part 1) ----
+      // ---- counts: one integer atomic per distinct code of this warp ----
       const int kk = valid ? bk : 255;
       const unsigned same = __match_any_sync(0xffffffffu, kk);
-      const int rank = __popc(same & ((1u << lane) - 1u));
+      if (valid && (same & ((1u << lane) - 1u)) == 0u) atomicAdd(&cnt_s[bk], __popc(same));
       mbar_wait(&sh->idx_free[g], ph2 ^ 1u);            // the statistics warps are done with tile it - 2
-      if (valid && rank == 0) cw[(g * 4 + q) * KMAX + bk] = __popc(same);
-      sidx[g * TR + r] = valid ? (bk | (rank << 8)) : -1;
+      sidx[g * TR + r] = bk;
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&sh->idx_ready[g]);
@@ -355,145 +446,88 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
       }
     }
   } else {
-    // ================= statistics warps: counting sort by code, run sums in registers, ordered bin updates =================
-    const int sw = warp - SCAN_WARPS, st = tid - SCAN_WARPS * 32;
-    const uint32_t dw_a = smem_u32(dw_s), carry_a = smem_u32(carry), order_a = smem_u32(order);
-    // this lane's column pair (2 lane, 2 lane + 1): k-block image, 16-byte chunk, byte inside the chunk
-    const uint32_t lane_base = (uint32_t)((lane >> 4) * XT + ((lane & 1) << 3));
-    const uint32_t lane_cx = (uint32_t)(((lane & 15) >> 1) << 4);
+    // ================= statistics warps: 32 rows each, private bins, ordered read-add-write =================
+    const int sw = warp - SCAN_WARPS;
+    const uint32_t bins_a = smem_u32(bins) + (uint32_t)((sw * K * 64 + 2 * lane) * 4);
+    const uint32_t sidx_a = smem_u32(sidx);
+    // this lane's column pair (2 lane, 2 lane + 1): k-block image, byte inside the chunk; 16-byte chunk index
+    const uint32_t lane_base = (uint32_t)((lane >> 4) * XT + ((lane & 1) << 3) + sw * SROWS * 128);
+    const uint32_t lane_c = (uint32_t)((lane & 15) >> 1);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % NSTAGE, a = it & 1;
       const long long r0 = (long long)(blockIdx.x + it * gridDim.x) * TR;
       const long long left = p.N - r0;
       const int rows = left < TR ? (int)left : TR;
+      const int n = rows - sw * SROWS;                 // rows of this warp that exist (may be <= 0 or > SROWS)
       mbar_wait(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);
+      // the row values do not depend on the indices: load them while the scan warps work (rows beyond N are zeros)
+      const uint32_t x_a = smem_u32(xs + s * TILE_BYTES) + lane_base;
+      float2 v[SROWS];
+#pragma unroll
+      for (int i = 0; i < SROWS; ++i) v[i] = lds_v2(x_a + (uint32_t)(i * 128) + ((((uint32_t)i & 7u) ^ lane_c) << 4));
       mbar_wait(&sh->idx_ready[a], (uint32_t)(it >> 1) & 1u);
-      const int* cwa = cw + a * 4 * KMAX;
-      if (sw == 0) {
-        // offsets: lane owns codes lane and lane + 32
-        int c0[4], c1[4];
+      if (!(p.debug & 1)) {
+        // four rows per step: their bins are fetched together, equal bins are forwarded in registers, and the stores go out
+        // in row order (a later row of the same code overwrites with the cumulative value).  Rows beyond N are zeros and
+        // carry a valid code, so they need no special case.
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          c0[q] = cwa[q * KMAX + lane];
-          c1[q] = cwa[q * KMAX + 32 + lane];
-        }
-        const int t0 = c0[0] + c0[1] + c0[2] + c0[3], t1 = c1[0] + c1[1] + c1[2] + c1[3];
-        int i0 = t0, i1 = t1;
+        for (int h = 0; h < SROWS; h += 16) {
+          int kc[16];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int u0 = __shfl_up_sync(0xffffffffu, i0, o), u1 = __shfl_up_sync(0xffffffffu, i1, o);
-          if (lane >= o) {
-            i0 += u0;
-            i1 += u1;
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const uint4 o4 = lds_u4(sidx_a + (uint32_t)((a * TR + sw * SROWS + h + i4 * 4) * 4));
+            kc[i4 * 4 + 0] = (int)o4.x;
+            kc[i4 * 4 + 1] = (int)o4.y;
+            kc[i4 * 4 + 2] = (int)o4.z;
+            kc[i4 * 4 + 3] = (int)o4.w;
           }
-        }
-        const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
-        int o0 = i0 - t0, o1 = tot0 + i1 - t1;
-        start[lane] = o0;
-        start[32 + lane] = o1;
-        cnt_s[lane] += t0;
-        cnt_s[32 + lane] += t1;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          qoff[q * KMAX + lane] = o0;
-          qoff[q * KMAX + 32 + lane] = o1;
-          o0 += c0[q];
-          o1 += c1[q];
-        }
-      }
-      bar_sync(1, STAT_WARPS * 32);
-      if (st < TR) {
-        const int v = sidx[a * TR + st];
-        if (v >= 0) {
-          const int k = v & 255, rank = v >> 8;
-          order[qoff[(st >> 5) * KMAX + k] + rank] = (st << 7) | (k << 16);
-        }
-      } else {
-        cw[a * 4 * KMAX + (st - TR)] = 0;             // the next tile of this parity starts from zero counts
-        cw[a * 4 * KMAX + st] = 0;
-      }
-      bar_sync(1, STAT_WARPS * 32);
-      // ---- this warp's 16 sorted positions: all loads first, then the run sums ----
-      const int p0 = sw * 16;
-      const int n = rows - p0 < 16 ? rows - p0 : 16;
-      if (lane == 0) carryk[sw] = -1;
-      if (n > 0) {
-        uint32_t rk[16];
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const uint4 o4 = lds_u4(order_a + (uint32_t)((p0 + i4 * 4) * 4));
-          rk[i4 * 4 + 0] = o4.x;
-          rk[i4 * 4 + 1] = o4.y;
-          rk[i4 * 4 + 2] = o4.z;
-          rk[i4 * 4 + 3] = o4.w;
-        }
-        const uint32_t x_a = smem_u32(xs + s * TILE_BYTES) + lane_base;
-        float2 v[16];
-        uint32_t lastrk = rk[0];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i < n) lastrk = rk[i];
-          else rk[i] = lastrk;                         // padding: same code, value zero
-          const uint32_t r128 = rk[i] & 0xFFFFu;
-          v[i] = lds_v2(x_a + r128 + (((r128 >> 3) & 0x70u) ^ lane_cx));
-          if (i >= n) v[i] = make_float2(0.f, 0.f);
-        }
-        int kprev = (int)(rk[0] >> 16);
-        const bool cont = start[kprev] < p0;           // the first run continues a code that began in an earlier warp's range
-        bool first = true;
-        float2 acc = v[0];
-#pragma unroll
-        for (int i = 1; i <= 16; ++i) {
-          const int k = (i < 16) ? (int)(rk[i] >> 16) : -1;
-          if (k != kprev) {                             // warp-uniform
-            if (first && cont) {
-              sts_v2(carry_a + (uint32_t)((sw * 64 + 2 * lane) * 4), acc);
-              if (lane == 0) carryk[sw] = kprev;
-            } else {
-              const uint32_t ba = dw_a + (uint32_t)((kprev * 64 + 2 * lane) * 4);
-              float2 bin = lds_v2(ba);
-              bin.x += acc.x;
-              bin.y += acc.y;
-              sts_v2(ba, bin);
+          for (int i = 0; i < 16; i += 4) {
+            if (h + i < n) {                               // warp-uniform
+              const uint32_t a0 = bins_a + (uint32_t)(kc[i] * 256), a1 = bins_a + (uint32_t)(kc[i + 1] * 256);
+              const uint32_t a2 = bins_a + (uint32_t)(kc[i + 2] * 256), a3 = bins_a + (uint32_t)(kc[i + 3] * 256);
+              float2 b0 = lds_v2(a0), b1 = lds_v2(a1), b2 = lds_v2(a2), b3 = lds_v2(a3);
+              b0.x += v[h + i].x;
+              b0.y += v[h + i].y;
+              if (a1 == a0) b1 = b0;
+              b1.x += v[h + i + 1].x;
+              b1.y += v[h + i + 1].y;
+              if (a2 == a1) b2 = b1;
+              else if (a2 == a0) b2 = b0;
+              b2.x += v[h + i + 2].x;
+              b2.y += v[h + i + 2].y;
+              if (a3 == a2) b3 = b2;
+              else if (a3 == a1) b3 = b1;
+              else if (a3 == a0) b3 = b0;
+              b3.x += v[h + i + 3].x;
+              b3.y += v[h + i + 3].y;
+              sts_v2(a0, b0);
+              sts_v2(a1, b1);
+              sts_v2(a2, b2);
+              sts_v2(a3, b3);
             }
-            first = false;
-            kprev = k;
-            acc = make_float2(0.f, 0.f);
-          }
-          if (i < 16) {
-            acc.x += v[i].x;
-            acc.y += v[i].y;
           }
         }
       }
-      bar_sync(1, STAT_WARPS * 32);
+      __syncwarp();
       if (lane == 0) {
         mbar_arrive(&sh->empty[s]);
         mbar_arrive(&sh->idx_free[a]);
-      }
-      if (sw == 0) {
-        // run continuations, in warp order
-        for (int w = 1; w < STAT_WARPS; ++w) {
-          const int kc = carryk[w];
-          if (kc >= 0) {
-            const float2 c = lds_v2(carry_a + (uint32_t)((w * 64 + 2 * lane) * 4));
-            const uint32_t ba = dw_a + (uint32_t)((kc * 64 + 2 * lane) * 4);
-            float2 bin = lds_v2(ba);
-            bin.x += c.x;
-            bin.y += c.y;
-            sts_v2(ba, bin);
-          }
-        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  // ---- publish this CTA's partial statistics ----
+  // ---- publish this CTA's partial statistics (the private bins are summed in warp order) ----
   {
     float* out = p.partials + (size_t)blockIdx.x * K * 65;
     for (int i = tid; i < K; i += NT) out[i] = (float)cnt_s[i];
-    for (int i = tid; i < K * 64; i += NT) out[K + i] = dw_s[i];
+    for (int i = tid; i < K * 64; i += NT) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < STAT_WARPS; ++w) a += bins[w * K * 64 + i];
+      out[K + i] = a;
+    }
   }
   if (warp == MMA_WARP) {
     tc_fence_after();
@@ -517,10 +551,9 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-size_t smem_bytes_tma(int Kpad) {
-  size_t b = (size_t)NSTAGE * TILE_BYTES + (size_t)2 * Kpad * 128 + (size_t)Kpad * 64 * 4;
-  b += (size_t)(2 * KMAX) * 4 + (size_t)KMAX * 4 + (size_t)(2 * 4 * KMAX) * 4 + (size_t)(4 * KMAX) * 4 + (size_t)KMAX * 4;
-  b += (size_t)(2 * TR) * 4 + (size_t)TR * 4 + (size_t)STAT_WARPS * 64 * 4 + (size_t)STAT_WARPS * 4 + sizeof(Sh);
+size_t smem_bytes_tma(int K, int Kpad) {
+  size_t b = (size_t)NSTAGE * TILE_BYTES + (size_t)2 * Kpad * 128 + (size_t)STAT_WARPS * K * 64 * 4;
+  b += (size_t)(3 * KMAX) * 4 + (size_t)(2 * TR) * 4 + sizeof(Sh);
   return b + 1024 + 64;
 }
 
@@ -555,7 +588,11 @@ int launch_assign_tma(const float* z, long long N, const float* cb, int K, int64
   p.cb = cb; p.idx = idx; p.partials = partials; p.N = N; p.K = K;
   p.Kpad = (K + 15) / 16 * 16;
   p.ntiles = (int)((N + TR - 1) / TR);
-  const size_t smem = smem_bytes_tma(p.Kpad);
+  {
+    const char* dbg = getenv("VQS_TMA_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  const size_t smem = smem_bytes_tma(K, p.Kpad);
   static size_t configured = 0;
   if (smem > configured) {
     VQS_CUDA(cudaFuncSetAttribute(vq_assign_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
