@@ -257,7 +257,8 @@ def vq_bench(dev, pk, rows, K=44, D=64, iters=20):
     out['peak_source'] = pk['src']
     out['bytes_per_row'] = 20 * D + 16
     out['K'], out['D'] = K, D
-    out['search_engine'] = 'cuda_core (exact fp32 FMA); the tcgen05 engine is opt-in (ops.vq_set_engine)'
+    out['search_engine'] = ('auto: flat rows -> streaming engine (TMA tiles as raw tf32 tcgen05 operands + exact fp32 '
+                            'settlement, identical indices); (B,D,T) rows -> CUDA cores (exact fp32 FMA)')
     return out
 
 

@@ -274,6 +274,9 @@ TC_CASES = [  # (K, D, B, T, layout, data)
     # a few enormous codes (what the first EMA steps do to never-used codes): the per-code error bound must not
     # push every row into the exact path, and indices must still agree
     (44, 64, 8, 96, 'bdt', 'huge'), (4096, 64, 8, 96, 'bdt', 'huge'),
+    # flat rows, K <= 48: the streaming engine (TMA tiles as raw tf32 operands, vq_assign_tma_kernel)
+    (29, 64, 1, 5000, 'flat', 'trained'), (48, 64, 1, 4097, 'flat', 'randn'), (1, 64, 1, 300, 'flat', 'randn'),
+    (44, 64, 1, 100, 'flat', 'near_dup'), (17, 64, 1, 33000, 'flat', 'huge'), (44, 64, 1, 1 << 20, 'flat', 'trained'),
 ]
 
 

@@ -15,8 +15,8 @@
 //     statistics warps owns 32 rows of every tile and a PRIVATE copy of the bins in shared memory (lane = column pair),
 //     so its read-add-write sequences are ordered and the final sum over warps / CTAs is fixed -> deterministic.  Counts
 //     are integers (match.any + one shared-memory atomic per distinct code and warp).
-// Warp roles (448 threads, one persistent CTA per SM): warps 0-7 scan (two groups alternating tiles, TMEM lane quarter =
-// warp % 4), warps 8-11 statistics, warp 12 TMA producer, warp 13 TMEM allocator + MMA issuer.
+// Warp roles (576 threads, one persistent CTA per SM): warps 0-11 scan (three groups taking tiles round-robin, TMEM lane
+// quarter = warp % 4), warps 12-15 statistics, warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -40,7 +40,9 @@ constexpr int TR = 128;                  // rows per tile
 constexpr int XT = TR * 128;             // bytes of one k-block image (32 columns)
 constexpr int TILE_BYTES = 2 * XT;       // 32 KB
 constexpr int NSTAGE = 5;
-constexpr int SCAN_WARPS = 8, STAT_WARPS = 4;
+constexpr int NGROUP = 3;                // scan groups (4 warps each) taking tiles round-robin, one TMEM accumulator each
+constexpr int SCAN_WARPS = 4 * NGROUP, STAT_WARPS = 4;
+constexpr int NIDX = 4;                  // index buffers between the scan and the statistics warps
 constexpr int SROWS = TR / STAT_WARPS;   // rows of a tile per statistics warp
 constexpr int TMA_WARP = SCAN_WARPS + STAT_WARPS, MMA_WARP = TMA_WARP + 1;
 constexpr int NT = (MMA_WARP + 1) * 32;
@@ -54,14 +56,15 @@ constexpr float EPS2 = 2.0e-5f;
 constexpr float BIG = 3.0e38f;
 
 struct Sh {
-  uint64_t full[NSTAGE], empty[NSTAGE], tmem_full[2], tmem_empty[2], idx_ready[2], idx_free[2];
+  uint64_t full[NSTAGE], empty[NSTAGE], tmem_full[NGROUP], tmem_empty[NGROUP], idx_ready[NIDX], idx_free[NIDX];
   uint32_t tmem_base;
 };
 
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+// issues the load only: tmem_ld_wait() before the values are used
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -70,10 +73,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
                "r"(bytes)
@@ -90,6 +93,21 @@ __device__ __forceinline__ float2 lds_v2(uint32_t addr) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
   return v;
 }
+template <int IMM>
+__device__ __forceinline__ float4 lds_v4_imm(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4 + %5];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr), "n"(IMM)
+               : "memory");
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ float2 lds_v2_imm(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + %3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(IMM) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts_v2(uint32_t addr, float2 v) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
@@ -97,6 +115,98 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
+}
+
+// one physical 16-byte chunk (both k-block images) of a row against the matching chunks of two code rows
+__device__ __forceinline__ void settle_chunk(uint32_t xa, uint32_t pc4, uint32_t e1a, uint32_t e2a, uint32_t e1b,
+                                             uint32_t e2b, float (&p)[4], float (&q)[4]) {
+  {
+    const float4 xv = lds_v4_imm<0>(xa);
+    const float4 ea = lds_v4_imm<0>(e1a ^ pc4), eb = lds_v4_imm<0>(e2a ^ pc4);
+    p[0] = fmaf(xv.x, ea.x, p[0]);
+    p[1] = fmaf(xv.y, ea.y, p[1]);
+    p[2] = fmaf(xv.z, ea.z, p[2]);
+    p[3] = fmaf(xv.w, ea.w, p[3]);
+    q[0] = fmaf(xv.x, eb.x, q[0]);
+    q[1] = fmaf(xv.y, eb.y, q[1]);
+    q[2] = fmaf(xv.z, eb.z, q[2]);
+    q[3] = fmaf(xv.w, eb.w, q[3]);
+  }
+  {
+    const float4 xv = lds_v4_imm<XT>(xa);
+    const float4 ea = lds_v4_imm<0>(e1b ^ pc4), eb = lds_v4_imm<0>(e2b ^ pc4);
+    p[0] = fmaf(xv.x, ea.x, p[0]);
+    p[1] = fmaf(xv.y, ea.y, p[1]);
+    p[2] = fmaf(xv.z, ea.z, p[2]);
+    p[3] = fmaf(xv.w, ea.w, p[3]);
+    q[0] = fmaf(xv.x, eb.x, q[0]);
+    q[1] = fmaf(xv.y, eb.y, q[1]);
+    q[2] = fmaf(xv.z, eb.z, q[2]);
+    q[3] = fmaf(xv.w, eb.w, q[3]);
+  }
+}
+
+// 16 rows of a statistics warp (H = 0: rows 0-15, 1: rows 16-31): this lane's column pair of every row
+template <int H>
+__device__ __forceinline__ void stats_load_half(const uint32_t (&xrow)[8], float2 (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = lds_v2_imm<H * 2048>(xrow[i]);
+    v[8 + i] = lds_v2_imm<H * 2048 + 1024>(xrow[i]);
+  }
+}
+// ... added to the warp's private bins.  Four rows per step: their bins are fetched together when all four differ (87 % of
+// random steps), otherwise one row after the other; stores in row order.  Rows beyond N are zeros and carry a valid code,
+// so they need no special case.  sidx holds the byte offset of each row's bin row.
+__device__ __forceinline__ void stats_rmw_half(uint32_t sidx_a, uint32_t bins_a, const float2 (&v)[16], int n) {
+  int kc[16];
+#pragma unroll
+  for (int i4 = 0; i4 < 4; ++i4) {
+    const uint4 o4 = lds_u4(sidx_a + (uint32_t)(i4 * 16));
+    kc[i4 * 4 + 0] = (int)o4.x;
+    kc[i4 * 4 + 1] = (int)o4.y;
+    kc[i4 * 4 + 2] = (int)o4.z;
+    kc[i4 * 4 + 3] = (int)o4.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    if (i < n) {                                        // warp-uniform
+      const uint32_t a0 = bins_a + (uint32_t)kc[i], a1 = bins_a + (uint32_t)kc[i + 1];
+      const uint32_t a2 = bins_a + (uint32_t)kc[i + 2], a3 = bins_a + (uint32_t)kc[i + 3];
+      if (a0 != a1 && a0 != a2 && a0 != a3 && a1 != a2 && a1 != a3 && a2 != a3) {
+        float2 b0 = lds_v2(a0), b1 = lds_v2(a1), b2 = lds_v2(a2), b3 = lds_v2(a3);
+        b0.x += v[i].x;
+        b0.y += v[i].y;
+        b1.x += v[i + 1].x;
+        b1.y += v[i + 1].y;
+        b2.x += v[i + 2].x;
+        b2.y += v[i + 2].y;
+        b3.x += v[i + 3].x;
+        b3.y += v[i + 3].y;
+        sts_v2(a0, b0);
+        sts_v2(a1, b1);
+        sts_v2(a2, b2);
+        sts_v2(a3, b3);
+      } else {
+        float2 b0 = lds_v2(a0);
+        b0.x += v[i].x;
+        b0.y += v[i].y;
+        sts_v2(a0, b0);
+        b0 = lds_v2(a1);
+        b0.x += v[i + 1].x;
+        b0.y += v[i + 1].y;
+        sts_v2(a1, b0);
+        b0 = lds_v2(a2);
+        b0.x += v[i + 2].x;
+        b0.y += v[i + 2].y;
+        sts_v2(a2, b0);
+        b0 = lds_v2(a3);
+        b0.x += v[i + 3].x;
+        b0.y += v[i + 3].y;
+        sts_v2(a3, b0);
+      }
+    }
+  }
 }
 
 // byte offset of element (row r, column j) of a 64-column tile stored as two k-block images of `rows` x 128 B
@@ -137,24 +247,26 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
   float* se = bins + STAT_WARPS * K * 64;                           // [KMAX]  |e_k|^2
   float* sea = se + KMAX;                                           // [KMAX]  |e_k|^2 (1 - EPS1), BIG beyond K
   int* cnt_s = reinterpret_cast<int*>(sea + KMAX);                  // [KMAX]  this CTA's counts
-  int* sidx = cnt_s + KMAX;                                         // [2][128] code of every row of a tile
-  Sh* sh = reinterpret_cast<Sh*>(sidx + 2 * TR);
+  int* sidx = cnt_s + KMAX;                                         // [NIDX][128] code of every row of a tile
+  Sh* sh = reinterpret_cast<Sh*>(sidx + NIDX * TR);
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&sh->full[s], 1);
       mbar_init(&sh->empty[s], 1 + 4 + STAT_WARPS);   // score MMAs (commit) + the tile's scan group + statistics warps
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NGROUP; ++a) {
       mbar_init(&sh->tmem_full[a], 1);
       mbar_init(&sh->tmem_empty[a], 4);
+    }
+    for (int a = 0; a < NIDX; ++a) {
       mbar_init(&sh->idx_ready[a], 4);
       mbar_init(&sh->idx_free[a], STAT_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * Kpad) tmem_cols <<= 1;
+  while ((int)tmem_cols < NGROUP * Kpad) tmem_cols <<= 1;
   if (warp == MMA_WARP) tmem_alloc(&sh->tmem_base, tmem_cols);
   for (int e = tid; e < Kpad * 64; e += NT) {
     const int k = e >> 6, j = e & 63;
@@ -186,7 +298,7 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
       for (int it = 0; it < my_tiles; ++it) {
         const int s = it % NSTAGE;
         const long long r0 = (long long)(blockIdx.x + it * gridDim.x) * TR;
-        mbar_wait(&sh->empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
+        mbar_wait_sleep(&sh->empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
         mbar_expect_tx(&sh->full[s], TILE_BYTES);
         const uint32_t dst = smem_u32(xs + s * TILE_BYTES);
         tma_load_2d(dst, &tmap, 0, (int)r0, &sh->full[s]);         // rows beyond N arrive as zeros
@@ -200,9 +312,9 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
       const uint32_t idesc = make_idesc_tf32(Kpad);
       const uint32_t cb_a = smem_u32(cbs);
       for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % NSTAGE, a = it & 1;
-        mbar_wait(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);
-        mbar_wait(&sh->tmem_empty[a], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        const int s = it % NSTAGE, a = it % NGROUP;
+        mbar_wait_sleep(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);
+        mbar_wait_sleep(&sh->tmem_empty[a], ((uint32_t)(it / NGROUP) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t x_a = smem_u32(xs + s * TILE_BYTES);
         const uint32_t dst = tmem_base + (uint32_t)(a * Kpad);
@@ -225,56 +337,65 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
     // ================= scan warps: scores -> index =================
     const int g = warp >> 2, q = warp & 3;
     const int r = q * 32 + lane;
-    const int sub = lane >> 3, u8 = lane & 7;          // settlement: 8 lanes per row, lane = 8 columns
-    for (int it = g; it < my_tiles; it += 2) {
+    for (int it = g; it < my_tiles; it += NGROUP) {
       const int s = it % NSTAGE;
-      const uint32_t ph2 = (uint32_t)(it >> 1) & 1u;
+      const uint32_t ph2 = (uint32_t)(it / NGROUP) & 1u;
       const long long r0 = (long long)(blockIdx.x + it * gridDim.x) * TR;
       const long long left = p.N - r0;
       const int rows = left < TR ? (int)left : TR;
       const uint8_t* xt = xs + s * TILE_BYTES;
-      mbar_wait(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);   // acquire the TMA writes for this thread's own reads
+      mbar_wait_sleep(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);   // acquire the TMA writes for this thread's own reads
       // |x|^2 (any order: it only scales the bounds) while the MMAs run; lanes walk the 16-byte chunks of their row in a
       // rotated order so that every quarter-warp touches 8 distinct bank groups; four independent chains
       float sx;
       {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int kb = 0; kb < ((p.debug & 2) ? 0 : 2); ++kb) {
+        // physical chunk (r & 7) ^ i: row base and chunk offset combine by XOR (the row base is 128-byte aligned)
+        const uint32_t x0 = (smem_u32(xt) + (uint32_t)(r * 128)) ^ (uint32_t)((r & 7) << 4);
+        if (!(p.debug & 2)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int pc = (r + i) & 7;
-            const float4 h = *reinterpret_cast<const float4*>(xt + kb * XT + r * 128 + (pc << 4));
+            const float4 h = lds_v4_imm<0>(x0 ^ (uint32_t)(i << 4)), h2 = lds_v4_imm<XT>(x0 ^ (uint32_t)(i << 4));
             a0 = fmaf(h.x, h.x, a0);
             a1 = fmaf(h.y, h.y, a1);
             a2 = fmaf(h.z, h.z, a2);
             a3 = fmaf(h.w, h.w, a3);
+            a0 = fmaf(h2.x, h2.x, a0);
+            a1 = fmaf(h2.y, h2.y, a1);
+            a2 = fmaf(h2.z, h2.z, a2);
+            a3 = fmaf(h2.w, h2.w, a3);
           }
         }
         sx = ((a0 + a1) + (a2 + a3)) * 1.0001f;
       }
-      mbar_wait(&sh->tmem_full[g], ph2);
+      mbar_wait_sleep(&sh->tmem_full[g], ph2);
       tc_fence_after();
       // ---- lower bounds adj_k = |e_k|^2 (1 - EPS1) - 2 x.e_k with k in the low 6 mantissa bits: three smallest, kept by
       //      two independent min/max chains (even / odd codes) ----
       float b = INFINITY, s2 = INFINITY, t3 = INFINITY, b1 = INFINITY, s21 = INFINITY, t31 = INFINITY;
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * Kpad);
-      for (int c0 = 0; c0 < ((p.debug & 4) ? 16 : Kpad); c0 += 16) {
-        float v[16];
-        tmem_ld16(ta + (uint32_t)c0, v);
+      float v[KMAX];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float adj0 = fmaf(-2.f, v[j], sea[c0 + j]), adj1 = fmaf(-2.f, v[j + 1], sea[c0 + j + 1]);
-          const float key0 = __uint_as_float((__float_as_uint(adj0) & 0xFFFFFFC0u) | (uint32_t)(c0 + j));
-          const float key1 = __uint_as_float((__float_as_uint(adj1) & 0xFFFFFFC0u) | (uint32_t)(c0 + j + 1));
-          const float h0 = fmaxf(b, key0), h1 = fmaxf(b1, key1);
-          b = fminf(b, key0);
-          b1 = fminf(b1, key1);
-          const float g0 = fmaxf(s2, h0), g1 = fmaxf(s21, h1);
-          s2 = fminf(s2, h0);
-          s21 = fminf(s21, h1);
-          t3 = fminf(t3, g0);
-          t31 = fminf(t31, g1);
+      for (int c0 = 0; c0 < KMAX; c0 += 16)
+        if (c0 < Kpad) tmem_ld16(ta + (uint32_t)c0, v + c0);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c0 = 0; c0 < KMAX; c0 += 16) {
+        if (c0 < ((p.debug & 4) ? 16 : Kpad)) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float adj0 = fmaf(-2.f, v[c0 + j], sea[c0 + j]), adj1 = fmaf(-2.f, v[c0 + j + 1], sea[c0 + j + 1]);
+            const float key0 = __uint_as_float((__float_as_uint(adj0) & 0xFFFFFFC0u) | (uint32_t)(c0 + j));
+            const float key1 = __uint_as_float((__float_as_uint(adj1) & 0xFFFFFFC0u) | (uint32_t)(c0 + j + 1));
+            const float h0 = fmaxf(b, key0), h1 = fmaxf(b1, key1);
+            b = fminf(b, key0);
+            b1 = fminf(b1, key1);
+            const float g0 = fmaxf(s2, h0), g1 = fmaxf(s21, h1);
+            s2 = fminf(s2, h0);
+            s21 = fminf(s21, h1);
+            t3 = fminf(t3, g0);
+            t31 = fminf(t31, g1);
+          }
         }
       }
       tc_fence_before();
@@ -299,58 +420,32 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
       const float tol2 = 2.f * EPS1 * (sx + se[k1]);
       const bool close2 = (p.debug & 2) ? false : !((s2 - b) > tol2);
       const bool close3 = !((t3 - b) > tol2);
-      // ---- exactly two candidates: fp32 re-score, four rows per pass (8 lanes per row, lane = 8 columns) ----
-      unsigned m2 = __ballot_sync(0xffffffffu, close2 && !close3);
-      unsigned canon = __ballot_sync(0xffffffffu, close2 && close3);
-      while (m2) {
-        int rsel = -1;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int f = m2 ? __ffs(m2) - 1 : -1;
-          if (i == sub) rsel = f;
-          m2 &= m2 - 1;                                 // (0 & 0xffffffff stays 0)
-        }
-        const bool have = rsel >= 0;
-        const int src = have ? rsel : lane;
-        const int c1 = __shfl_sync(0xffffffffu, k1, src), c2 = __shfl_sync(0xffffffffu, k2, src);
-        const float sxr = __shfl_sync(0xffffffffu, sx, src);
-        const int R = q * 32 + src;
-        const int kbo = u8 >> 2, ch = (u8 & 3) * 2;     // k-block image, first of two 16-byte chunks
-        const uint8_t* xr = xt + kbo * XT + R * 128;
-        const uint8_t* e1r = cbs + kbo * Kpad * 128 + c1 * 128;
-        const uint8_t* e2r = cbs + kbo * Kpad * 128 + c2 * 128;
-        const float4 xa = *reinterpret_cast<const float4*>(xr + ((ch ^ (R & 7)) << 4));
-        const float4 xb = *reinterpret_cast<const float4*>(xr + (((ch + 1) ^ (R & 7)) << 4));
-        const float4 ea = *reinterpret_cast<const float4*>(e1r + ((ch ^ (c1 & 7)) << 4));
-        const float4 eb = *reinterpret_cast<const float4*>(e1r + (((ch + 1) ^ (c1 & 7)) << 4));
-        const float4 fa = *reinterpret_cast<const float4*>(e2r + ((ch ^ (c2 & 7)) << 4));
-        const float4 fb = *reinterpret_cast<const float4*>(e2r + (((ch + 1) ^ (c2 & 7)) << 4));
-        float d1 = fmaf(xa.w, ea.w, fmaf(xa.z, ea.z, fmaf(xa.y, ea.y, xa.x * ea.x))) +
-                   fmaf(xb.w, eb.w, fmaf(xb.z, eb.z, fmaf(xb.y, eb.y, xb.x * eb.x)));
-        float d2 = fmaf(xa.w, fa.w, fmaf(xa.z, fa.z, fmaf(xa.y, fa.y, xa.x * fa.x))) +
-                   fmaf(xb.w, fb.w, fmaf(xb.z, fb.z, fmaf(xb.y, fb.y, xb.x * fb.x)));
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-          d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-          d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-        }
-        const float se1 = se[c1], se2 = se[c2];
-        const float dd1 = (sxr + se1) - 2.f * d1, dd2 = (sxr + se2) - 2.f * d2;
+      // ---- exactly two candidates (~7 % of random rows): the row's own lane re-scores both in fp32 ----
+      bool unsafe = false;
+      if (close2 && !close3) {
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        // walk the PHYSICAL 16-byte chunks of the row (immediate offsets); the matching chunk of a code row is an XOR away
+        const uint32_t xr = smem_u32(xt) + (uint32_t)(r * 128);
+        const uint32_t e1a = (smem_u32(cbs) + (uint32_t)(k1 * 128)) ^ (uint32_t)(((r ^ k1) & 7) << 4);
+        const uint32_t e2a = (smem_u32(cbs) + (uint32_t)(k2 * 128)) ^ (uint32_t)(((r ^ k2) & 7) << 4);
+        const uint32_t e1b = e1a + (uint32_t)(Kpad * 128), e2b = e2a + (uint32_t)(Kpad * 128);
+        float pa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int pc = 0; pc < 8; ++pc) settle_chunk(xr + (uint32_t)(pc << 4), (uint32_t)(pc << 4), e1a, e2a, e1b, e2b, pa, qa);
+        p0 = pa[0]; p1 = pa[1]; p2 = pa[2]; p3 = pa[3];
+        q0 = qa[0]; q1 = qa[1]; q2 = qa[2]; q3 = qa[3];
+        const float se1 = se[k1], se2 = se[k2];
+        const float dd1 = (sx + se1) - 2.f * ((p0 + p1) + (p2 + p3)), dd2 = (sx + se2) - 2.f * ((q0 + q1) + (q2 + q3));
         const float diff = dd1 - dd2;
-        const bool safe = fabsf(diff) > 2.f * EPS2 * (sxr + fmaxf(se1, se2));
-        const int win = diff < 0.f ? c1 : c2;
-        canon |= __reduce_or_sync(0xffffffffu, (have && !safe && u8 == 0) ? (1u << rsel) : 0u);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int wr = __shfl_sync(0xffffffffu, (have && safe) ? rsel : -1, i * 8);
-          const int ww = __shfl_sync(0xffffffffu, win, i * 8);
-          if (lane == wr) bk = ww;
-        }
+        if (fabsf(diff) > 2.f * EPS2 * (sx + fmaxf(se1, se2))) bk = diff < 0.f ? k1 : k2;
+        else unsafe = true;                              // too close for an order-independent decision
       }
+      unsigned canon = __ballot_sync(0xffffffffu, close2 && close3);
+      const unsigned canon2 = __ballot_sync(0xffffffffu, unsafe);
       // ---- three or more candidates: fp32 re-score of ALL codes (lanes = codes lane, lane + 32), best two ----
       {
         unsigned m3 = canon;
-        canon = 0u;
+        canon = canon2;
         while (m3) {
           const int rr = __ffs(m3) - 1;
           m3 &= m3 - 1;
@@ -411,6 +506,7 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
         int bkk = 0x7fffffff;
         for (int k = lane; k < K; k += 32) {
           float dot = 0.f;
+#pragma unroll 4
           for (int j = 0; j < 64; ++j)
             dot = fmaf(*reinterpret_cast<const float*>(xt + elem_off64(R, j, TR)),
                        *reinterpret_cast<const float*>(cbs + elem_off64(k, j, Kpad)), dot);
@@ -437,11 +533,12 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
       const int kk = valid ? bk : 255;
       const unsigned same = __match_any_sync(0xffffffffu, kk);
       if (valid && (same & ((1u << lane) - 1u)) == 0u) atomicAdd(&cnt_s[bk], __popc(same));
-      mbar_wait(&sh->idx_free[g], ph2 ^ 1u);            // the statistics warps are done with tile it - 2
-      sidx[g * TR + r] = bk;
+      const int ib = it % NIDX;
+      mbar_wait_sleep(&sh->idx_free[ib], ((uint32_t)(it / NIDX) & 1u) ^ 1u);   // the statistics warps are done with tile it - NIDX
+      sidx[ib * TR + r] = bk * 256;                    // byte offset of the code's bin row
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&sh->idx_ready[g]);
+        mbar_arrive(&sh->idx_ready[ib]);
         mbar_arrive(&sh->empty[s]);                     // this warp no longer reads the row tile
       }
     }
@@ -454,66 +551,28 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
     const uint32_t lane_base = (uint32_t)((lane >> 4) * XT + ((lane & 1) << 3) + sw * SROWS * 128);
     const uint32_t lane_c = (uint32_t)((lane & 15) >> 1);
     for (int it = 0; it < my_tiles; ++it) {
-      const int s = it % NSTAGE, a = it & 1;
+      const int s = it % NSTAGE, a = it % NIDX;
       const long long r0 = (long long)(blockIdx.x + it * gridDim.x) * TR;
       const long long left = p.N - r0;
       const int rows = left < TR ? (int)left : TR;
       const int n = rows - sw * SROWS;                 // rows of this warp that exist (may be <= 0 or > SROWS)
-      mbar_wait(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);
+      mbar_wait_sleep(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);
       // the row values do not depend on the indices: load them while the scan warps work (rows beyond N are zeros)
       const uint32_t x_a = smem_u32(xs + s * TILE_BYTES) + lane_base;
-      float2 v[SROWS];
+      uint32_t xrow[8];                                // rows i, i + 8, ... share the swizzle: one base per i & 7
 #pragma unroll
-      for (int i = 0; i < SROWS; ++i) v[i] = lds_v2(x_a + (uint32_t)(i * 128) + ((((uint32_t)i & 7u) ^ lane_c) << 4));
-      mbar_wait(&sh->idx_ready[a], (uint32_t)(it >> 1) & 1u);
-      if (!(p.debug & 1)) {
-        // four rows per step: their bins are fetched together, equal bins are forwarded in registers, and the stores go out
-        // in row order (a later row of the same code overwrites with the cumulative value).  Rows beyond N are zeros and
-        // carry a valid code, so they need no special case.
-#pragma unroll
-        for (int h = 0; h < SROWS; h += 16) {
-          int kc[16];
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const uint4 o4 = lds_u4(sidx_a + (uint32_t)((a * TR + sw * SROWS + h + i4 * 4) * 4));
-            kc[i4 * 4 + 0] = (int)o4.x;
-            kc[i4 * 4 + 1] = (int)o4.y;
-            kc[i4 * 4 + 2] = (int)o4.z;
-            kc[i4 * 4 + 3] = (int)o4.w;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            if (h + i < n) {                               // warp-uniform
-              const uint32_t a0 = bins_a + (uint32_t)(kc[i] * 256), a1 = bins_a + (uint32_t)(kc[i + 1] * 256);
-              const uint32_t a2 = bins_a + (uint32_t)(kc[i + 2] * 256), a3 = bins_a + (uint32_t)(kc[i + 3] * 256);
-              float2 b0 = lds_v2(a0), b1 = lds_v2(a1), b2 = lds_v2(a2), b3 = lds_v2(a3);
-              b0.x += v[h + i].x;
-              b0.y += v[h + i].y;
-              if (a1 == a0) b1 = b0;
-              b1.x += v[h + i + 1].x;
-              b1.y += v[h + i + 1].y;
-              if (a2 == a1) b2 = b1;
-              else if (a2 == a0) b2 = b0;
-              b2.x += v[h + i + 2].x;
-              b2.y += v[h + i + 2].y;
-              if (a3 == a2) b3 = b2;
-              else if (a3 == a1) b3 = b1;
-              else if (a3 == a0) b3 = b0;
-              b3.x += v[h + i + 3].x;
-              b3.y += v[h + i + 3].y;
-              sts_v2(a0, b0);
-              sts_v2(a1, b1);
-              sts_v2(a2, b2);
-              sts_v2(a3, b3);
-            }
-          }
-        }
-      }
+      for (int i = 0; i < 8; ++i) xrow[i] = x_a + (uint32_t)(i * 128) + ((((uint32_t)i) ^ lane_c) << 4);
+      float2 v[16];
+      stats_load_half<0>(xrow, v);
+      mbar_wait_sleep(&sh->idx_ready[a], (uint32_t)(it / NIDX) & 1u);
+      const uint32_t sidx_t = sidx_a + (uint32_t)((a * TR + sw * SROWS) * 4);
+      if (!(p.debug & 1)) stats_rmw_half(sidx_t, bins_a, v, n);
+      stats_load_half<1>(xrow, v);
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&sh->empty[s]);
-        mbar_arrive(&sh->idx_free[a]);
-      }
+      if (lane == 0) mbar_arrive(&sh->empty[s]);       // the row values are in registers: the stage can be refilled
+      if (!(p.debug & 1)) stats_rmw_half(sidx_t + 64u, bins_a, v, n - 16);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->idx_free[a]);
     }
   }
   tc_fence_before();
@@ -553,7 +612,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 size_t smem_bytes_tma(int K, int Kpad) {
   size_t b = (size_t)NSTAGE * TILE_BYTES + (size_t)2 * Kpad * 128 + (size_t)STAT_WARPS * K * 64 * 4;
-  b += (size_t)(3 * KMAX) * 4 + (size_t)(2 * TR) * 4 + sizeof(Sh);
+  b += (size_t)(3 * KMAX) * 4 + (size_t)(NIDX * TR) * 4 + sizeof(Sh);
   return b + 1024 + 64;
 }
 
