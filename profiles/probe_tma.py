@@ -34,7 +34,14 @@ if len(sys.argv) < 2 or sys.argv[1] == 'time':
     K, N = 44, 1 << 22
     W = torch.randn(K, D, device=dev); z = torch.randn(N, D, device=dev)
     ws = ops.vq_workspace(K, D, dev); idx = torch.empty(N, dtype=torch.int64, device=dev); st = torch.empty(K * (D + 1), device=dev)
-    for eng in ('tensor_core', 'cuda_core'):
+    cs = torch.zeros(K, device=dev); ew = torch.randn(K, D, device=dev)
+    for state in ('randn codebook', 'after 10 EMA updates'):
+      if state != 'randn codebook':
+        ops.vq_set_engine('auto')
+        for _ in range(10):
+            ops.vq_assign(z, W, LAYOUT_FLAT_ND, ws, idx=idx, stats=st); ops.vq_ema_update(cs, ew, W, st, 0.99, 1e-5)
+      print(state, flush=True)
+      for eng in ('tensor_core', 'cuda_core'):
         ops.vq_set_engine(eng)
         for _ in range(3): ops.vq_assign(z, W, LAYOUT_FLAT_ND, ws, idx=idx, stats=st)
         torch.cuda.synchronize()

@@ -48,9 +48,11 @@ constexpr int TMA_WARP = SCAN_WARPS + STAT_WARPS, MMA_WARP = TMA_WARP + 1;
 constexpr int NT = (MMA_WARP + 1) * 32;
 constexpr int KMAX = 48;              // four private bin copies of K x 64 floats must fit beside the tile ring
 // Tensor-core filter.  kind::tf32 drops the low 13 mantissa bits of both operands: |x_j e_j - tf32(x_j) tf32(e_j)| <
-// (2 * 2^-10 + 2^-20) |x_j e_j|, so the score error is < 2 * 1.955e-3 |x||e_k| <= 1.955e-3 (|x|^2 + |e_k|^2); packing the
-// code index into 6 mantissa bits adds < 1.6e-5, the fp32 rounding of the formula itself < 1e-5 of the same scale.
-constexpr float EPS1 = 2.2e-3f;
+// (2 * 2^-10 + 2^-20) |x_j e_j|, so the score s_k = |e_k|^2 - 2 x.e_k is off by < 3.91e-3 |x||e_k| (Cauchy-Schwarz); packing
+// the code index into 6 mantissa bits adds < 1.6e-5 (|x|^2 + |e_k|^2), the fp32 rounding of the formula itself < 1e-5 of
+// the same scale:  tau_k = EPSA |x||e_k| + EPSB (|x|^2 + |e_k|^2).  (The |x||e_k| form matters: an EMA-trained codebook
+// has |e_k| << |x|, and with the looser (|x|^2 + |e_k|^2) / 2 twice as many rows went to the fp32 settlement.)
+constexpr float EPSA = 4.0e-3f, EPSB = 3.2e-5f;
 // fp32 filter: two fp32 evaluations of (|x|^2 + |e|^2) - 2 x.e in ANY summation order differ by < 2e-5 (|x|^2 + |e|^2)
 constexpr float EPS2 = 2.0e-5f;
 constexpr float BIG = 3.0e38f;
@@ -60,9 +62,6 @@ struct Sh {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 // issues the load only: tmem_ld_wait() before the values are used
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -245,8 +244,9 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
   uint8_t* cbs = xs + NSTAGE * TILE_BYTES;                          // [2 k-blocks][Kpad codes][128 B], raw fp32
   float* bins = reinterpret_cast<float*>(cbs + 2 * Kpad * 128);     // [STAT_WARPS][K][64] private dw bins
   float* se = bins + STAT_WARPS * K * 64;                           // [KMAX]  |e_k|^2
-  float* sea = se + KMAX;                                           // [KMAX]  |e_k|^2 (1 - EPS1), BIG beyond K
-  int* cnt_s = reinterpret_cast<int*>(sea + KMAX);                  // [KMAX]  this CTA's counts
+  float* sea = se + KMAX;                                           // [KMAX]  |e_k|^2 (1 - EPSB), BIG beyond K
+  float* sqa = sea + KMAX;                                          // [KMAX]  EPSA |e_k|
+  int* cnt_s = reinterpret_cast<int*>(sqa + KMAX);                  // [KMAX]  this CTA's counts
   int* sidx = cnt_s + KMAX;                                         // [NIDX][128] code of every row of a tile
   Sh* sh = reinterpret_cast<Sh*>(sidx + NIDX * TR);
 
@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
         s = fmaf(v, v, s);
       }
     se[k] = (k < K) ? s : BIG;
-    sea[k] = (k < K) ? s * (1.f - EPS1) : BIG;
+    sea[k] = (k < K) ? s * (1.f - EPSB) : BIG;
+    sqa[k] = (k < K) ? EPSA * sqrtf(s) * 1.0001f : 0.f;
     cnt_s[k] = 0;
   }
   fence_proxy_async();   // the codebook image was written through the generic proxy
@@ -368,9 +369,10 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
         }
         sx = ((a0 + a1) + (a2 + a3)) * 1.0001f;
       }
+      const float nrsx = -sqrtf(sx) * 1.0001f;             // -|x| (upper bound)
       mbar_wait_sleep(&sh->tmem_full[g], ph2);
       tc_fence_after();
-      // ---- lower bounds adj_k = |e_k|^2 (1 - EPS1) - 2 x.e_k with k in the low 6 mantissa bits: three smallest, kept by
+      // ---- lower bounds adj_k = s_k - EPSB |e_k|^2 - EPSA |x||e_k| with k in the low 6 mantissa bits: three smallest, kept by
       //      two independent min/max chains (even / odd codes) ----
       float b = INFINITY, s2 = INFINITY, t3 = INFINITY, b1 = INFINITY, s21 = INFINITY, t31 = INFINITY;
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * Kpad);
@@ -384,7 +386,8 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
         if (c0 < ((p.debug & 4) ? 16 : Kpad)) {
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            const float adj0 = fmaf(-2.f, v[c0 + j], sea[c0 + j]), adj1 = fmaf(-2.f, v[c0 + j + 1], sea[c0 + j + 1]);
+            const float adj0 = fmaf(nrsx, sqa[c0 + j], fmaf(-2.f, v[c0 + j], sea[c0 + j]));
+            const float adj1 = fmaf(nrsx, sqa[c0 + j + 1], fmaf(-2.f, v[c0 + j + 1], sea[c0 + j + 1]));
             const float key0 = __uint_as_float((__float_as_uint(adj0) & 0xFFFFFFC0u) | (uint32_t)(c0 + j));
             const float key1 = __uint_as_float((__float_as_uint(adj1) & 0xFFFFFFC0u) | (uint32_t)(c0 + j + 1));
             const float h0 = fmaxf(b, key0), h1 = fmaxf(b1, key1);
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
       const int k1 = (int)(__float_as_uint(b) & 63u);
       const int k2 = (int)(__float_as_uint(s2) & 63u);
       int bk = k1;
-      const float tol2 = 2.f * EPS1 * (sx + se[k1]);
+      const float tol2 = 2.f * (EPSB * (sx + se[k1]) - nrsx * sqa[k1]);
       const bool close2 = (p.debug & 2) ? false : !((s2 - b) > tol2);
       const bool close3 = !((t3 - b) > tol2);
       // ---- exactly two candidates (~7 % of random rows): the row's own lane re-scores both in fp32 ----
@@ -612,7 +615,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 size_t smem_bytes_tma(int K, int Kpad) {
   size_t b = (size_t)NSTAGE * TILE_BYTES + (size_t)2 * Kpad * 128 + (size_t)STAT_WARPS * K * 64 * 4;
-  b += (size_t)(3 * KMAX) * 4 + (size_t)(NIDX * TR) * 4 + sizeof(Sh);
+  b += (size_t)(4 * KMAX) * 4 + (size_t)(NIDX * TR) * 4 + sizeof(Sh);
   return b + 1024 + 64;
 }
 
