@@ -204,6 +204,17 @@ int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int accumulate
  *               ([hi | lo] x 128 rows x 32 floats, SWIZZLE_128B), M = d0 / d1, Cred = d1 / d0 */
 int vqs_permute_weight(const float* w, int d0, int d1, int k, int mode, float* out, vqs_stream_t stream);
 
+/* The same re-arrangement for up to VQS_PERMUTE_MAX_ITEMS weights in ONE launch (the training step rebuilds ~25 GEMM
+ * operands per step from the freshly updated parameters; replaces that many vqs_permute_weight calls). `items` is a
+ * HOST array, read during the call. */
+#define VQS_PERMUTE_MAX_ITEMS 32
+typedef struct {
+  const float* w; /* (d0, d1, k) parameter as stored by nn.Conv1d / nn.ConvTranspose1d */
+  float* out;     /* as for vqs_permute_weight */
+  int d0, d1, k, mode;
+} vqs_permute_item;
+int vqs_permute_weights(const vqs_permute_item* items, int n, vqs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* element-wise pieces of the path                                                                  */
 /* ------------------------------------------------------------------------------------------------ */

@@ -190,3 +190,30 @@ def test_amsgrad_matches_oracle_and_torch():
     # fp32 parameters vs the fp64 oracle: within 2 ulp of the largest parameter (the updates are ~lr = 2e-4 per step)
     assert float(np.max(np.abs(pd.cpu().numpy() - po))) < 2 * 1.2e-7 * np.abs(po).max() + 1e-5 * 2e-4 * 3
     assert rel_err(vmd.cpu().numpy(), vm) < TOL
+
+
+def test_permute_weights_batched_matches_single_calls():
+    """vqs_permute_weights (one launch for all the step's GEMM operands) == vqs_permute_weight item by item, every mode
+    and kernel size, including operand images whose M is not a multiple of 128 (zero rows) and more than one chunk of
+    VQS_PERMUTE_MAX_ITEMS items."""
+    dev = _dev()
+    from vq_vae_speech_b200 import ops
+    rng = np.random.RandomState(3)
+    items, want = [], []
+    for rep in range(3):
+        for (d0, d1, k) in [(5, 7, 3), (64, 96, 1), (39, 64, 2), (200, 32, 4), (128, 64, 3), (33, 65, 2)]:
+            w = _t(rng.randn(d0, d1, k), dev)
+            for mode in range(5):
+                if mode == 3 and d1 % 32:
+                    continue
+                if mode == 4 and d0 % 32:
+                    continue
+                ref = ops.permute_weight(w, mode=mode)
+                out = torch.full_like(ref, float('nan'))
+                items.append((w, out, mode))
+                want.append(ref)
+    assert len(items) > 64
+    ops.permute_weights(items)
+    torch.cuda.synchronize()
+    for (w, out, mode), ref in zip(items, want):
+        assert torch.equal(out, ref), 'mode %d shape %s' % (mode, tuple(w.shape))

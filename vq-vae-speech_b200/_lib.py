@@ -43,6 +43,13 @@ class WgradDesc(Structure):
     ]
 
 
+class PermuteItem(Structure):
+    """struct vqs_permute_item (include/vqs_b200.h)."""
+    _fields_ = [('w', c_void_p), ('out', c_void_p), ('d0', c_int), ('d1', c_int), ('k', c_int), ('mode', c_int)]
+
+
+PERMUTE_MAX_ITEMS = 32
+
 # name -> (restype, argtypes); every symbol include/vqs_b200.h declares
 PROTOTYPES = {
     'vqs_version': (c_int, []),
@@ -65,6 +72,7 @@ PROTOTYPES = {
     'vqs_wgrad_gemm': (c_int, [POINTER(WgradDesc), c_void_p, c_size_t, c_void_p]),
     'vqs_bias_grad': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     'vqs_permute_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'vqs_permute_weights': (c_int, [POINTER(PermuteItem), c_int, c_void_p]),
     'vqs_upsample2_fwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     'vqs_upsample2_bwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     'vqs_jitter_fwd': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p]),

@@ -382,11 +382,9 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
 //   copy laid out exactly as the MMA reads it (128 rows x 128 B, SWIZZLE_128B), values pre-split x = hi + lo.  The GEMM
 //   kernel then fetches its A operand with ONE cp.async.bulk per k-block instead of 512 thread loads + splits.
 template <int KS>
-__global__ void __launch_bounds__(256) permute_weight_kernel(const float* __restrict__ w, int d0, int d1, int mode,
-                                                             float* __restrict__ out) {
+__device__ __forceinline__ void permute_weight_tile(const float* __restrict__ w, int d0, int d1, int mode,
+                                                    float* __restrict__ out, int a0, int b0, float* tile) {
   constexpr int ROW = 32 * KS + 1;
-  __shared__ float tile[32 * ROW];
-  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
   const int tid = threadIdx.x;
   // load: for each a, the 32*KS contiguous floats w[a][b0 .. b0+31][*]
   for (int i = tid; i < 32 * 32 * KS; i += 256) {
@@ -441,6 +439,40 @@ __global__ void __launch_bounds__(256) permute_weight_kernel(const float* __rest
       out[base + off] = h;
       out[base + 4096 + off] = v - h;
     }
+  }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) permute_weight_kernel(const float* __restrict__ w, int d0, int d1, int mode,
+                                                             float* __restrict__ out) {
+  __shared__ float tile[32 * (32 * KS + 1)];
+  permute_weight_tile<KS>(w, d0, d1, mode, out, blockIdx.y * 32, blockIdx.x * 32, tile);
+}
+
+// All weight re-arrangements of a training step in ONE launch (25 separate launches cost 0.34 ms per step, mostly launch
+// gaps and tails): block -> (item, 32 x 32 tile) through a prefix table in the kernel parameters.
+struct PermuteBatch {
+  const float* w[VQS_PERMUTE_MAX_ITEMS];
+  float* out[VQS_PERMUTE_MAX_ITEMS];
+  int d0[VQS_PERMUTE_MAX_ITEMS], d1[VQS_PERMUTE_MAX_ITEMS];
+  unsigned char ks[VQS_PERMUTE_MAX_ITEMS], mode[VQS_PERMUTE_MAX_ITEMS];
+  int first[VQS_PERMUTE_MAX_ITEMS + 1];   // first block of every item
+  int n;
+};
+
+__global__ void __launch_bounds__(256) permute_weights_kernel(const __grid_constant__ PermuteBatch pb) {
+  __shared__ float tile[32 * (32 * 4 + 1)];
+  int it = 0;
+  while (it + 1 < pb.n && (int)blockIdx.x >= pb.first[it + 1]) ++it;
+  const int local = blockIdx.x - pb.first[it];
+  const int d0 = pb.d0[it], d1 = pb.d1[it], mode = pb.mode[it];
+  const int nbx = (d1 + 31) / 32;
+  const int a0 = (local / nbx) * 32, b0 = (local % nbx) * 32;
+  switch (pb.ks[it]) {
+    case 1: permute_weight_tile<1>(pb.w[it], d0, d1, mode, pb.out[it], a0, b0, tile); break;
+    case 2: permute_weight_tile<2>(pb.w[it], d0, d1, mode, pb.out[it], a0, b0, tile); break;
+    case 3: permute_weight_tile<3>(pb.w[it], d0, d1, mode, pb.out[it], a0, b0, tile); break;
+    default: permute_weight_tile<4>(pb.w[it], d0, d1, mode, pb.out[it], a0, b0, tile); break;
   }
 }
 
@@ -551,6 +583,33 @@ extern "C" int vqs_permute_weight(const float* w, int d0, int d1, int k, int mod
     case 3: permute_weight_kernel<3><<<grid, 256, 0, st>>>(w, d0, d1, mode, out); break;
     default: permute_weight_kernel<4><<<grid, 256, 0, st>>>(w, d0, d1, mode, out); break;
   }
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vqs_permute_weights(const vqs_permute_item* items, int n, vqs_stream_t stream) {
+  VQS_CHECK_ARG(items && n >= 1 && n <= VQS_PERMUTE_MAX_ITEMS, "vqs_permute_weights: 1..%d items", VQS_PERMUTE_MAX_ITEMS);
+  cudaStream_t st = (cudaStream_t)stream;
+  PermuteBatch pb;
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    const vqs_permute_item& q = items[i];
+    VQS_CHECK_ARG(q.w && q.out && q.d0 > 0 && q.d1 > 0 && q.k >= 1 && q.k <= 4 && q.mode >= 0 && q.mode <= 4,
+                  "vqs_permute_weights: bad item %d (kernel size 1..4, mode 0..4)", i);
+    if (q.mode >= 3) {
+      const int M = q.mode == 3 ? q.d0 : q.d1, Cred = q.mode == 3 ? q.d1 : q.d0;
+      VQS_CHECK_ARG(Cred % 32 == 0, "vqs_permute_weights: operand images need Cred %% 32 == 0 (item %d: %d)", i, Cred);
+      if (M % 128 != 0)   // rows beyond M stay zero
+        VQS_CUDA(cudaMemsetAsync(q.out, 0, (size_t)((M + 127) / 128) * (q.k * Cred / 32) * 8192 * sizeof(float), st));
+    }
+    pb.w[i] = q.w; pb.out[i] = q.out; pb.d0[i] = q.d0; pb.d1[i] = q.d1;
+    pb.ks[i] = (unsigned char)q.k; pb.mode[i] = (unsigned char)q.mode;
+    pb.first[i] = blocks;
+    blocks += ((q.d0 + 31) / 32) * ((q.d1 + 31) / 32);
+  }
+  pb.first[n] = blocks;
+  pb.n = n;
+  permute_weights_kernel<<<blocks, 256, 0, st>>>(pb);
   VQS_LAUNCH_CHECK();
   return 0;
 }

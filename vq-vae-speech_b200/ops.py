@@ -269,6 +269,19 @@ def permute_weight(w, out=None, mode=0):
     return out
 
 
+def permute_weights(items):
+    """[(w, out, mode), ...] -> the same re-arrangements as permute_weight, _lib.PERMUTE_MAX_ITEMS of them per launch."""
+    items = list(items)
+    for lo in range(0, len(items), _lib.PERMUTE_MAX_ITEMS):
+        chunk = items[lo:lo + _lib.PERMUTE_MAX_ITEMS]
+        arr = (_lib.PermuteItem * len(chunk))()
+        for i, (w, out, mode) in enumerate(chunk):
+            d0, d1, k = w.shape
+            arr[i].w, arr[i].out = _p(w), _p(out)
+            arr[i].d0, arr[i].d1, arr[i].k, arr[i].mode = d0, d1, k, int(mode)
+        _call('vqs_permute_weights', (arr, len(chunk)), keep=(arr, chunk))
+
+
 def tensor_core_engine():
     return _PRECISION != _lib.PREC_FP32
 

@@ -220,9 +220,7 @@ class FusedTrainStep(object):
         P, G, WP, ws = self._p, self.grads, self.wperm, self.ws_wgrad
         nl = self.nl
         # ---- 0. weight re-arrangements for this step's dgrad / transposed-conv GEMMs ----
-        for (name, role), (buf, tap, mode) in WP.items():
-            if buf is not None:
-                ops.permute_weight(P(name), buf, mode=mode)
+        ops.permute_weights([(P(name), buf, mode) for (name, role), (buf, tap, mode) in WP.items() if buf is not None])
 
         def A(name, role):
             buf, tap, mode = WP[(name, role)]
