@@ -36,6 +36,9 @@ CONV_CASES = [  # (B, Cin, Cout, L, k, stride, pad)
     (2, 39, 48, 47, 3, 1, 1), (2, 48, 48, 47, 4, 2, 2), (3, 48, 64, 24, 3, 1, 1), (2, 96, 80, 24, 1, 1, 0),
     (5, 64, 768, 24, 3, 1, 1), (64, 768, 768, 24, 3, 1, 1), (16, 768, 64, 96, 3, 1, 1), (2, 7, 2, 9, 3, 1, 1),
     (4, 130, 200, 47, 4, 2, 2), (1, 768, 768, 5, 3, 1, 1), (3, 64, 96, 47, 4, 2, 2), (9, 256, 160, 31, 2, 1, 0),
+    # whole 128-row tiles, unit stride, L % 4 == 0, k = 1: shapes the TMA-fed wgrad kernel (wgrad_tma.cu) accepts
+    (4, 128, 256, 48, 1, 1, 0), (3, 256, 128, 20, 1, 1, 0), (70, 128, 128, 36, 1, 1, 0), (64, 768, 768, 24, 1, 1, 0),
+    (4, 128, 256, 48, 3, 1, 1),
 ]
 
 
@@ -217,3 +220,26 @@ def test_permute_weights_batched_matches_single_calls():
     torch.cuda.synchronize()
     for (w, out, mode), ref in zip(items, want):
         assert torch.equal(out, ref), 'mode %d shape %s' % (mode, tuple(w.shape))
+
+
+@pytest.mark.parametrize('B,C,M,L', [(4, 128, 256, 48), (3, 256, 128, 20), (70, 128, 128, 36), (64, 768, 768, 24)])
+def test_wgrad_tma_engine_matches_oracle(B, C, M, L, monkeypatch):
+    """The opt-in TMA-fed weight-gradient kernel (VQS_WGRAD_TMA=1: tensor-map boxes as raw tf32 operands, threads only
+    derive the lo tiles) on the shapes it accepts (1 x 1 convolutions), incl. the fused input ReLU and accumulation."""
+    dev = _dev()
+    from vq_vae_speech_b200 import functional as F, ops
+    monkeypatch.setenv('VQS_WGRAD_TMA', '1')
+    prev = ops.set_precision('3xtf32')
+    try:
+        rng = np.random.RandomState(B + C)
+        x, gy = rng.randn(B, C, L), rng.randn(B, M, L)
+        xd, gyd = _t(x, dev), _t(gy, dev)
+        dW = torch.empty(M, C, 1, device=dev)
+        ws = F._wgrad_ws(M, C, 1, B, L, dev)
+        F.conv1d_wgrad(gyd, xd, dW, 1, 0, ws)
+        dw_o, _ = mo.conv1d_wgrad(gy, x, 1, 1, 0)
+        assert rel_err(dW.cpu().numpy(), dw_o) < 1e-5
+        F.conv1d_wgrad(gyd, xd, dW, 1, 0, ws, accumulate=True)
+        assert rel_err(dW.cpu().numpy(), 2 * dw_o) < 1e-5
+    finally:
+        ops.set_precision(prev)

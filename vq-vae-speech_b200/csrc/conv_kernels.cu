@@ -517,7 +517,13 @@ extern "C" size_t vqs_wgrad_workspace_bytes(int M, int Cred, int ksz, int B, int
   WgradPlan pl = plan_wgrad(M, Cred * ksz, B * La);
   WgradPlan pt = plan_wgrad(M, Cred * ksz, B * La, 32, true);
   int s = pl.splits > pt.splits ? pl.splits : pt.splits;
-  return s > 1 ? (size_t)s * M * Cred * ksz * sizeof(float) : 0;
+  size_t need = s > 1 ? (size_t)s * M * Cred * ksz * sizeof(float) : 0;
+  if (M % 128 == 0 && Cred % 128 == 0) {   // the TMA-fed kernel always goes through the workspace (tile blocks + reduce)
+    WgradPlan pm = plan_wgrad(M, Cred * ksz, B * ((La + 31) / 32) * 32, 32, true);
+    size_t nt = (size_t)pm.splits * M * Cred * ksz * sizeof(float);
+    if (nt > need) need = nt;
+  }
+  return need;
 }
 
 extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t workspace_bytes, vqs_stream_t stream) {
@@ -529,6 +535,19 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
   p.d = *d;
   p.Nw = d->Cred * d->ksz;
   p.Kred = d->B * d->La;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wgrad_tma_supported(p)) {
+    // both operands K-major in HBM: TMA boxes straight into the UMMA layout, threads only derive the lo tiles
+    WgradPlan pm = plan_wgrad(d->M, p.Nw, wgrad_tma_kblocks(p) * 32, 32, true);
+    p.splits = pm.splits;
+    p.kt_per_split = pm.kt_per_split;
+    const size_t need_t = (size_t)pm.splits * d->M * p.Nw * sizeof(float);
+    if (need_t > workspace_bytes || !workspace) {
+      set_error("vqs_wgrad_gemm: workspace %zu < %zu", workspace_bytes, need_t);
+      return VQS_ERR_WORKSPACE;
+    }
+    return launch_wgrad_tma(p, (float*)workspace, st);
+  }
   const bool tc = d->precision != VQS_PREC_FP32 && wgrad_tc_supported(p);
   WgradPlan pl = tc ? plan_wgrad(d->M, p.Nw, p.Kred, 32, true) : plan_wgrad(d->M, p.Nw, p.Kred);
   p.splits = pl.splits;
@@ -540,7 +559,6 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
     return VQS_ERR_WORKSPACE;
   }
   p.partial = pl.splits > 1 ? (float*)workspace : nullptr;
-  cudaStream_t st = (cudaStream_t)stream;
   int e;
   if (tc) e = launch_wgrad_tc(p, d->precision, st);
   else if (pl.bm == 128 && pl.bn == 128) e = launch_wgrad<128, 128>(p, st);
