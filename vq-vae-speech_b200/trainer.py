@@ -161,7 +161,12 @@ class FusedTrainStep(object):
             b['d_hh%d' % i] = f(B, R_dec, L2)
             if i > 0:
                 b['d_x%d' % i] = f(B, C, L2)
-        b['s'], b['t1'], b['t2'] = f(B, C, L2), f(B, C, L2), f(B, C, L2 + 2)
+        # the reconstruction is trimmed to T frames (vq_vae.py:133-137) and conv_trans_3 has kernel 2: only the first
+        # min(L2 + 2, T) positions of conv_trans_2's output are ever read -- the rest is neither computed nor back-propagated
+        # (N = 64 x 50 = 3200 columns were 150 tiles = two waves on 148 SMs; 64 x 47 are 144)
+        Lt2 = min(L2 + 2, T)
+        self.dims['Lt2'] = Lt2
+        b['s'], b['t1'], b['t2'] = f(B, C, L2), f(B, C, L2), f(B, C, Lt2)
         b['recon'], b['g_recon'] = f(B, Fo, T), f(B, Fo, T)
         b['recon_loss'] = torch.zeros(1, dtype=torch.float32, device=dev)
         b['one'] = torch.ones(1, dtype=torch.float32, device=dev)
@@ -215,6 +220,7 @@ class FusedTrainStep(object):
     def _emit_step(self):
         m, b, d = self.model, self.buf, self.dims
         B, T, Tq, L2, C, D, K, Fi, Fo = d['B'], d['T'], d['Tq'], d['L2'], d['C'], d['D'], d['K'], d['Fi'], d['Fo']
+        Lt2 = d['Lt2']
         E, DEC = '_encoder.', '_decoder.'
         RS1, RS2 = '_residual_stack._layers.0._block.1.weight', '_residual_stack._layers.0._block.3.weight'
         P, G, WP, ws = self._p, self.grads, self.wperm, self.ws_wgrad
@@ -290,7 +296,7 @@ class FusedTrainStep(object):
                              add_pre=xd[i], add_pre_relu=True, relu=last)
         tfwd(b['s'], DEC + '_conv_trans_1.weight', P(DEC + '_conv_trans_1.bias'), 1, out=b['t1'],
                           relu=True)
-        tfwd(b['t1'], DEC + '_conv_trans_2.weight', P(DEC + '_conv_trans_2.bias'), 0, out=b['t2'],
+        tfwd(b['t1'], DEC + '_conv_trans_2.weight', P(DEC + '_conv_trans_2.bias'), 0, out_len=Lt2, out=b['t2'],
                           relu=True)
         tfwd(b['t2'], DEC + '_conv_trans_3.weight', P(DEC + '_conv_trans_3.bias'), 0, out_len=T,
                           out=b['recon'])                                          # trimmed to T (vq_vae.py:133-137)
@@ -299,10 +305,10 @@ class FusedTrainStep(object):
         ops.mse_fwd_bwd(b['recon'], b['x'], (Fi * T, T, 1), 1.0, b['recon_loss'], b['g_recon'], self.ws_mse)
 
         # ---- 5. decoder backward ----
-        gq2 = self._view('gA2', C, L2 + 2)
+        gq2 = self._view('gA2', C, Lt2)
         F.convT1d_wgrad(b['g_recon'], b['t2'], G[DEC + '_conv_trans_3.weight'], 0, ws)
         ops.bias_grad(b['g_recon'], G[DEC + '_conv_trans_3.bias'])
-        tdgrad(b['g_recon'], DEC + '_conv_trans_3.weight', L2 + 2, 0, out=gq2, mask=b['t2'],
+        tdgrad(b['g_recon'], DEC + '_conv_trans_3.weight', Lt2, 0, out=gq2, mask=b['t2'],
                         mask_kind=MASK_FLOAT)
         gq1 = self._view('gB2', C, L2)
         F.convT1d_wgrad(gq2, b['t1'], G[DEC + '_conv_trans_2.weight'], 0, ws)
