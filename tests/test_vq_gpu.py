@@ -328,3 +328,45 @@ def test_vq_tensor_core_engine_matches_cuda_core_engine(K, D, B, T, lay, data):
     mism = idx_tc.cpu().numpy() != idx_o
     assert not np.any(mism & ~(near | near_fp32))
     assert float(st_tc[:K].sum()) == N
+
+
+def test_vq_streaming_engine_fuzz_matches_cuda_core_engine():
+    """Random (K, N, data) draws through the streaming engine (vq_assign_tma_kernel: flat rows, K <= 48) against the exact
+    fp32 CUDA-core search: identical indices and counts, dw within 1e-5, and bit-identical results on a second run."""
+    dev = _dev()
+    from vq_vae_speech_b200 import ops, LAYOUT_FLAT_ND
+    rng = np.random.RandomState(2024)
+    D = 64
+    try:
+        for case in range(40):
+            K = int(rng.randint(1, 49))
+            N = int(rng.choice([1, 31, 127, 128, 129, 1000, 4096, 20011, 70000]))
+            kind = rng.choice(['randn', 'trained', 'tiny_codes', 'dup', 'scaled'])
+            W = rng.randn(K, D).astype(np.float32)
+            if kind == 'tiny_codes':
+                W *= 0.05                                  # an EMA-shrunk codebook: |e| << |x|
+            if kind == 'dup' and K > 2:
+                W[K - 1] = W[0]
+                W[K // 2] = W[0] * (1 + 1e-7)
+            if kind == 'scaled':
+                W *= 300.0
+            if kind == 'trained':
+                rows = (W[rng.randint(0, K, N)] + 0.05 * rng.randn(N, D)).astype(np.float32)
+            else:
+                rows = (rng.randn(N, D) * (300.0 if kind == 'scaled' else 1.0)).astype(np.float32)
+            z, Wd = _t(rows, dev), _t(W, dev)
+            ws = ops.vq_workspace(K, D, dev)
+            ops.vq_set_engine('cuda_core')
+            i_cc, s_cc = ops.vq_assign(z, Wd, LAYOUT_FLAT_ND, ws)
+            i_cc, s_cc = i_cc.clone(), s_cc.clone()
+            ops.vq_set_engine('tensor_core')
+            i_tc, s_tc = ops.vq_assign(z, Wd, LAYOUT_FLAT_ND, ws)
+            i_tc, s_tc = i_tc.clone(), s_tc.clone()
+            i_t2, s_t2 = ops.vq_assign(z, Wd, LAYOUT_FLAT_ND, ws)
+            tag = 'case %d: K=%d N=%d %s' % (case, K, N, kind)
+            assert torch.equal(i_tc, i_cc), tag + ': %d rows differ' % int((i_tc != i_cc).sum())
+            assert torch.equal(s_tc[:K], s_cc[:K]), tag
+            assert rel_err(s_tc[K:].cpu().numpy(), s_cc[K:].cpu().numpy()) < TOL, tag
+            assert torch.equal(i_tc, i_t2) and torch.equal(s_tc, s_t2), tag + ': not deterministic'
+    finally:
+        ops.vq_set_engine('auto')
