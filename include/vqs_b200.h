@@ -243,6 +243,15 @@ int vqs_add(const float* a, const float* b, long long n, float* out, vqs_stream_
 /* strided (B, L, C) -> NCL (B, C, L) copy: the `.permute(0, 2, 1).contiguous().float()` of convolutional_vq_vae.py:118. */
 int vqs_blc_to_ncl(const float* in, int B, int L, int C, float* out, vqs_stream_t stream);
 
+/* Weight normalisation of the use_kaiming_normal configurations (nn.utils.weight_norm, dim 0: src/modules/
+ * conv1d_builder.py:41-43, conv_transpose1d_builder.py:41-43, residual.py:45-47,57-59).  The weight (rows, cols) is the
+ * (d0, d1*k) view of the conv parameter; g has `rows` entries.
+ *   fwd: w = v * g / ||v||_row, norm[row] = ||v||_row (kept for the backward)
+ *   bwd: grad_g = <dw, v>_row / norm,  grad_v = g / norm * (dw - v <dw, v>_row / norm^2)      (autograd of the above) */
+int vqs_weight_norm_fwd(const float* v, const float* g, float* w, float* norm, int rows, int cols, vqs_stream_t stream);
+int vqs_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* norm, float* grad_v,
+                        float* grad_g, int rows, int cols, vqs_stream_t stream);
+
 /* Feature normalisation of the data feed, on the GPU (reference: `(dic['input_features'] - train_mean) / train_std` in
  * numpy float64, src/dataset/vctk_features_dataset.py:56-58, then `.float()` in convolutional_vq_vae.py:118):
  *   out[i] = (float)((in[i] - mean[i % F]) / std[i % F])      in float64 -> bit-identical to the reference's values. */

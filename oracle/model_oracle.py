@@ -162,6 +162,37 @@ RS1 = '_residual_stack._layers.0._block.1.weight'
 RS2 = '_residual_stack._layers.0._block.3.weight'
 
 
+def wn_expand(p, dtype=np.float64):
+    """use_kaiming_normal: every conv is wrapped in nn.utils.weight_norm (conv1d_builder.py:41-43,
+    conv_transpose1d_builder.py:41-43, residual.py:45-47,57-59), i.e. weight = g * v / ||v|| with the norm over all
+    dims but 0 (torch._weight_norm, dim = 0).  Returns p plus the derived '<layer>.weight' entries."""
+    if not any(k.endswith('.weight_v') for k in p):
+        return p
+    q = dict(p)
+    for k in p:
+        if k.endswith('.weight_v'):
+            v = np.asarray(p[k], dtype)
+            g = np.asarray(p[k[:-2] + '_g'], dtype)
+            n = np.sqrt((v.reshape(v.shape[0], -1) ** 2).sum(1)).reshape((-1,) + (1,) * (v.ndim - 1))
+            q[k[:-2]] = v * (g / n)
+    return q
+
+
+def wn_fold_grads(p, grads, dtype=np.float64):
+    """Autograd of the reparametrisation: d/dg = <dW, v> / ||v||,  d/dv = g / ||v|| * (dW - v <dW, v> / ||v||^2)."""
+    for k in p:
+        if k.endswith('.weight_v') and k[:-2] in grads:
+            v = np.asarray(p[k], dtype)
+            g = np.asarray(p[k[:-2] + '_g'], dtype)
+            dW = grads.pop(k[:-2])
+            shp = (-1,) + (1,) * (v.ndim - 1)
+            n = np.sqrt((v.reshape(v.shape[0], -1) ** 2).sum(1)).reshape(shp)
+            dot = (dW * v).reshape(v.shape[0], -1).sum(1).reshape(shp)
+            grads[k[:-2] + '_g'] = dot / n
+            grads[k] = (g / n) * (dW - v * dot / (n * n))
+    return grads
+
+
 def trainable_names(params, ema):
     """Parameters Adam actually updates.  In EMA mode `_vq._embedding.weight` / `_vq._ema_w` are
     re-created every step (ema.py:154,156) so the optimizer's references never see a gradient."""
@@ -181,6 +212,7 @@ def model_forward(p, x_btf, cfg, jitter_src=None, training=True, dtype=np.float6
     """ConvolutionalVQVAE.forward.  x_btf: (B, T, F).  p: dict name -> array (state_dict names).
     cfg: commitment_cost, decay, epsilon, num_residual_layers.  Returns (outputs dict, cache)."""
     c = {}
+    p = wn_expand(p, dtype)
     g = lambda n: np.asarray(p[n], dtype)
     nl = cfg['num_residual_layers']
     x = np.ascontiguousarray(np.asarray(x_btf, dtype).transpose(0, 2, 1))      # vq_vae.py:118
@@ -239,6 +271,7 @@ def model_forward(p, x_btf, cfg, jitter_src=None, training=True, dtype=np.float6
 
 def model_backward(p, c, out, target_bft, cfg, dtype=np.float64):
     """d(loss)/d(params) for loss = vq_loss + mean((recon - target)^2)  (trainer.py:54-63)."""
+    p_raw, p = p, wn_expand(p, dtype)
     g = lambda n: np.asarray(p[n], dtype)
     recon = out['reconstructed_x']
     target = np.asarray(target_bft, dtype)
@@ -297,7 +330,7 @@ def model_backward(p, c, out, target_bft, cfg, dtype=np.float64):
     ga1 = gh2 + conv1d_dgrad(gp2, w, c['a1'].shape[2], 1, 1)
     gp1 = ga1 * (c['p1'] > 0)
     grads[ENC + '_conv_1.weight'], grads[ENC + '_conv_1.bias'] = conv1d_wgrad(gp1, c['x'], 3, 1, 1)
-    return grads, recon_loss
+    return wn_fold_grads(p_raw, grads, dtype), recon_loss
 
 
 def amsgrad_step(param, grad, m, v, vmax, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):

@@ -65,6 +65,14 @@ class PortVQVAE(nn.Module):
         self.t1 = nn.ConvTranspose1d(C, C, 3, padding=1)
         self.t2 = nn.ConvTranspose1d(C, C, 3, padding=0)
         self.t3 = nn.ConvTranspose1d(C, Fo, 2, padding=0)
+        self.weight_norm = bool(cfg.get('use_kaiming_normal', False))
+        if self.weight_norm:     # conv1d_builder.py:41-43, conv_transpose1d_builder.py:41-43, residual.py:45-47,57-59
+            # (_pre_vq_conv is a plain nn.Conv1d: convolutional_vq_vae.py:61-66)
+            for name in ('e1', 'e2', 'e3', 'e4', 'e5', 'd1', 't1', 't2', 't3'):
+                setattr(self, name, nn.utils.weight_norm(getattr(self, name)))
+            for res in (self.eres, self.dres):
+                res.c1 = nn.utils.weight_norm(res.c1)
+                res.c2 = nn.utils.weight_norm(res.c2)
 
     # name map to the reference's state_dict keys (for loading golden initial weights)
     KEYMAP = {'e1': '_encoder._conv_1', 'e2': '_encoder._conv_2', 'e3': '_encoder._conv_3', 'e4': '_encoder._conv_4',
@@ -72,13 +80,17 @@ class PortVQVAE(nn.Module):
               't1': '_decoder._conv_trans_1', 't2': '_decoder._conv_trans_2', 't3': '_decoder._conv_trans_3'}
 
     def load_reference_state(self, sd):
+        def put(mod, key):
+            for suffix in (('weight_g', 'weight_v') if hasattr(mod, 'weight_g') else ('weight',)):
+                getattr(mod, suffix).copy_(torch.as_tensor(sd[key + '.' + suffix]))
+
         with torch.no_grad():
             for mine, ref in self.KEYMAP.items():
-                getattr(self, mine).weight.copy_(torch.as_tensor(sd[ref + '.weight']))
+                put(getattr(self, mine), ref)
                 getattr(self, mine).bias.copy_(torch.as_tensor(sd[ref + '.bias']))
             for mine, ref in (('eres', '_encoder'), ('dres', '_decoder')):
-                getattr(self, mine).c1.weight.copy_(torch.as_tensor(sd[ref + '._residual_stack._layers.0._block.1.weight']))
-                getattr(self, mine).c2.weight.copy_(torch.as_tensor(sd[ref + '._residual_stack._layers.0._block.3.weight']))
+                put(getattr(self, mine).c1, ref + '._residual_stack._layers.0._block.1')
+                put(getattr(self, mine).c2, ref + '._residual_stack._layers.0._block.3')
             self.emb.weight.copy_(torch.as_tensor(sd['_vq._embedding.weight']))
             if self.ema:
                 self.ema_w.copy_(torch.as_tensor(sd['_vq._ema_w']))

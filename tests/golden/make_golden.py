@@ -152,6 +152,9 @@ def model_case(name, B=2, T=47, steps=3, seed=1234, **over):
 if __name__ == '__main__':
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == '--only-kaiming':      # added after the other fixtures were committed
+        model_case('ema_k29_kaiming', decay=0.99, num_embeddings=29, use_kaiming_normal=True, seed=777)
+        sys.exit(0)
     # VQ bottleneck alone (BASELINE.json configs[2]: vq44, vq29, vq10x2) + layout / tie edge cases
     vq_case('ema_k44_d64_b2_t24', 44, 64, 2, 24, True)
     vq_case('ema_k29_d64_b2_t24', 29, 64, 2, 24, True, seed=1)
@@ -169,3 +172,5 @@ if __name__ == '__main__':
     model_case('ema_jitter_k29', decay=0.99, num_embeddings=29, use_jitter=True, seed=5678)
     model_case('noema_k10_d2', decay=0.0, num_embeddings=10, embedding_dim=2, seed=4242)
     model_case('ema_k44_b5_t191', decay=0.99, B=5, T=191, steps=2, num_hiddens=32, residual_channels=24)
+    # weight-normalised convs (use_kaiming_normal: conv1d_builder.py:41-43, residual.py:45-47,57-59)
+    model_case('ema_k29_kaiming', decay=0.99, num_embeddings=29, use_kaiming_normal=True, seed=777)

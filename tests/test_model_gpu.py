@@ -31,6 +31,7 @@ def _cfg(g):
     for k in ('decay', 'commitment_cost', 'jitter_probability', 'learning_rate'):
         cfg[k] = float(g['cfg_' + k])
     cfg['use_jitter'] = bool(g['cfg_use_jitter'])
+    cfg['use_kaiming_normal'] = bool(g['cfg_use_kaiming_normal'])
     return cfg
 
 

@@ -136,7 +136,8 @@ def test_torch_port_matches_reference(case):
     from oracle.torch_port import PortTrainer
     g = load_golden(case)
     cfg = dict(output_features_filters=13, augment_output_features=True, input_features_filters=13,
-               augment_input_features=True, use_jitter=bool(g['cfg_use_jitter']))
+               augment_input_features=True, use_jitter=bool(g['cfg_use_jitter']),
+               use_kaiming_normal=bool(g['cfg_use_kaiming_normal']))
     for k in ('num_hiddens', 'num_residual_layers', 'embedding_dim', 'num_embeddings', 'residual_channels'):
         cfg[k] = int(g['cfg_' + k])
     for k in ('decay', 'commitment_cost', 'jitter_probability', 'learning_rate'):

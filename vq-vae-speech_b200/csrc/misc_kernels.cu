@@ -208,6 +208,49 @@ __global__ void __launch_bounds__(256) amsgrad_kernel(float* __restrict__ p, con
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// weight normalisation (use_kaiming_normal: nn.utils.weight_norm, dim 0): one block per slice along dim 0
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];   // fixed order: deterministic
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256) weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                              float* __restrict__ w, float* __restrict__ norm, int cols) {
+  __shared__ float red[8];
+  const size_t base = (size_t)blockIdx.x * cols;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += 256) {
+    const float x = v[base + i];
+    s = fmaf(x, x, s);
+  }
+  const float n = sqrtf(block_sum_256(s, red));
+  const float scale = g[blockIdx.x] / n;
+  for (int i = threadIdx.x; i < cols; i += 256) w[base + i] = v[base + i] * scale;
+  if (threadIdx.x == 0) norm[blockIdx.x] = n;
+}
+
+__global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                                              const float* __restrict__ g, const float* __restrict__ norm,
+                                                              float* __restrict__ gv, float* __restrict__ gg, int cols) {
+  __shared__ float red[8];
+  const size_t base = (size_t)blockIdx.x * cols;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += 256) s = fmaf(dw[base + i], v[base + i], s);
+  const float dot = block_sum_256(s, red);
+  const float n = norm[blockIdx.x];
+  const float a = g[blockIdx.x] / n, c = dot / (n * n);
+  for (int i = threadIdx.x; i < cols; i += 256) gv[base + i] = a * (dw[base + i] - v[base + i] * c);
+  if (threadIdx.x == 0) gg[blockIdx.x] = dot / n;
+}
+
 }  // namespace
 }  // namespace vqs
 
@@ -307,6 +350,22 @@ extern "C" int vqs_amsgrad_step(float* p, const float* g, float* m, float* v, fl
   }
   amsgrad_kernel<<<ew_grid(n, 8), 256, 0, st>>>(p, g, m, v, vmax, n4, n, step, lr, beta1, beta2, (float)eps,
                                                 (float)g_scale);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vqs_weight_norm_fwd(const float* v, const float* g, float* w, float* norm, int rows, int cols,
+                                   vqs_stream_t stream) {
+  VQS_CHECK_ARG(v && g && w && norm && rows > 0 && cols > 0, "vqs_weight_norm_fwd: bad arguments");
+  weight_norm_fwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(v, g, w, norm, cols);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vqs_weight_norm_bwd(const float* dw, const float* v, const float* g, const float* norm, float* grad_v,
+                                   float* grad_g, int rows, int cols, vqs_stream_t stream) {
+  VQS_CHECK_ARG(dw && v && g && norm && grad_v && grad_g && rows > 0 && cols > 0, "vqs_weight_norm_bwd: bad arguments");
+  weight_norm_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(dw, v, g, norm, grad_v, grad_g, cols);
   VQS_LAUNCH_CHECK();
   return 0;
 }

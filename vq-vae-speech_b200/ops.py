@@ -282,6 +282,17 @@ def permute_weights(items):
         _call('vqs_permute_weights', (arr, len(chunk)), keep=(arr, chunk))
 
 
+def weight_norm_fwd(v, g, w, norm):
+    """w = v * g / ||v|| per slice along dim 0 (nn.utils.weight_norm); norm receives ||v||."""
+    rows = v.shape[0]
+    _call('vqs_weight_norm_fwd', (_p(v), _p(g), _p(w), _p(norm), rows, v.numel() // rows))
+
+
+def weight_norm_bwd(dw, v, g, norm, grad_v, grad_g):
+    rows = v.shape[0]
+    _call('vqs_weight_norm_bwd', (_p(dw), _p(v), _p(g), _p(norm), _p(grad_v), _p(grad_g), rows, v.numel() // rows))
+
+
 def tensor_core_engine():
     return _PRECISION != _lib.PREC_FP32
 

@@ -46,10 +46,6 @@ class FusedTrainStep(object):
         if self.dev.type != 'cuda':
             raise RuntimeError('FusedTrainStep needs the model on a CUDA device (no CPU path)')
         enc, dec, vq = model._encoder, model._decoder, model._vq
-        for m in model.modules():
-            if hasattr(m, 'weight_g'):
-                raise NotImplementedError('weight-normalised convs (use_kaiming_normal) run through the autograd '
-                                          'module path, not the fused step')
         self.is_ema = isinstance(vq, VectorQuantizerEMA)
         self.nl = enc._residual_stack._num_residual_layers
         if self.nl < 1:
@@ -109,18 +105,42 @@ class FusedTrainStep(object):
                 self.param_names.append(name)
                 if first_decoder is None and name.startswith('_decoder.'):
                     first_decoder = off
+        # weight-normalised convs (use_kaiming_normal): the optimizer owns weight_g / weight_v; the effective
+        # weight w = g v / ||v|| and its gradient dW live in scratch buffers the GEMMs use under the plain '.weight' name
+        self.wn = {}
+        self.weight_names = [n for n in self.param_names if n.endswith('.weight')]
+        offs_by_name = dict((n, o) for (n, _), o in zip(params, offs))
+        for name in self.param_names:
+            if name.endswith('.weight_v'):
+                base = name[:-2]
+                v = self._p(name)
+                self.wn[base] = dict(v=v, g=self._p(base + '_g'), w=torch.empty_like(v), dw=torch.zeros_like(v),
+                                     norm=torch.empty(v.shape[0], dtype=torch.float32, device=dev), off=offs_by_name[name])
+                self.grads[base] = self.wn[base]['dw']
+                self.weight_names.append(base)
         self.bucket_split = first_decoder if first_decoder is not None else total
         # gradient allreduce buckets, in the order the backward pass completes them (flat order is encoder, pre_vq, [vq],
         # decoder): decoder transposed convs | rest of the decoder | encoder conv_4 .. pre_vq (+ codebook) | conv_1 .. conv_3
-        offs_by_name = dict((n, o) for (n, _), o in zip(params, offs))
-        cut_t = offs_by_name.get('_decoder._conv_trans_1.weight', total)
-        cut_e = offs_by_name.get('_encoder._conv_4.weight', 0)
+        def first_of(prefix, default):
+            o = [off for n, off in offs_by_name.items() if n.startswith(prefix)]
+            return min(o) if o else default
+
+        cut_t = first_of('_decoder._conv_trans_1.', total)
+        cut_e = first_of('_encoder._conv_4.', 0)
         self.buckets = {'dec_convT': (cut_t, total), 'dec_rest': (self.bucket_split, cut_t),
                         'enc_hi': (cut_e, self.bucket_split), 'enc_lo': (0, cut_e)}
         self.n_params = sum(p.numel() for _, p in params)
 
     def _p(self, name):
+        if name in getattr(self, 'wn', {}):
+            return self.wn[name]['w']           # effective weight of a weight-normalised conv
         return dict(self.model.named_parameters())[name].data
+
+    def _emit_wn_fold(self, lo, hi):
+        """dW of the weight-normalised convs whose parameters lie in flat range [lo, hi) -> gradients of g and v."""
+        for base, w in self.wn.items():
+            if lo <= w['off'] < hi:
+                ops.weight_norm_bwd(w['dw'], w['v'], w['g'], w['norm'], self.grads[base + '_v'], self.grads[base + '_g'])
 
     def _alloc_buffers(self):
         m = self.model
@@ -180,8 +200,8 @@ class FusedTrainStep(object):
         # GEMM-ready weight operands, rebuilt at the top of every step by vqs_permute_weight: (name, role) ->
         # (buffer or None when the parameter is used as is, tap flag, permute mode)
         self.wperm = {}
-        for name in self.param_names:
-            if not name.endswith('weight') or name.startswith('_vq.'):
+        for name in self.weight_names:
+            if name.startswith('_vq.'):
                 continue
             p = self._p(name)
             roles = ('convT_fwd', 'convT_dgrad') if '_conv_trans_' in name else ('conv_fwd', 'conv_dgrad')
@@ -225,7 +245,9 @@ class FusedTrainStep(object):
         RS1, RS2 = '_residual_stack._layers.0._block.1.weight', '_residual_stack._layers.0._block.3.weight'
         P, G, WP, ws = self._p, self.grads, self.wperm, self.ws_wgrad
         nl = self.nl
-        # ---- 0. weight re-arrangements for this step's dgrad / transposed-conv GEMMs ----
+        # ---- 0. effective weights of weight-normalised convs, then the GEMM-ready operand images ----
+        for base, w in self.wn.items():
+            ops.weight_norm_fwd(w['v'], w['g'], w['w'], w['norm'])
         ops.permute_weights([(P(name), buf, mode) for (name, role), (buf, tap, mode) in WP.items() if buf is not None])
 
         def A(name, role):
@@ -318,6 +340,7 @@ class FusedTrainStep(object):
         F.convT1d_wgrad(gq1, b['s'], G[DEC + '_conv_trans_1.weight'], 1, ws)
         ops.bias_grad(gq1, G[DEC + '_conv_trans_1.bias'])
         tdgrad(gq1, DEC + '_conv_trans_1.weight', L2, 1, out=g, mask=b['s'], mask_kind=MASK_FLOAT)
+        self._emit_wn_fold(*self.buckets['dec_convT'])
         if self.world > 1:       # the three transposed convs are done: their gradients start travelling now
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_convT']))
         other = self._view('gB2', C, L2)
@@ -340,6 +363,7 @@ class FusedTrainStep(object):
             ops.jitter_bwd(b['gqj'], b['jitter_src'], gq)
         else:
             cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=gq)
+        self._emit_wn_fold(*self.buckets['dec_rest'])
         if self.world > 1:       # decoder gradients are complete: allreduce the rest of them under the encoder's backward
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_rest']))
 
@@ -384,6 +408,7 @@ class FusedTrainStep(object):
         gp3 = b['gA1']
         cdgrad(gp4, E + '_conv_4.weight', Tq, 1, 1, out=gp3, add_pre=gh4, mask=b['a3'],
                        mask_kind=MASK_FLOAT)
+        self._emit_wn_fold(*self.buckets['enc_hi'])
         if self.world > 1:       # conv_4 .. pre_vq (and the codebook gradient) are final
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_hi']))
         # conv_3 (k4 s2 p2): a3 = relu(conv3(h2))
@@ -402,6 +427,7 @@ class FusedTrainStep(object):
 
         # ---- 8. gradient allreduce (average) + fused AMSGrad over the flat buffers (trainer.py:41-42,68) ----
         g_scale = 1.0
+        self._emit_wn_fold(*self.buckets['enc_lo'])
         if self.world > 1:
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_lo']))
             ops.record_callable(self._wait_buckets)
