@@ -243,6 +243,15 @@ int vqs_add(const float* a, const float* b, long long n, float* out, vqs_stream_
 /* strided (B, L, C) -> NCL (B, C, L) copy: the `.permute(0, 2, 1).contiguous().float()` of convolutional_vq_vae.py:118. */
 int vqs_blc_to_ncl(const float* in, int B, int L, int C, float* out, vqs_stream_t stream);
 
+/* Eval-mode distance tables of the bottleneck (src/models/vector_quantizer.py:108-127; the EMA class raises NameError on
+ * the same lines): Euclidean distances torch.dist(x, y, 2) between VQ rows, in itertools order.
+ *   mode 0: product(rows of a, rows of b)   -> out[n * m],          out[i * m + j] = |a_i - b_j|      (frames vs codes)
+ *   mode 1: combinations(rows of a, 2)      -> out[n (n - 1) / 2],  pairs (0,1), (0,2), ..., (1,2), ...
+ * The rows of `a` follow `layout` exactly as in vqs_vq_assign (n = B * T rows; FLAT_ND: pass B = n, T = 1); b is a plain
+ * (m, D) matrix (the codebook). */
+int vqs_pairwise_l2(const float* a, int layout, int B, int D, int T, const float* b, int m, int mode, float* out,
+                    vqs_stream_t stream);
+
 /* Weight normalisation of the use_kaiming_normal configurations (nn.utils.weight_norm, dim 0: src/modules/
  * conv1d_builder.py:41-43, conv_transpose1d_builder.py:41-43, residual.py:45-47,57-59).  The weight (rows, cols) is the
  * (d0, d1*k) view of the conv parameter; g has `rows` entries.

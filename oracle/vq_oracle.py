@@ -83,6 +83,26 @@ def assign(flat, W):
     return idx, gap_rel < NEAR_TIE_REL, gap_rel
 
 
+def eval_distance_tables(z, W, dtype=np.float64):
+    """The three eval-only outputs of VectorQuantizer.forward (vector_quantizer.py:108-127): Euclidean distances
+    torch.dist(x, y, 2) over itertools.combinations(flat_input, 2) viewed (B, -1), combinations(embedding, 2), and
+    product(flat_input, embedding) viewed (B, T, K).  (The EMA class raises NameError on these lines.)"""
+    z = np.asarray(z, dtype)
+    W = np.asarray(W, dtype)
+    B, D, T = z.shape
+    flat = rows_from_bdt(z).astype(dtype)
+
+    def pdist(a, b):
+        return np.sqrt(((a[:, None, :] - b[None, :, :]) ** 2).sum(-1))
+
+    iu = np.triu_indices(flat.shape[0], 1)          # row-major upper triangle == itertools.combinations order
+    enc = pdist(flat, flat)[iu].reshape(B, -1)
+    ku = np.triu_indices(W.shape[0], 1)
+    emb = pdist(W, W)[ku]
+    fve = pdist(flat, W).reshape(B, T, -1)
+    return enc, emb, fve
+
+
 def one_hot(idx, K, dtype=np.float32):
     """zeros(N, K).scatter_(1, idx, 1) (ema.py:118-119)."""
     enc = np.zeros((len(idx), K), dtype)

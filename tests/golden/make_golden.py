@@ -95,6 +95,22 @@ def vq_case(name, K, D, B, T, ema, steps=3, seed=0, trained_like=False, dup_code
     print('wrote', name)
 
 
+def vq_eval_tables_case(name, K, D, B, T, seed):
+    """Eval-mode forward of the reference VectorQuantizer with compute_distances_if_possible=True: the three O(N^2)
+    distance tables (vector_quantizer.py:108-127; the EMA class raises NameError there)."""
+    torch.manual_seed(seed)
+    vq = VectorQuantizer(K, D, 0.25, 'cpu').eval()
+    with torch.no_grad():
+        vq._embedding.weight.normal_()
+    z = torch.randn(B, D, T)
+    outs = vq(z, compute_distances_if_possible=True)
+    rec = dict(K=K, D=D, B=B, T=T, W=np32(vq._embedding.weight), z=np32(z), idx=np32(outs[5]),
+               encoding_distances=np32(outs[7]), embedding_distances=np32(outs[8]),
+               frames_vs_embedding_distances=np32(outs[9]), quantized=np32(outs[1]), concat=np32(outs[10]))
+    np.savez_compressed(os.path.join(HERE, f'evaltables_{name}.npz'), **rec)
+    print('wrote', name)
+
+
 def model_cfg(**over):
     cfg = dict(output_features_filters=13, augment_output_features=True, output_features_dim=47, verbose=False,
                input_features_dim=47, num_hiddens=48, num_residual_layers=2, use_kaiming_normal=False,
@@ -152,6 +168,10 @@ def model_case(name, B=2, T=47, steps=3, seed=1234, **over):
 if __name__ == '__main__':
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == '--only-evaltables':   # added later as well
+        vq_eval_tables_case('noema_k44_d64_b2_t24', 44, 64, 2, 24, seed=11)
+        vq_eval_tables_case('noema_k10_d2_b3_t17', 10, 2, 3, 17, seed=12)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == '--only-kaiming':      # added after the other fixtures were committed
         model_case('ema_k29_kaiming', decay=0.99, num_embeddings=29, use_kaiming_normal=True, seed=777)
         sys.exit(0)
@@ -172,5 +192,7 @@ if __name__ == '__main__':
     model_case('ema_jitter_k29', decay=0.99, num_embeddings=29, use_jitter=True, seed=5678)
     model_case('noema_k10_d2', decay=0.0, num_embeddings=10, embedding_dim=2, seed=4242)
     model_case('ema_k44_b5_t191', decay=0.99, B=5, T=191, steps=2, num_hiddens=32, residual_channels=24)
+    vq_eval_tables_case('noema_k44_d64_b2_t24', 44, 64, 2, 24, seed=11)
+    vq_eval_tables_case('noema_k10_d2_b3_t17', 10, 2, 3, 17, seed=12)
     # weight-normalised convs (use_kaiming_normal: conv1d_builder.py:41-43, residual.py:45-47,57-59)
     model_case('ema_k29_kaiming', decay=0.99, num_embeddings=29, use_kaiming_normal=True, seed=777)

@@ -155,3 +155,15 @@ def test_torch_port_matches_reference(case):
         assert rel_err(r['vq_loss'], g[f'vq_loss{s}']) < TOL
         assert rel_err(r['reconstruction_loss'], g[f'recon_loss{s}']) < TOL
         assert rel_err(r['perplexity'], g[f'perplexity{s}']) < TOL
+
+
+@pytest.mark.parametrize('case', ['evaltables_noema_k44_d64_b2_t24', 'evaltables_noema_k10_d2_b3_t17'])
+def test_oracle_eval_distance_tables(case):
+    """Eval-only pairwise distance tables (vector_quantizer.py:108-127) against the reference's own output."""
+    g = load_golden(case)
+    enc, emb, fve = vqo.eval_distance_tables(g['z'], g['W'])
+    assert enc.shape == g['encoding_distances'].shape and emb.shape == g['embedding_distances'].shape
+    assert fve.shape == g['frames_vs_embedding_distances'].shape
+    assert rel_err(enc, g['encoding_distances']) < TOL
+    assert rel_err(emb, g['embedding_distances']) < TOL
+    assert rel_err(fve, g['frames_vs_embedding_distances']) < TOL

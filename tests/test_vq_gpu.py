@@ -370,3 +370,43 @@ def test_vq_streaming_engine_fuzz_matches_cuda_core_engine():
             assert torch.equal(i_tc, i_t2) and torch.equal(s_tc, s_t2), tag + ': not deterministic'
     finally:
         ops.vq_set_engine('auto')
+
+
+@pytest.mark.parametrize('case', ['evaltables_noema_k44_d64_b2_t24', 'evaltables_noema_k10_d2_b3_t17'])
+def test_eval_mode_distance_tables_match_reference(case):
+    """Eval-mode forward with compute_distances_if_possible=True: the three pairwise distance tables of
+    vector_quantizer.py:108-127 (one vqs_pairwise_l2 launch each instead of O(N^2) Python torch.dist calls) against the
+    reference's own output; also for the EMA class, where the reference raises NameError."""
+    dev = _dev()
+    from vq_vae_speech_b200.vector_quantizer import VectorQuantizer, VectorQuantizerEMA
+    from conftest import load_golden
+    g = load_golden(case)
+    K, D = int(g['K']), int(g['D'])
+    z = _t(g['z'], dev)
+    for vq in (VectorQuantizer(K, D, 0.25, dev), VectorQuantizerEMA(K, D, 0.25, 0.99, dev)):
+        vq = vq.to(dev).eval()
+        with torch.no_grad():
+            vq._embedding.weight.copy_(_t(g['W'], dev))
+        outs = vq(z, compute_distances_if_possible=True)
+        assert np.array_equal(outs[5].cpu().numpy().reshape(-1), g['idx'].reshape(-1))
+        for slot, key in ((7, 'encoding_distances'), (8, 'embedding_distances'), (9, 'frames_vs_embedding_distances')):
+            assert tuple(outs[slot].shape) == g[key].shape, key
+            assert rel_err(outs[slot].cpu().numpy(), g[key]) < TOL, key
+        assert rel_err(outs[10].cpu().numpy(), g['concat']) < TOL
+        assert all(o is None for o in vq(z, compute_distances_if_possible=False)[7:10])
+        assert all(o is None for o in vq.train()(z)[7:10])
+
+
+def test_pairwise_l2_large_matches_oracle():
+    """combinations / product ordering at a size where the triangular index needs the exact integer correction."""
+    dev = _dev()
+    from vq_vae_speech_b200 import ops, LAYOUT_FLAT_ND, LAYOUT_BDT_AS_DTB
+    rng = np.random.RandomState(5)
+    B, D, T, K = 7, 64, 33, 29
+    z = rng.randn(B, D, T).astype(np.float32)
+    W = rng.randn(K, D).astype(np.float32)
+    enc, emb, fve = vqo.eval_distance_tables(z, W)
+    zd, Wd = _t(z, dev), _t(W, dev)
+    assert rel_err(ops.pairwise_l2(zd, LAYOUT_BDT_AS_DTB, D).cpu().numpy(), enc.reshape(-1)) < TOL
+    assert rel_err(ops.pairwise_l2(Wd, LAYOUT_FLAT_ND, D).cpu().numpy(), emb) < TOL
+    assert rel_err(ops.pairwise_l2(zd, LAYOUT_BDT_AS_DTB, D, Wd).cpu().numpy(), fve.reshape(-1)) < TOL

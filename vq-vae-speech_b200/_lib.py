@@ -83,6 +83,7 @@ PROTOTYPES = {
     'vqs_relu_bwd': (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     'vqs_add': (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     'vqs_blc_to_ncl': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'vqs_pairwise_l2': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'vqs_weight_norm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'vqs_weight_norm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'vqs_normalize_features': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),

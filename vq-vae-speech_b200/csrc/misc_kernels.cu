@@ -251,6 +251,46 @@ __global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __res
   if (threadIdx.x == 0) gg[blockIdx.x] = dot / n;
 }
 
+// ------------------------------------------------------------------------------------------------
+// eval-mode distance tables (vector_quantizer.py:108-127: torch.dist(x, y, 2) over itertools pairs)
+// ------------------------------------------------------------------------------------------------
+// element (row r, column j) of the VQ rows of `z` in either layout (vqs_b200.h: VQS_LAYOUT_*)
+__device__ __forceinline__ float vq_row_elem(const float* __restrict__ z, int layout, int B, int D, int T, long long r,
+                                             int j) {
+  if (layout == VQS_LAYOUT_FLAT_ND) return __ldg(z + r * D + j);
+  const long long f = r * D + j, P = (long long)T * B;
+  const long long d = f / P, rem = f - d * P;
+  const long long t = rem / B, b = rem - t * B;
+  return __ldg(z + (b * D + d) * T + t);
+}
+
+__global__ void __launch_bounds__(256) pairwise_l2_kernel(const float* __restrict__ a, int layout, int B, int D, int T,
+                                                          long long n, const float* __restrict__ bm, int m, int mode,
+                                                          long long total, float* __restrict__ out) {
+  for (long long p = blockIdx.x * 256ll + threadIdx.x; p < total; p += (long long)gridDim.x * 256) {
+    long long i, j;
+    if (mode == 0) {                 // itertools.product(rows of a, rows of b): p = i * m + j
+      i = p / m;
+      j = p - i * m;
+    } else {                         // itertools.combinations(rows of a, 2): row i starts at i n - i (i + 1) / 2
+      const double nn = 2.0 * (double)n - 1.0;
+      i = (long long)floor((nn - sqrt(nn * nn - 8.0 * (double)p)) * 0.5);
+      if (i < 0) i = 0;
+      while (i > 0 && i * n - i * (i + 1) / 2 > p) --i;
+      while ((i + 1) * n - (i + 1) * (i + 2) / 2 <= p) ++i;
+      j = p - (i * n - i * (i + 1) / 2) + i + 1;
+    }
+    float s = 0.f;
+    for (int c = 0; c < D; ++c) {
+      const float x = vq_row_elem(a, layout, B, D, T, i, c);
+      const float y = (mode == 0) ? __ldg(bm + j * D + c) : vq_row_elem(a, layout, B, D, T, j, c);
+      const float df = __fsub_rn(x, y);
+      s = fmaf(df, df, s);
+    }
+    out[p] = sqrtf(s);
+  }
+}
+
 }  // namespace
 }  // namespace vqs
 
@@ -366,6 +406,21 @@ extern "C" int vqs_weight_norm_bwd(const float* dw, const float* v, const float*
                                    float* grad_g, int rows, int cols, vqs_stream_t stream) {
   VQS_CHECK_ARG(dw && v && g && norm && grad_v && grad_g && rows > 0 && cols > 0, "vqs_weight_norm_bwd: bad arguments");
   weight_norm_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(dw, v, g, norm, grad_v, grad_g, cols);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vqs_pairwise_l2(const float* a, int layout, int B, int D, int T, const float* b, int m, int mode, float* out,
+                               vqs_stream_t stream) {
+  VQS_CHECK_ARG(a && out && B > 0 && D > 0 && T > 0 && (mode == 0 || mode == 1), "vqs_pairwise_l2: bad arguments");
+  VQS_CHECK_ARG(layout == VQS_LAYOUT_FLAT_ND || layout == VQS_LAYOUT_BDT_AS_DTB, "vqs_pairwise_l2: unknown layout %d", layout);
+  VQS_CHECK_ARG(mode == 1 || (b && m > 0), "vqs_pairwise_l2: mode 0 needs the second row set");
+  const long long n = (long long)B * T;
+  const long long total = mode == 0 ? n * m : n * (n - 1) / 2;
+  if (total <= 0) return 0;
+  long long blocks = (total + 255) / 256;
+  const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+  pairwise_l2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, layout, B, D, T, n, b, m, mode, total, out);
   VQS_LAUNCH_CHECK();
   return 0;
 }

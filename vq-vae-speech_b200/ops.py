@@ -282,6 +282,21 @@ def permute_weights(items):
         _call('vqs_permute_weights', (arr, len(chunk)), keep=(arr, chunk))
 
 
+def pairwise_l2(a, layout, D, b=None):
+    """Euclidean distances between VQ rows in itertools order: product(rows(a), rows(b)) when b is given (n * m values),
+    combinations(rows(a), 2) otherwise (n (n - 1) / 2 values).  vector_quantizer.py:108-127."""
+    B, D_, T = vq_shape(a, layout, D)
+    n = B * T
+    if b is not None:
+        out = torch.empty(n * b.shape[0], dtype=torch.float32, device=a.device)
+        _call('vqs_pairwise_l2', (_p(a), layout, B, D_, T, _p(b), b.shape[0], 0, _p(out)))
+    else:
+        out = torch.empty(n * (n - 1) // 2, dtype=torch.float32, device=a.device)
+        if out.numel():
+            _call('vqs_pairwise_l2', (_p(a), layout, B, D_, T, None, 0, 1, _p(out)))
+    return out
+
+
 def weight_norm_fwd(v, g, w, norm):
     """w = v * g / ||v|| per slice along dim 0 (nn.utils.weight_norm); norm receives ||v||."""
     rows = v.shape[0]

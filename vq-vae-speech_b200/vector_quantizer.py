@@ -6,8 +6,9 @@ Same constructors, forward signature, 11-tuple return order, attribute and state
     nn.Parameter objects every step (ema.py:154,156) -- values, names and requires_grad are identical, storage is stable
     (CUDA graphs, data parallelism); only `id()` differs;
   * inputs must be CUDA fp32 tensors: there is no CPU path;
-  * the eval-only O(N^2) Python distance loops (ema.py:122-140; they raise NameError in the reference's EMA class) are
-    not reproduced: those three tuple slots are None.
+  * the eval-only O(N^2) Python distance loops (vector_quantizer.py:108-127 / ema.py:122-140) are ONE kernel launch each
+    (vqs_pairwise_l2, same itertools ordering and shapes).  The reference's EMA class raises NameError on those lines
+    (`product` is never imported there); here both classes return the tables.
 """
 import torch
 import torch.nn as nn
@@ -70,6 +71,24 @@ class _VQBase(nn.Module):
         self.last_stats = want['stats']
         return quantized, scalars, encodings, distances, idx.view(N, 1), want.get('q_rows')
 
+    def _eval_tables(self, inputs, compute_distances_if_possible):
+        """(encoding_distances (B, -1), embedding_distances (K (K-1)/2,), frames_vs_embedding_distances (B, T, K)) in eval
+        mode, (None, None, None) otherwise -- vector_quantizer.py:108-127."""
+        if self.training or not compute_distances_if_possible:
+            return None, None, None
+        D = self._embedding_dim
+        x = inputs.float().contiguous()
+        W = self._embedding.weight.detach().contiguous()
+        layout = LAYOUT_FLAT_ND if x.dim() == 2 else self.layout
+        if layout == LAYOUT_FLAT_ND:
+            batch, time = 1, x.shape[0]
+        else:
+            batch, time = x.shape[0], x.shape[2]
+        enc = ops.pairwise_l2(x, layout, D).view(batch, -1)
+        emb = ops.pairwise_l2(W, LAYOUT_FLAT_ND, D)
+        fve = ops.pairwise_l2(x, layout, D, W).view(batch, time, -1)
+        return enc, emb, fve
+
     @property
     def embedding(self):
         return self._embedding
@@ -98,7 +117,8 @@ class VectorQuantizerEMA(_VQBase):
         vq_loss = scalars[3]
         perplexity = scalars[2].detach()
         losses = {'vq_loss': vq_loss.item()} if self.sync_losses else {'vq_loss': vq_loss.detach()}
-        return (vq_loss, quantized, perplexity, encodings, distances, idx, losses, None, None, None, concat)
+        enc_d, emb_d, fve_d = self._eval_tables(inputs, compute_distances_if_possible)
+        return (vq_loss, quantized, perplexity, encodings, distances, idx, losses, enc_d, emb_d, fve_d, concat)
 
 
 class VectorQuantizer(_VQBase):
@@ -124,4 +144,5 @@ class VectorQuantizer(_VQBase):
         else:
             d = scalars.detach()
             losses = {'e_latent_loss': d[1], 'q_latent_loss': d[1], 'commitment_loss': d[3], 'vq_loss': d[4]}
-        return (vq_loss, quantized, perplexity, encodings, distances, idx, losses, None, None, None, concat)
+        enc_d, emb_d, fve_d = self._eval_tables(inputs, compute_distances_if_possible)
+        return (vq_loss, quantized, perplexity, encodings, distances, idx, losses, enc_d, emb_d, fve_d, concat)
