@@ -249,6 +249,12 @@ def model_forward(p, x_btf, cfg, jitter_src=None, training=True, dtype=np.float6
     if jitter_src is not None:
         q = q[:, :, jitter_src]
     c['jitter_src'] = jitter_src
+    c['n_spk'] = 0
+    if cfg.get('speaker_features') is not None:
+        # deconvolutional_decoder.py:108-111: (B, 40) speaker features repeated over time, concatenated on the channel axis
+        sf = np.asarray(cfg['speaker_features'], dtype)
+        c['n_spk'] = sf.shape[1]
+        q = np.concatenate([q, np.repeat(sf[:, :, None], q.shape[2], axis=2)], axis=1)
     c['dec_in'] = q
     d1 = conv1d_fwd(q, g(DEC + '_conv_1.weight'), g(DEC + '_conv_1.bias'), 1, 1)
     u = upsample2(d1)
@@ -296,6 +302,8 @@ def model_backward(p, c, out, target_bft, cfg, dtype=np.float64):
     w = g(DEC + '_conv_1.weight')
     grads[DEC + '_conv_1.weight'], grads[DEC + '_conv_1.bias'] = conv1d_wgrad(gd1, c['dec_in'], 3, 1, 1)
     gq = conv1d_dgrad(gd1, w, c['dec_in'].shape[2], 1, 1)
+    if c['n_spk']:
+        gq = gq[:, :gq.shape[1] - c['n_spk']]              # the speaker features are constants of the step
     if c['jitter_src'] is not None:
         # in-place column copies from a detached clone: replaced columns get zero gradient (jitter.py:49,68)
         keep = (c['jitter_src'] == np.arange(len(c['jitter_src'])))

@@ -60,7 +60,8 @@ class PortVQVAE(nn.Module):
             self.ema_w.data.normal_()
         else:
             self.emb.weight.data.uniform_(-1 / K, 1 / K)
-        self.d1 = nn.Conv1d(D, C, 3, padding=1)
+        # deconvolutional_decoder.py:56: +40 channels of speaker features when use_speaker_conditioning
+        self.d1 = nn.Conv1d(D + (40 if cfg.get('use_speaker_conditioning', False) else 0), C, 3, padding=1)
         self.dres = _Res(C, cfg['residual_channels'])
         self.t1 = nn.ConvTranspose1d(C, C, 3, padding=1)
         self.t2 = nn.ConvTranspose1d(C, C, 3, padding=0)
@@ -125,7 +126,7 @@ class PortVQVAE(nn.Module):
         ppl = torch.exp(-(p * torch.log(p + 1e-10)).sum())
         return loss, q.permute(2, 0, 1).contiguous(), ppl, idx
 
-    def forward(self, x_btf, jitter_src=None):
+    def forward(self, x_btf, jitter_src=None, speaker_features=None):
         nl = self.cfg['num_residual_layers']
         x = x_btf.permute(0, 2, 1).contiguous().float()
         a1 = F.relu(self.e1(x))
@@ -142,6 +143,8 @@ class PortVQVAE(nn.Module):
             keep = torch.as_tensor(jitter_src == np.arange(len(jitter_src)))
             src = torch.as_tensor(jitter_src, dtype=torch.long)
             q = torch.where(keep[None, None, :], q, q.detach()[:, :, src])   # replaced columns carry no gradient
+        if speaker_features is not None:     # (B, 40), repeated over time (global_conditioning.py:52-57)
+            q = torch.cat([q, speaker_features[:, :, None].expand(-1, -1, q.shape[2])], dim=1)
         y = F.interpolate(self.d1(q), scale_factor=2)
         for _ in range(nl):
             y = self.dres(y)
@@ -161,13 +164,13 @@ class PortTrainer(object):
         self.model = PortVQVAE(cfg).train()
         self.opt = torch.optim.Adam(self.model.parameters(), lr=cfg['learning_rate'], amsgrad=True)
 
-    def step(self, x_btf):
+    def step(self, x_btf, speaker_features=None):
         cfg = self.cfg
         src = None
         if cfg['use_jitter']:
             src = jitter_plan(x_btf.shape[1] // 2 + 1, cfg['jitter_probability'])
         self.opt.zero_grad()
-        recon, vq_loss, ppl, idx = self.model(x_btf, src)
+        recon, vq_loss, ppl, idx = self.model(x_btf, src, speaker_features)
         target = x_btf.permute(0, 2, 1).contiguous().float()
         recon_loss = F.mse_loss(recon, target)
         loss = vq_loss + recon_loss

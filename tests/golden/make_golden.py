@@ -122,7 +122,7 @@ def model_cfg(**over):
     return cfg
 
 
-def model_case(name, B=2, T=47, steps=3, seed=1234, **over):
+def model_case(name, B=2, T=47, steps=3, seed=1234, speakers=0, **over):
     """`steps` full trainer iterations (convolutional_trainer.py:44-74 restated: the trainer module itself
     needs matplotlib/tqdm-free imports that are absent here)."""
     cfg = model_cfg(**over)
@@ -132,7 +132,8 @@ def model_case(name, B=2, T=47, steps=3, seed=1234, **over):
     opt = torch.optim.Adam(model.parameters(), lr=cfg['learning_rate'], amsgrad=True)
     crit = torch.nn.MSELoss()
     rec = {f'cfg_{k}': v for k, v in cfg.items() if isinstance(v, (int, float, bool))}
-    rec.update(B=B, T=T, steps=steps, seed=seed)
+    rec.update(B=B, T=T, steps=steps, seed=seed, speakers=speakers)
+    speaker_dic = {'p%03d' % i: i for i in range(speakers)} if speakers else None
     for k, v in model.state_dict().items():
         rec['init.' + k] = np32(v)
     for s in range(steps):
@@ -140,7 +141,18 @@ def model_case(name, B=2, T=47, steps=3, seed=1234, **over):
         target = x.permute(0, 2, 1).contiguous().float()
         rng_state = np.random.get_state()
         opt.zero_grad()
-        recon, vq_loss, losses, perplexity, idx, _ = model(x, None, None)
+        speaker_id = None
+        if speakers:
+            # the reference draws a fresh random speaker embedding inside forward (global_conditioning.py:34): pin the
+            # host RNG right before the call so that a replay can draw the same one
+            speaker_id = torch.randint(0, speakers, (B, 1))
+            torch.manual_seed(1000 + s)
+            probe = torch.nn.Embedding(speakers, 40)
+            probe.weight.data.normal_(0, 0.1)
+            rec[f'speaker_id{s}'] = np32(speaker_id)
+            rec[f'speaker_features{s}'] = np32(probe.weight[speaker_id.view(-1)])
+            torch.manual_seed(1000 + s)
+        recon, vq_loss, losses, perplexity, idx, _ = model(x, speaker_dic, speaker_id)
         recon_loss = crit(recon, target)
         loss = vq_loss + recon_loss
         loss.backward()
@@ -172,6 +184,9 @@ if __name__ == '__main__':
         vq_eval_tables_case('noema_k44_d64_b2_t24', 44, 64, 2, 24, seed=11)
         vq_eval_tables_case('noema_k10_d2_b3_t17', 10, 2, 3, 17, seed=12)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == '--only-speaker':
+        model_case('ema_k29_speaker', decay=0.99, num_embeddings=29, use_speaker_conditioning=True, speakers=5, seed=99)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == '--only-kaiming':      # added after the other fixtures were committed
         model_case('ema_k29_kaiming', decay=0.99, num_embeddings=29, use_kaiming_normal=True, seed=777)
         sys.exit(0)
@@ -194,5 +209,7 @@ if __name__ == '__main__':
     model_case('ema_k44_b5_t191', decay=0.99, B=5, T=191, steps=2, num_hiddens=32, residual_channels=24)
     vq_eval_tables_case('noema_k44_d64_b2_t24', 44, 64, 2, 24, seed=11)
     vq_eval_tables_case('noema_k10_d2_b3_t17', 10, 2, 3, 17, seed=12)
+    # speaker conditioning (deconvolutional_decoder.py:108-111; experiments_vq29-mfcc39.json:21)
+    model_case('ema_k29_speaker', decay=0.99, num_embeddings=29, use_speaker_conditioning=True, speakers=5, seed=99)
     # weight-normalised convs (use_kaiming_normal: conv1d_builder.py:41-43, residual.py:45-47,57-59)
     model_case('ema_k29_kaiming', decay=0.99, num_embeddings=29, use_kaiming_normal=True, seed=777)

@@ -32,6 +32,7 @@ def _cfg(g):
         cfg[k] = float(g['cfg_' + k])
     cfg['use_jitter'] = bool(g['cfg_use_jitter'])
     cfg['use_kaiming_normal'] = bool(g['cfg_use_kaiming_normal'])
+    cfg['use_speaker_conditioning'] = bool(g['cfg_use_speaker_conditioning'])
     return cfg
 
 
@@ -77,7 +78,14 @@ def test_module_path_matches_reference(case):
         x = torch.from_numpy(g[f'x{s}']).to(dev)
         for p in params:
             p.grad = None
-        recon, vq_loss, losses, perplexity, idx, _ = model(x, None, None)
+        speaker_dic = speaker_id = None
+        if cfg['use_speaker_conditioning']:
+            # the decoder draws a fresh random speaker embedding from the host RNG inside forward, like the reference
+            # (global_conditioning.py:34); make_golden.py pinned the RNG to 1000 + s right before the call
+            speaker_dic = {'p%03d' % i: i for i in range(int(g['speakers']))}
+            speaker_id = torch.from_numpy(g[f'speaker_id{s}'])
+            torch.manual_seed(1000 + s)
+        recon, vq_loss, losses, perplexity, idx, _ = model(x, speaker_dic, speaker_id)
         recon_loss = F.mse_loss(recon, x.permute(0, 2, 1))
         loss = vq_loss + recon_loss
         loss.backward()
@@ -120,6 +128,10 @@ def test_fused_step_matches_reference(case, use_graph, precision):
     g = load_golden(case)
     model, cfg = _build(g, dev)
     B, T = int(g['B']), int(g['T'])
+    if cfg['use_speaker_conditioning']:      # host RNG inside forward: module path only
+        with pytest.raises(NotImplementedError):
+            FusedTrainStep(model, B, T, cfg['learning_rate'], use_graph=use_graph, precision=precision)
+        return
     eng = FusedTrainStep(model, B, T, cfg['learning_rate'], use_graph=use_graph, precision=precision)
     if cfg['use_jitter']:
         np.random.seed(int(g['seed']))

@@ -107,6 +107,8 @@ def test_model_oracle_matches_reference(case):
         if use_jitter:
             src = mo.jitter_plan(int(g['T']) // 2 + 1, float(g['cfg_jitter_probability']))
             assert np.array_equal(src, g[f'jitter_src{s}'])
+        if 'speakers' in g and int(g['speakers']):          # the step's speaker features (drawn by the reference's forward)
+            cfg['speaker_features'] = g[f'speaker_features{s}']
         r = mo.train_step(p, opt, g[f'x{s}'], cfg, jitter_src=src)
         ref_idx = g[f'idx{s}'].reshape(-1)
         assert not np.any((r['encoding_indices'].reshape(-1) != ref_idx) & ~r['near_tie'])
@@ -137,7 +139,8 @@ def test_torch_port_matches_reference(case):
     g = load_golden(case)
     cfg = dict(output_features_filters=13, augment_output_features=True, input_features_filters=13,
                augment_input_features=True, use_jitter=bool(g['cfg_use_jitter']),
-               use_kaiming_normal=bool(g['cfg_use_kaiming_normal']))
+               use_kaiming_normal=bool(g['cfg_use_kaiming_normal']),
+               use_speaker_conditioning=bool(g['cfg_use_speaker_conditioning']))
     for k in ('num_hiddens', 'num_residual_layers', 'embedding_dim', 'num_embeddings', 'residual_channels'):
         cfg[k] = int(g['cfg_' + k])
     for k in ('decay', 'commitment_cost', 'jitter_probability', 'learning_rate'):
@@ -147,7 +150,8 @@ def test_torch_port_matches_reference(case):
     tr.model.load_reference_state({k[5:]: v for k, v in g.items() if k.startswith('init.')})
     np.random.seed(int(g['seed']))
     for s in range(int(g['steps'])):
-        r = tr.step(torch.from_numpy(g[f'x{s}']))
+        sf = torch.from_numpy(g[f'speaker_features{s}']) if cfg['use_speaker_conditioning'] else None
+        r = tr.step(torch.from_numpy(g[f'x{s}']), speaker_features=sf)
         if cfg['use_jitter']:
             assert np.array_equal(r['jitter_src'], g[f'jitter_src{s}'])
         assert np.array_equal(r['encoding_indices'].numpy().reshape(-1), g[f'idx{s}'].reshape(-1))

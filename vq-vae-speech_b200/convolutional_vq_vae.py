@@ -60,10 +60,8 @@ class DeconvolutionalDecoder(nn.Module):
         self._verbose = verbose
         if self._use_jitter:
             self._jitter = Jitter(jitter_probability)
-        if self._use_speaker_conditioning:
-            # deconvolutional_decoder.py:108-111 concatenates a freshly-initialised random speaker embedding every call
-            # (global_conditioning.py:34); it is off in every north-star config and outside the hot-path scope
-            raise NotImplementedError('use_speaker_conditioning=True is outside the B200 hot-path scope (SURVEY 8f N4)')
+        # deconvolutional_decoder.py:56: the speaker features add 40 input channels ("FIXME hardcoded" there)
+        in_channels = in_channels + 40 if self._use_speaker_conditioning else in_channels
         self._conv_1 = Conv1DBuilder.build(in_channels, num_hiddens, 3, padding=1,
                                            use_kaiming_normal=use_kaiming_normal)
         self._upsample = nn.Upsample(scale_factor=2)   # kept for attribute parity; the kernel is vqs_upsample2_fwd
@@ -82,6 +80,16 @@ class DeconvolutionalDecoder(nn.Module):
         x = inputs
         if self._use_jitter and self.training:
             x = self._jitter(x)
+        if self._use_speaker_conditioning:
+            # deconvolutional_decoder.py:108-111 / global_conditioning.py:34-57: a FRESH nn.Embedding(len(speaker_dic), 40)
+            # drawn N(0, 0.1) on every call (host RNG; same constructor + normal_ sequence, so the same seed gives the same
+            # features), looked up per utterance and repeated over time.  Host-side plumbing: no arithmetic.
+            B, _, T = x.shape
+            emb = nn.Embedding(len(speaker_dic), 40, padding_idx=None)
+            emb.weight.data.normal_(0, 0.1)
+            emb = emb.to(x.device)
+            gc = emb(speaker_id.to(x.device).view(B, -1).long()).transpose(1, 2)          # (B, 40, 1)
+            x = torch.cat([x, gc.expand(B, -1, T).contiguous()], dim=1)
         x = self._conv_1(x)
         x = F.upsample2(x)
         x = self._residual_stack(x)

@@ -46,6 +46,9 @@ class FusedTrainStep(object):
         if self.dev.type != 'cuda':
             raise RuntimeError('FusedTrainStep needs the model on a CUDA device (no CPU path)')
         enc, dec, vq = model._encoder, model._decoder, model._vq
+        if getattr(dec, '_use_speaker_conditioning', False):
+            raise NotImplementedError('use_speaker_conditioning draws a fresh random embedding on the host every forward '
+                                      '(global_conditioning.py:34): module path only, not the captured step')
         self.is_ema = isinstance(vq, VectorQuantizerEMA)
         self.nl = enc._residual_stack._num_residual_layers
         if self.nl < 1:
