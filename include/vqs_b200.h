@@ -167,6 +167,10 @@ typedef struct vqs_conv_gemm_desc {
   const void* mask2;
   int mask2_kind;
   int precision; /* VQS_PREC_* : which GEMM engine computes acc */
+  /* Optional scratch (may be NULL / 0): lets the tensor-core engines split the reduction of few-tile GEMMs (M <= 128) with
+   * a bias-only epilogue over several CTAs; needs splits * M * B * Lout floats, splits <= #SMs / tiles. */
+  void* splitk_ws;
+  size_t splitk_ws_bytes;
 } vqs_conv_gemm_desc;
 
 int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream);

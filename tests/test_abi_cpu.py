@@ -41,9 +41,10 @@ def test_struct_layout_matches_c():
 #include <stddef.h>
 #include "vqs_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(vqs_conv_gemm_desc), offsetof(vqs_conv_gemm_desc, x_sb),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(vqs_conv_gemm_desc), offsetof(vqs_conv_gemm_desc, x_sb),
          offsetof(vqs_conv_gemm_desc, out), offsetof(vqs_conv_gemm_desc, precision),
-         sizeof(vqs_wgrad_desc), offsetof(vqs_wgrad_desc, dW));
+         sizeof(vqs_wgrad_desc), offsetof(vqs_wgrad_desc, dW), offsetof(vqs_conv_gemm_desc, splitk_ws),
+         offsetof(vqs_conv_gemm_desc, splitk_ws_bytes), sizeof(vqs_permute_item));
   return 0;
 }'''
     import tempfile
@@ -54,7 +55,8 @@ int main(void) {
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
         vals = [int(v) for v in subprocess.check_output([exe]).split()]
     C, W = _lib.ConvGemmDesc, _lib.WgradDesc
-    assert vals == [ctypes.sizeof(C), C.x_sb.offset, C.out.offset, C.precision.offset, ctypes.sizeof(W), W.dW.offset]
+    assert vals == [ctypes.sizeof(C), C.x_sb.offset, C.out.offset, C.precision.offset, ctypes.sizeof(W), W.dW.offset,
+                    C.splitk_ws.offset, C.splitk_ws_bytes.offset, ctypes.sizeof(_lib.PermuteItem)]
 
 
 def test_argument_validation_without_gpu():

@@ -243,3 +243,33 @@ def test_wgrad_tma_engine_matches_oracle(B, C, M, L, monkeypatch):
         assert rel_err(dW.cpu().numpy(), 2 * dw_o) < 1e-5
     finally:
         ops.set_precision(prev)
+
+
+@pytest.mark.parametrize('B,Cin,Cout,L,k', [(64, 768, 64, 24, 3), (16, 256, 39, 48, 3), (8, 512, 128, 40, 1)])
+def test_conv_forward_split_k_matches_oracle(B, Cin, Cout, L, k):
+    """Few-tile conv GEMMs (M <= 128) with a bias-only epilogue and a scratch buffer split the reduction over several CTAs
+    (gemm_tc.cu: partial tiles + conv_splitk_epilogue_kernel); same 1e-5 bar, and identical to the unsplit result's
+    oracle."""
+    dev = _dev()
+    from vq_vae_speech_b200 import functional as F, ops
+    prev = ops.set_precision('3xtf32')
+    try:
+        rng = np.random.RandomState(Cin + Cout)
+        x = rng.randn(B, Cin, L)
+        w = rng.randn(Cout, Cin, k) / np.sqrt(Cin * k)
+        b = rng.randn(Cout)
+        pad = (k - 1) // 2
+        y_o = mo.conv1d_fwd(x, w, b, 1, pad)
+        xd, wd, bd = _t(x, dev), _t(w, dev), _t(b, dev)
+        ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        A = F.gemm_weight(wd, 'conv_fwd')
+        n0 = ops._lib.launch_count()
+        y = F.conv1d_forward(xd, A, bd, 1, pad, splitk_ws=ws)
+        assert ops._lib.launch_count() - n0 == 2, 'expected the split kernel + its epilogue'
+        assert rel_err(y.cpu().numpy(), y_o) < 1e-5
+        y2 = F.conv1d_forward(xd, A, bd, 1, pad)                       # no scratch: single pass
+        assert rel_err(y2.cpu().numpy(), y_o) < 1e-5
+        y3 = F.conv1d_forward(xd, A, bd, 1, pad, relu=True, splitk_ws=ws)   # not a bias-only epilogue: no split
+        assert rel_err(y3.cpu().numpy(), np.maximum(y_o, 0)) < 1e-5
+    finally:
+        ops.set_precision(prev)

@@ -28,6 +28,7 @@ class ConvGemmDesc(Structure):
         ('mask_out', c_void_p), ('mask', c_void_p), ('mask_kind', c_int),
         ('add_post', c_void_p), ('out', c_void_p), ('out2', c_void_p), ('mask2', c_void_p), ('mask2_kind', c_int),
         ('precision', c_int),
+        ('splitk_ws', c_void_p), ('splitk_ws_bytes', c_size_t),
     ]
 
 

@@ -498,6 +498,9 @@ extern "C" int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream) {
   p.cpb = d->Cred / 32 > 0 ? d->Cred / 32 : 1;
   p.divCpb = FastDiv((uint32_t)p.cpb);
   p.divCred = FastDiv((uint32_t)d->Cred);
+  p.splits = 1;
+  p.kt_per_split = 0;
+  p.partial = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (d->a_tap_major == 2) {
     VQS_CHECK_ARG(d->precision != VQS_PREC_FP32 && conv_tc_supported(p),

@@ -10,6 +10,10 @@ struct ConvParams {
   int a_vec;  // A rows are 16-byte aligned and Ktot % 4 == 0
   int cpb;    // 32-wide k-blocks per tap (tap-major A): Cred / 32
   FastDiv divL, divCpb, divCred;
+  // split-K (tensor-core engines, few-tile GEMMs with a bias-only epilogue): grid.z CTAs take kt_per_split k-blocks each
+  // and write raw accumulators to partial[z][M][Ntot]; conv_splitk_epilogue_kernel sums them and adds the bias
+  int splits, kt_per_split;
+  float* partial;
 };
 
 struct WgradParams {

@@ -229,8 +229,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   if constexpr (MODE == 0) a_image = prm.p.d.a_tap_major == 2;
   int nkb, kb_begin;
   if constexpr (MODE == 0) {
-    nkb = (prm.p.Ktot + BKF - 1) / BKF;
-    kb_begin = 0;
+    const int total = (prm.p.Ktot + BKF - 1) / BKF;
+    kb_begin = prm.p.splits > 1 ? blockIdx.z * prm.p.kt_per_split : 0;
+    int kb_end = prm.p.splits > 1 ? kb_begin + prm.p.kt_per_split : total;
+    if (kb_end > total) kb_end = total;
+    nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;
   } else {
     const int total = (prm.p.Kred + BKF - 1) / BKF;
     kb_begin = blockIdx.z * prm.p.kt_per_split;
@@ -437,6 +440,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
       const bool n_ok = n < Ncols;
       if constexpr (MODE == 0) {
         const vqs_conv_gemm_desc& d = prm.p.d;
+        if (prm.p.partial != nullptr) {      // split-K: raw accumulators, coalesced along n
+          float* po = prm.p.partial + (size_t)blockIdx.z * d.M * prm.p.Ntot;
+          for (int r = 0; r < 32; ++r) {
+            const int m = m0 + q * 32 + r;
+            if (m >= d.M) break;
+            if (n_ok) po[(size_t)m * prm.p.Ntot + n] = stg[r * 33 + lane];
+          }
+          __syncwarp();
+          continue;
+        }
         uint32_t b = 0, l = 0;
         if (n_ok) prm.p.divL.divmod((uint32_t)n, b, l);
         const size_t col = (size_t)b * d.M * d.Lout + l;
@@ -543,6 +556,20 @@ bool conv_tc_supported(const ConvParams& p) {
 }
 bool wgrad_tc_supported(const WgradParams& p) { return p.d.ksz >= 1 && p.d.ksz <= 4 && p.Kred >= 32; }
 
+// out[b][m][l] = bias[m] + sum_z partial[z][m][n = b * Lout + l]
+__global__ void __launch_bounds__(256) conv_splitk_epilogue_kernel(const float* __restrict__ partial, int splits, int M,
+                                                                   int Ntot, int Lout, const float* __restrict__ bias,
+                                                                   float* __restrict__ out) {
+  const long long total = (long long)M * Ntot;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int m = (int)(i / Ntot), n = (int)(i - (long long)m * Ntot);
+    float a = bias ? __ldg(bias + m) : 0.f;
+    for (int z = 0; z < splits; ++z) a += partial[(size_t)z * total + i];
+    const int b = n / Lout, l = n - b * Lout;
+    out[((size_t)b * M + m) * Lout + l] = a;
+  }
+}
+
 int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
   TcParams<0> prm;
   prm.p = p;
@@ -554,8 +581,38 @@ int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
   const long long t128 = (long long)mt * ((p.Ntot + 127) / 128), t64 = (long long)mt * ((p.Ntot + 63) / 64);
   const double c128 = (double)((t128 + sms - 1) / sms), c64 = 0.6 * (double)((t64 + sms - 1) / sms);
   int bn = (c128 <= c64) ? 128 : 64;
-  dim3 grid((p.Ntot + bn - 1) / bn, mt, 1);
-  return launch_tc<0>(prm, p.d.ksz, bn, precision, grid, st);
+  // Split-K for GEMMs that offer only a handful of tiles (M <= 128 layers: pre_vq conv, the decoder's first dgrad, the
+  // last transposed conv: 12 - 24 CTAs walking 48 - 72 k-blocks each = 0.05 - 0.066 ms).  Needs the caller's scratch
+  // (splitk_ws) and a bias-only epilogue; partial sums are folded in a fixed order -> deterministic.
+  const vqs_conv_gemm_desc& d = p.d;
+  const int nkb = (p.Ktot + BKF - 1) / BKF;
+  const bool plain = !d.add_pre && !d.relu && !d.mask_out && !d.mask_kind && !d.add_post && !d.out2;
+  prm.p.splits = 1;
+  prm.p.partial = nullptr;
+  if (plain && d.splitk_ws != nullptr && nkb >= 8) {
+    bn = 64;
+    const long long tiles = (long long)mt * ((p.Ntot + 63) / 64);
+    if (tiles * 3 <= sms) {
+      int s = (int)(sms / tiles);
+      if (s > nkb / 4) s = nkb / 4;
+      const size_t need = (size_t)s * d.M * p.Ntot * sizeof(float);
+      if (s >= 2 && need <= d.splitk_ws_bytes) {
+        prm.p.kt_per_split = (nkb + s - 1) / s;
+        prm.p.splits = (nkb + prm.p.kt_per_split - 1) / prm.p.kt_per_split;
+        prm.p.partial = (float*)d.splitk_ws;
+      }
+    }
+  }
+  dim3 grid((p.Ntot + bn - 1) / bn, mt, prm.p.splits);
+  if (int e = launch_tc<0>(prm, p.d.ksz, bn, precision, grid, st)) return e;
+  if (prm.p.partial != nullptr) {
+    const long long total = (long long)d.M * p.Ntot;
+    const long long blocks = (total + 255) / 256;
+    conv_splitk_epilogue_kernel<<<(int)(blocks < 4 * sms ? blocks : 4 * sms), 256, 0, st>>>(
+        prm.p.partial, prm.p.splits, d.M, p.Ntot, d.Lout, d.bias, d.out);
+    VQS_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 int launch_wgrad_tc(const WgradParams& p, int precision, cudaStream_t st) {

@@ -200,7 +200,8 @@ def vq_grad_codebook(stats, codebook, g_loss, coef, out=None, accumulate=False):
 # ------------------------------------------------------------------------------------------------
 def conv_gemm(A, X, out, M, Cred, ksz, B, Lin, Lout, l_mul, j_mul, off, l_div=1, x_strides=None, x_relu=False,
               bias=None, add_pre=None, add_pre_relu=False, relu=False, mask_out=None, mask=None, mask_kind=MASK_NONE,
-              add_post=None, out2=None, mask2=None, mask2_kind=MASK_NONE, precision=None, a_tap_major=False):
+              add_post=None, out2=None, mask2=None, mask2_kind=MASK_NONE, precision=None, a_tap_major=False,
+              splitk_ws=None):
     """acc[b,m,l] = sum_{c,j} A[m, c*ksz+j] * X'[b, c, (l*l_mul + j*j_mul + off)/l_div] followed by the fused epilogue
     documented in include/vqs_b200.h.  x_strides = (batch, channel, position) element strides of X (default NCL)."""
     d = ConvGemmDesc()
@@ -227,6 +228,9 @@ def conv_gemm(A, X, out, M, Cred, ksz, B, Lin, Lout, l_mul, j_mul, off, l_div=1,
     d.mask2 = _pany(mask2)
     d.mask2_kind = mask2_kind if mask2 is not None else MASK_NONE
     d.precision = _PRECISION if precision is None else _lib.PRECISIONS[precision]
+    d.splitk_ws = _pany(splitk_ws)
+    d.splitk_ws_bytes = splitk_ws.numel() * splitk_ws.element_size() if splitk_ws is not None else 0
+    d._splitk_ws_ref = splitk_ws                # keeps the scratch tensor alive with the recorded descriptor
     _call('vqs_conv_gemm', (ctypes.byref(d),), d)
     return out
 

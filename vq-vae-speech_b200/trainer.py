@@ -290,7 +290,8 @@ class FusedTrainStep(object):
             else:
                 cfwd(b['e_hh%d' % i], E + RS2, None, 1, 0, out=b['enc_out'], add_pre=xs[i],
                                  add_pre_relu=True, relu=True, mask_out=b['m_e'], add_post=b['h5'])
-        cfwd(b['enc_out'], '_pre_vq_conv.weight', P('_pre_vq_conv.bias'), 1, 1, out=b['z'])
+        # (M = D = 64 output channels: a single row of tiles -> split-K over the wgrad scratch, see vqs_b200.h)
+        cfwd(b['enc_out'], '_pre_vq_conv.weight', P('_pre_vq_conv.bias'), 1, 1, out=b['z'], splitk_ws=ws)
 
         # ---- 2. VQ bottleneck ----
         vq = m._vq
@@ -324,7 +325,7 @@ class FusedTrainStep(object):
         tfwd(b['t1'], DEC + '_conv_trans_2.weight', P(DEC + '_conv_trans_2.bias'), 0, out_len=Lt2, out=b['t2'],
                           relu=True)
         tfwd(b['t2'], DEC + '_conv_trans_3.weight', P(DEC + '_conv_trans_3.bias'), 0, out_len=T,
-                          out=b['recon'])                                          # trimmed to T (vq_vae.py:133-137)
+                          out=b['recon'], splitk_ws=ws)                                          # trimmed to T (vq_vae.py:133-137)
 
         # ---- 4. loss (trainer.py:54-56): MSE against the input features, gradient in the same pass ----
         ops.mse_fwd_bwd(b['recon'], b['x'], (Fi * T, T, 1), 1.0, b['recon_loss'], b['g_recon'], self.ws_mse)
@@ -362,10 +363,10 @@ class FusedTrainStep(object):
         ops.bias_grad(gd1, G[DEC + '_conv_1.bias'])
         gq = b['gq']
         if self.use_jitter:
-            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=b['gqj'])
+            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=b['gqj'], splitk_ws=ws)
             ops.jitter_bwd(b['gqj'], b['jitter_src'], gq)
         else:
-            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=gq)
+            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=gq, splitk_ws=ws)
         self._emit_wn_fold(*self.buckets['dec_rest'])
         if self.world > 1:       # decoder gradients are complete: allreduce the rest of them under the encoder's backward
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_rest']))
