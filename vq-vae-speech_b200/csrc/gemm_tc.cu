@@ -556,17 +556,28 @@ bool conv_tc_supported(const ConvParams& p) {
 }
 bool wgrad_tc_supported(const WgradParams& p) { return p.d.ksz >= 1 && p.d.ksz <= 4 && p.Kred >= 32; }
 
-// out[b][m][l] = bias[m] + sum_z partial[z][m][n = b * Lout + l]
-__global__ void __launch_bounds__(256) conv_splitk_epilogue_kernel(const float* __restrict__ partial, int splits, int M,
-                                                                   int Ntot, int Lout, const float* __restrict__ bias,
-                                                                   float* __restrict__ out) {
-  const long long total = (long long)M * Ntot;
+// Folds the split-K partials partial[z][m][n = b * Lout + l] in a fixed order and applies the descriptor's fused epilogue
+// (vqs_b200.h: bias, add_pre (+relu), relu, mask_out, mask, add_post, out, out2 / mask2), coalesced along l.
+__global__ void __launch_bounds__(256) conv_splitk_epilogue_kernel(const float* __restrict__ partial, int splits,
+                                                                   int Ntot, const vqs_conv_gemm_desc d) {
+  const long long total = (long long)d.M * Ntot;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int m = (int)(i / Ntot), n = (int)(i - (long long)m * Ntot);
-    float a = bias ? __ldg(bias + m) : 0.f;
-    for (int z = 0; z < splits; ++z) a += partial[(size_t)z * total + i];
-    const int b = n / Lout, l = n - b * Lout;
-    out[((size_t)b * M + m) * Lout + l] = a;
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += partial[(size_t)z * total + i];
+    const int b = n / d.Lout, l = n - b * d.Lout;
+    const size_t o = ((size_t)b * d.M + m) * d.Lout + l;
+    if (d.bias) v += __ldg(d.bias + m);
+    if (d.add_pre) {
+      const float pre = d.add_pre[o];
+      v += d.add_pre_relu ? fmaxf(pre, 0.f) : pre;
+    }
+    if (d.relu) v = fmaxf(v, 0.f);
+    if (d.mask_out) d.mask_out[o] = v > 0.f ? 1 : 0;
+    if (d.mask_kind && !tc_mask_on(d.mask, d.mask_kind, o)) v = 0.f;
+    if (d.add_post) v += d.add_post[o];
+    d.out[o] = v;
+    if (d.out2) d.out2[o] = (!d.mask2_kind || tc_mask_on(d.mask2, d.mask2_kind, o)) ? v : 0.f;
   }
 }
 
@@ -581,26 +592,31 @@ int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
   const long long t128 = (long long)mt * ((p.Ntot + 127) / 128), t64 = (long long)mt * ((p.Ntot + 63) / 64);
   const double c128 = (double)((t128 + sms - 1) / sms), c64 = 0.6 * (double)((t64 + sms - 1) / sms);
   int bn = (c128 <= c64) ? 128 : 64;
-  // Split-K for GEMMs that offer only a handful of tiles (M <= 128 layers: pre_vq conv, the decoder's first dgrad, the
-  // last transposed conv: 12 - 24 CTAs walking 48 - 72 k-blocks each = 0.05 - 0.066 ms).  Needs the caller's scratch
-  // (splitk_ws) and a bias-only epilogue; partial sums are folded in a fixed order -> deterministic.
+  // Split-K (needs the caller's scratch, splitk_ws; partial sums are folded in a fixed order -> deterministic):
+  //  * a handful of tiles (M <= 128 layers: pre_vq conv, the decoder's first dgrad, the last transposed conv: 12 - 24 CTAs
+  //    walking 48 - 72 k-blocks each = 0.05 - 0.066 ms): 64-column tiles, as many splits as fill the machine;
+  //  * half a wave of 128-column tiles (the T_q = 24 layers: N = 1536 -> 72 tiles): two splits of 128 x 128 tiles instead
+  //    of one wave of 128 x 64 tiles that re-read the weight operand for half the work.
   const vqs_conv_gemm_desc& d = p.d;
   const int nkb = (p.Ktot + BKF - 1) / BKF;
-  const bool plain = !d.add_pre && !d.relu && !d.mask_out && !d.mask_kind && !d.add_post && !d.out2;
   prm.p.splits = 1;
   prm.p.partial = nullptr;
-  if (plain && d.splitk_ws != nullptr && nkb >= 8) {
-    bn = 64;
-    const long long tiles = (long long)mt * ((p.Ntot + 63) / 64);
-    if (tiles * 3 <= sms) {
-      int s = (int)(sms / tiles);
-      if (s > nkb / 4) s = nkb / 4;
-      const size_t need = (size_t)s * d.M * p.Ntot * sizeof(float);
-      if (s >= 2 && need <= d.splitk_ws_bytes) {
-        prm.p.kt_per_split = (nkb + s - 1) / s;
-        prm.p.splits = (nkb + prm.p.kt_per_split - 1) / prm.p.kt_per_split;
-        prm.p.partial = (float*)d.splitk_ws;
-      }
+  if (d.splitk_ws != nullptr && nkb >= 8) {
+    int s = 0, sbn = 0;
+    if (t64 * 3 <= sms) {
+      sbn = 64;
+      s = (int)(sms / t64);
+    } else if (t128 * 2 <= sms && t128 * 3 > sms && nkb >= 48) {   // (k = 1 layers, 24 k-blocks: the split loses)
+      sbn = 128;
+      s = (int)(sms / t128);
+    }
+    if (s > nkb / 4) s = nkb / 4;
+    const size_t need = (size_t)(s > 0 ? s : 0) * d.M * p.Ntot * sizeof(float);
+    if (s >= 2 && need <= d.splitk_ws_bytes) {
+      bn = sbn;
+      prm.p.kt_per_split = (nkb + s - 1) / s;
+      prm.p.splits = (nkb + prm.p.kt_per_split - 1) / prm.p.kt_per_split;
+      prm.p.partial = (float*)d.splitk_ws;
     }
   }
   dim3 grid((p.Ntot + bn - 1) / bn, mt, prm.p.splits);
@@ -608,8 +624,8 @@ int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
   if (prm.p.partial != nullptr) {
     const long long total = (long long)d.M * p.Ntot;
     const long long blocks = (total + 255) / 256;
-    conv_splitk_epilogue_kernel<<<(int)(blocks < 4 * sms ? blocks : 4 * sms), 256, 0, st>>>(
-        prm.p.partial, prm.p.splits, d.M, p.Ntot, d.Lout, d.bias, d.out);
+    conv_splitk_epilogue_kernel<<<(int)(blocks < 8 * sms ? blocks : 8 * sms), 256, 0, st>>>(prm.p.partial, prm.p.splits,
+                                                                                            p.Ntot, d);
     VQS_LAUNCH_CHECK();
   }
   return 0;

@@ -258,16 +258,21 @@ class FusedTrainStep(object):
             M, Cred, k = F._role_dims(tuple(P(name).shape), role)
             return F.GemmW(buf if buf is not None else P(name), tap, M, Cred, k)
 
+        # every conv-like GEMM may use the wgrad scratch for split-K (few-tile and half-wave shapes, see launch_conv_tc)
         def cfwd(xin, name, bias, stride, pad, **kw):
+            kw.setdefault('splitk_ws', ws)
             return F.conv1d_forward(xin, A(name, 'conv_fwd'), bias, stride, pad, **kw)
 
         def cdgrad(gy, name, Lx, stride, pad, **kw):
+            kw.setdefault('splitk_ws', ws)
             return F.conv1d_dgrad(gy, A(name, 'conv_dgrad'), Lx, stride, pad, **kw)
 
         def tfwd(xin, name, bias, pad, **kw):
+            kw.setdefault('splitk_ws', ws)
             return F.convT1d_forward(xin, A(name, 'convT_fwd'), bias, pad, **kw)
 
         def tdgrad(gy, name, Lx, pad, **kw):
+            kw.setdefault('splitk_ws', ws)
             return F.convT1d_dgrad(gy, A(name, 'convT_dgrad'), Lx, pad, **kw)
 
         # ---- 1. encoder forward (convolutional_encoder.py:118-146) ----
