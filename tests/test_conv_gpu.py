@@ -224,7 +224,7 @@ def test_permute_weights_batched_matches_single_calls():
 
 @pytest.mark.parametrize('B,C,M,L', [(4, 128, 256, 48), (3, 256, 128, 20), (70, 128, 128, 36), (64, 768, 768, 24)])
 def test_wgrad_tma_engine_matches_oracle(B, C, M, L, monkeypatch):
-    """The opt-in TMA-fed weight-gradient kernel (VQS_WGRAD_TMA=1: tensor-map boxes as raw tf32 operands, threads only
+    """The TMA-fed weight-gradient kernel (default on; VQS_WGRAD_TMA=0 disables it: tensor-map boxes as raw tf32 operands, threads only
     derive the lo tiles) on the shapes it accepts (1 x 1 convolutions), incl. the fused input ReLU and accumulation."""
     dev = _dev()
     from vq_vae_speech_b200 import functional as F, ops

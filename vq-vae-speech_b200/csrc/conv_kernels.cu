@@ -8,6 +8,8 @@
 // activation tensor (padding, stride, transposed-conv tap flip, nearest-neighbour index and input ReLU are all index
 // arithmetic in the loader), so no im2col buffer ever exists in HBM.
 #include "vqs_common.cuh"
+#include <math.h>
+
 #include "gemm_params.cuh"
 
 namespace vqs {
@@ -344,11 +346,35 @@ WgradPlan plan_wgrad(int M, int Nw, int Kred, int bk = BK, bool tc = false) {
   pl.bn = (tc || Nw > 64) ? 128 : 64;
   long long tiles = (long long)((M + pl.bm - 1) / pl.bm) * ((Nw + pl.bn - 1) / pl.bn);
   int ktiles = (Kred + bk - 1) / bk;
-  long long want = ((tc ? 3ll : 2ll) * num_sms() + tiles - 1) / tiles;
   int max_s = ktiles / 4 > 0 ? ktiles / 4 : 1;
+  if (max_s > 64) max_s = 64;
+  if (tc) {
+    // One CTA per SM: a launch costs ceil(tiles * splits / SMs) rounds of (k-blocks per CTA * 1.6 us + 4 us of
+    // prologue / epilogue) -- fitted on the B200 (768 x 2304 x 3072: 4 splits = 3 rounds of 24 k-blocks = 0.132 ms,
+    // 1 split of 48 k-blocks = 0.081 ms; 768 x 768 x 3072: 12 splits = 3 rounds of 8 = 0.060 ms) -- plus the reduction pass
+    // over the partials.  "3 CTAs per SM" (the first rule) paid a whole extra round on most layers of the step (1.52 ms of
+    // wgrad per step; 1.34 ms with the cheapest split).
+    const double sms = (double)num_sms();
+    double best = 1e30;
+    int best_kps = ktiles;
+    for (int s = 1; s <= max_s; ++s) {
+      const int kps = (ktiles + s - 1) / s;
+      const int se = (ktiles + kps - 1) / kps;
+      const double rounds = ceil((double)tiles * se / sms);
+      double cost = rounds * (kps * 1.6 + 4.0);
+      if (se > 1) cost += 2.0 + se * ((double)M * Nw * 4.0) / 5.0e6;
+      if (cost < best - 1e-9) {
+        best = cost;
+        best_kps = kps;
+      }
+    }
+    pl.kt_per_split = best_kps;
+    pl.splits = (ktiles + best_kps - 1) / best_kps;
+    return pl;
+  }
+  long long want = (2ll * num_sms() + tiles - 1) / tiles;
   int s = (int)(want < 1 ? 1 : want);
   if (s > max_s) s = max_s;
-  if (s > 64) s = 64;
   pl.kt_per_split = (ktiles + s - 1) / s;
   pl.splits = (ktiles + pl.kt_per_split - 1) / pl.kt_per_split;
   return pl;

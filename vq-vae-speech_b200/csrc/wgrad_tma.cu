@@ -271,11 +271,11 @@ bool wgrad_tma_supported(const WgradParams& p) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   // TMA needs 16-byte aligned box origins: every tap shift j*j_mul + off must be a multiple of 4 positions.  That holds
   // for the 1 x 1 convolutions only (k = 3, pad = 1 shifts by -1 / 0 / +1); shifted taps need a staged, re-aligned copy.
-  // Opt-in (VQS_WGRAD_TMA=1): on the training step's 1 x 1 layers it only ties with the gather kernel (0.060 vs 0.060 ms
-  // at Kred = 3072, 0.049 vs 0.046 ms at Kred = 1536 -- those launches are bound by split-K overheads, not by the
-  // operand feed), so the default stays with one code path until the shifted taps can use it too.
-  const char* on = getenv("VQS_WGRAD_TMA");
-  if (!on || on[0] != '1') return false;
+  // On by default (VQS_WGRAD_TMA=0 switches it off): on the step's 1 x 1 layers it beats the gather kernel by ~10 %
+  // (0.0416 vs 0.0453 ms at Kred = 3072, 0.031 vs 0.032 ms at Kred = 1536) although a quarter of its k-blocks is zero
+  // padding (L = 48 / 24 positions in blocks of 32).
+  const char* off = getenv("VQS_WGRAD_TMA");
+  if (off && off[0] == '0') return false;
   for (int j = 0; j < d.ksz; ++j)
     if ((j * d.j_mul + d.off) % 4 != 0) return false;
   return d.precision == VQS_PREC_TF32X3 && d.l_mul == 1 && d.La % 4 == 0 && d.Lx % 4 == 0 && d.M % 128 == 0 &&
