@@ -26,6 +26,8 @@
 // 32-wide k-block has ONE tap j and 32 consecutive channels: the padding / stride / bounds arithmetic of the gather is
 // done once per k-block per thread and the loads walk a constant channel stride (first build: (c, j) order, 815
 // instructions per thread per k-block, issue-bound at 43 TFLOP/s -- profiles/r01c_ncu_full_gemm_tc_vq.txt).
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "gemm_params.cuh"
@@ -619,6 +621,8 @@ int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
       prm.p.partial = (float*)d.splitk_ws;
     }
   }
+  // (Tried: running the heavy dgrad epilogues -- masks, skip additions, second output -- as a separate pass over raw
+  // accumulators instead of serially after each CTA's main loop: 3.42 vs 3.36 ms per step, so they stay in the kernel.)
   dim3 grid((p.Ntot + bn - 1) / bn, mt, prm.p.splits);
   if (int e = launch_tc<0>(prm, p.d.ksz, bn, precision, grid, st)) return e;
   if (prm.p.partial != nullptr) {
