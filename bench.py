@@ -37,6 +37,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=47, help='MFCC frames per utterance (length 7680 -> 47)')
     ap.add_argument('--decay', type=float, default=0.99)
     ap.add_argument('--codes', type=int, default=44)
+    ap.add_argument('--jitter', action='store_true', help='use_jitter = true (jitter.py:47-70, p = 0.12); BASELINE configs[4]')
     ap.add_argument('--precision', default='3xtf32', choices=['fp32', '3xtf32', 'tf32'],
                     help='GEMM engine of the conv GEMMs: 3xtf32 = tcgen05 with the fp32-accurate split (1e-5 parity)')
     ap.add_argument('--vq-rows', type=int, default=1 << 22)
@@ -109,7 +110,8 @@ def measured_traffic(kernel):
 
 def model_config(args):
     from vq_vae_speech_b200.trainer import reference_config
-    return reference_config(decay=args.decay, num_embeddings=args.codes, batch_size=args.batch)
+    return reference_config(decay=args.decay, num_embeddings=args.codes, batch_size=args.batch,
+                            use_jitter=bool(getattr(args, 'jitter', False)))
 
 
 def flops_of(entry):
@@ -186,6 +188,7 @@ def workload_config(args, world, batch_override=None):
     return {'workload': 'vq44-mfcc39 full training step (encoder + VectorQuantizerEMA %dx64 + decoder, MSE + vq_loss, '
                         'AMSGrad lr 2e-4), synthetic MFCC-39, T=%d' % (args.codes, args.frames),
             'per_gpu_batch': b, 'global_batch': b * world, 'frames': args.frames, 'decay': args.decay,
+            'use_jitter': bool(getattr(args, 'jitter', False)),
             'parallelism': 'dp%d' % world, 'gemm_engine': getattr(args, 'precision', None),
             'l2': 'no explicit flush: every step streams weights + optimizer state + activations >> 126 MB L2'}
 

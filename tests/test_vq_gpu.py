@@ -130,6 +130,11 @@ SWEEP = [  # (K, D, B, T, layout-name)  sizes the oracle finishes in seconds
     (10, 2, 2, 24, 'bdt'), (10, 2, 64, 96, 'bdt'), (100, 64, 5, 24, 'bdt'), (512, 64, 32, 96, 'bdt'),
     (1000, 64, 8, 24, 'bdt'), (4096, 64, 4, 96, 'bdt'), (44, 64, 1, 1000, 'flat'), (44, 48, 3, 50, 'bdt'),
     (7, 5, 3, 11, 'bdt'), (1, 64, 2, 24, 'bdt'), (44, 64, 1, 1, 'bdt'), (64, 128, 4, 24, 'bdt'),
+    # B >= 4 D: the element-wise kernels walk (B, D, T) in the blocked order (16 batch items x 8 frames per warp); B not a
+    # multiple of 16 and an odd number of 4-frame groups exercise its masks
+    (44, 64, 260, 20, 'bdt'), (29, 64, 300, 12, 'bdt'), (10, 2, 64, 8, 'bdt'),
+    # D = 64, B % 64 == 0, B >= 256: the tiled element-wise kernels (indices staged in shared memory); partial frame block
+    (44, 64, 320, 40, 'bdt'), (29, 64, 256, 8, 'bdt'),
 ]
 
 
@@ -277,6 +282,12 @@ TC_CASES = [  # (K, D, B, T, layout, data)
     # flat rows, K <= 48: the streaming engine (TMA tiles as raw tf32 operands, vq_assign_tma_kernel)
     (29, 64, 1, 5000, 'flat', 'trained'), (48, 64, 1, 4097, 'flat', 'randn'), (1, 64, 1, 300, 'flat', 'randn'),
     (44, 64, 1, 100, 'flat', 'near_dup'), (17, 64, 1, 33000, 'flat', 'huge'), (44, 64, 1, 1 << 20, 'flat', 'trained'),
+    # (B, D, T) rows with B % 64 == 0, K <= 48: the same streaming engine fed by the cp.async gather.  Tile shapes:
+    # 16 frames x 8 batch groups with a partial last frame block; 8 x 16; 32 x 4 with 4 of 32 frames in the last block
+    (44, 64, 512, 47, 'bdt', 'randn'), (29, 64, 1024, 24, 'bdt', 'trained'), (44, 64, 256, 100, 'bdt', 'near_dup'),
+    (48, 64, 2048, 32, 'bdt', 'huge'), (1, 64, 256, 33, 'bdt', 'randn'),
+    # batch groups not divisible by 4: 64 frames x 2 groups, 128 frames x 1 group
+    (44, 64, 384, 96, 'bdt', 'trained'), (31, 64, 192, 200, 'bdt', 'randn'),
 ]
 
 
@@ -368,6 +379,54 @@ def test_vq_streaming_engine_fuzz_matches_cuda_core_engine():
             assert torch.equal(s_tc[:K], s_cc[:K]), tag
             assert rel_err(s_tc[K:].cpu().numpy(), s_cc[K:].cpu().numpy()) < TOL, tag
             assert torch.equal(i_tc, i_t2) and torch.equal(s_tc, s_t2), tag + ': not deterministic'
+    finally:
+        ops.vq_set_engine('auto')
+
+
+def test_vq_streaming_engine_bdt_fuzz_matches_cuda_core_engine():
+    """The reference's own row layout through the streaming engine (vq_assign_tma_kernel<BDT>: rows gathered from the
+    (B, 64, T) tensor by cp.async, B % 64 == 0): identical indices and counts as the exact fp32 CUDA-core search, dw within
+    1e-5, bit-identical on a second run, and the indices sit at the reference's row positions (ema.py:101-106)."""
+    dev = _dev()
+    from vq_vae_speech_b200 import ops, LAYOUT_BDT_AS_DTB
+    rng = np.random.RandomState(77)
+    D = 64
+    try:
+        for case in range(24):
+            K = int(rng.randint(1, 49))
+            Q = int(rng.choice([4, 8, 12, 16, 20, 32, 64]))
+            T = int(rng.choice([8, 9, 16, 24, 31, 32, 33, 47, 64, 96, 191]))
+            B = 64 * Q
+            kind = rng.choice(['randn', 'trained', 'tiny_codes', 'dup'])
+            W = rng.randn(K, D).astype(np.float32)
+            if kind == 'tiny_codes':
+                W *= 0.05
+            if kind == 'dup' and K > 2:
+                W[K - 1] = W[0]
+                W[K // 2] = W[0] * (1 + 1e-7)
+            N = B * T
+            if kind == 'trained':
+                rows = (W[rng.randint(0, K, N)] + 0.05 * rng.randn(N, D)).astype(np.float32)
+            else:
+                rows = rng.randn(N, D).astype(np.float32)
+            z, Wd = _t(vqo.bdt_from_rows(rows, B, D, T), dev), _t(W, dev)
+            ws = ops.vq_workspace(K, D, dev)
+            ops.vq_set_engine('cuda_core')
+            i_cc, s_cc = ops.vq_assign(z, Wd, LAYOUT_BDT_AS_DTB, ws)
+            i_cc, s_cc = i_cc.clone(), s_cc.clone()
+            ops.vq_set_engine('tensor_core')
+            i_tc, s_tc = ops.vq_assign(z, Wd, LAYOUT_BDT_AS_DTB, ws)
+            i_tc, s_tc = i_tc.clone(), s_tc.clone()
+            i_t2, s_t2 = ops.vq_assign(z, Wd, LAYOUT_BDT_AS_DTB, ws)
+            tag = 'case %d: K=%d B=%d T=%d %s' % (case, K, B, T, kind)
+            assert torch.equal(i_tc, i_cc), tag + ': %d rows differ' % int((i_tc != i_cc).sum())
+            assert torch.equal(s_tc[:K], s_cc[:K]), tag
+            assert rel_err(s_tc[K:].cpu().numpy(), s_cc[K:].cpu().numpy()) < TOL, tag
+            assert torch.equal(i_tc, i_t2) and torch.equal(s_tc, s_t2), tag + ': not deterministic'
+            if case < 8 and kind in ('randn', 'trained'):   # against the oracle on the reference's rows
+                idx_o, near, _ = vqo.assign(rows, W)
+                mism = i_tc.cpu().numpy() != idx_o
+                assert not np.any(mism & ~near), tag
     finally:
         ops.vq_set_engine('auto')
 

@@ -17,9 +17,19 @@
 //     are integers (match.any + one shared-memory atomic per distinct code and warp).
 // Warp roles (576 threads, one persistent CTA per SM): warps 0-11 scan (three groups taking tiles round-robin, TMEM lane
 // quarter = warp % 4), warps 12-15 statistics, warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer.
+//
+// (B, D, T) rows (the reference's own layout, ema.py:101-106: row r = 64 consecutive elements of the (D, T, B) flattening)
+// run through the SAME pipeline when B is a multiple of 64: a row is then the 64 batch items b of one (d, t), a
+// transposing gather no TMA box can express.  The BDT instantiation replaces the TMA warp by two producer warps that
+// move a tile of TT frames x GB batch groups (TT * GB = 128 rows of one channel d) with 4-byte cp.async copies straight into the
+// swizzled operand layout: a warp request covers 8 consecutive t of 4 batch items (four full 32-byte sectors of HBM, 32
+// distinct banks of shared memory), one to three tiles per thread stay in flight, and a stage is published by cp.async.wait_group
+// -> fence.proxy.async -> mbarrier.arrive of every producer thread.  Frames beyond T are zero-filled rows that are not
+// counted.  Everything downstream (MMAs, scan, settlement, statistics) is shared with the flat instantiation.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "tc_common.cuh"
 
@@ -32,6 +42,13 @@ struct AssignTmaParams {
   long long N;
   int K, Kpad, ntiles;
   int debug;   // profiling aid (env VQS_TMA_DEBUG): bit 0 skips the statistics pass, bit 1 the settlement, bit 2 the scan
+  // (B, D, T) instantiation only: tile = (batch block bbb, channel d, frame block tb), tile id = (bbb * 64 + d) * NTB + tb
+  const float* z;
+  int T, Q;          // frames, batch groups per (d, t) = B / 64
+  int TT, GB;        // frames x batch groups per tile (TT * GB = 128), both powers of two, TT >= 8
+  int tt_shift;      // log2(TT)
+  int lag;           // tiles a producer thread keeps in flight behind the one it is issuing (1 .. 3)
+  FastDiv divNTB;    // NTB = ceil(T / TT) frame blocks
 };
 
 namespace {
@@ -46,6 +63,10 @@ constexpr int NIDX = 4;                  // index buffers between the scan and t
 constexpr int SROWS = TR / STAT_WARPS;   // rows of a tile per statistics warp
 constexpr int TMA_WARP = SCAN_WARPS + STAT_WARPS, MMA_WARP = TMA_WARP + 1;
 constexpr int NT = (MMA_WARP + 1) * 32;
+// (B, D, T) instantiation: warp TMA_WARP and one more behind the MMA warp.  19 warps = at most 5 per SM sub-partition keeps
+// the 96-register budget of the scan warps (21 warps: ptxas caps at 80 registers and spills 180 bytes).
+constexpr int PROD_WARPS = 2;
+constexpr int NT_BDT = NT + (PROD_WARPS - 1) * 32;
 constexpr int KMAX = 48;              // four private bin copies of K x 64 floats must fit beside the tile ring
 // Tensor-core filter.  kind::tf32 drops the low 13 mantissa bits of both operands: |x_j e_j - tf32(x_j) tf32(e_j)| <
 // (2 * 2^-10 + 2^-20) |x_j e_j|, so the score s_k = |e_k|^2 - 2 x.e_k is off by < 3.91e-3 |x||e_k| (Cauchy-Schwarz); packing
@@ -86,6 +107,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// 4-byte asynchronous copy; src_bytes = 0 writes a zero instead of reading
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const float* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ float2 lds_v2(uint32_t addr) {
   float2 v;
@@ -234,8 +259,24 @@ __device__ __forceinline__ float row_sumsq_canon(const uint8_t* xt, int r) {
   return b0 + b1;
 }
 
-__global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                              const AssignTmaParams p) {
+// where tile `tile` of the (B, D, T) instantiation lives: channel d, first frame t0, first batch group bb0
+struct BdtTile {
+  int d, t0, bb0;
+};
+__device__ __forceinline__ BdtTile bdt_tile(const AssignTmaParams& p, int tile) {
+  uint32_t rest, tb;
+  p.divNTB.divmod((uint32_t)tile, rest, tb);
+  BdtTile t;
+  t.d = (int)(rest & 63u);
+  t.t0 = (int)tb << p.tt_shift;
+  t.bb0 = (int)(rest >> 6) * p.GB;
+  return t;
+}
+
+template <bool BDT>
+__global__ void __launch_bounds__(BDT ? NT_BDT : NT, 1) vq_assign_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                             const AssignTmaParams p) {
+  constexpr int NT = BDT ? vqs::NT_BDT : vqs::NT;      // threads of this instantiation (shadows the flat constant)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -252,7 +293,7 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->full[s], BDT ? PROD_WARPS * 32 : 1);
       mbar_init(&sh->empty[s], 1 + 4 + STAT_WARPS);   // score MMAs (commit) + the tile's scan group + statistics warps
     }
     for (int a = 0; a < NGROUP; ++a) {
@@ -293,7 +334,46 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
   const uint32_t tmem_base = sh->tmem_base;
   const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp == TMA_WARP) {
+  if (BDT && (warp == TMA_WARP || warp > MMA_WARP)) {
+    // ================= gather producers ((B, D, T) rows): 4-byte cp.async into the swizzled operand layout =================
+    const int pw = warp == TMA_WARP ? 0 : warp - MMA_WARP;          // 0 .. PROD_WARPS-1: owns the 16-byte chunks jc = pw + PROD_WARPS u
+    const int l7 = lane & 7, jl = lane >> 3;                        // frame within a group of 8, column within a chunk
+    const int ntc = p.TT >> 3;                                      // groups of 8 frames per tile
+    const uint32_t colT = (uint32_t)(64 * p.T);                     // elements between consecutive batch items
+    const int L = p.lag;
+    for (int it = 0; it < my_tiles + L + 1; ++it) {
+      if (it >= L + 1) {                                            // tile it-L-1 has landed: publish its stage
+        if (L == 1) cp_async_wait<1>();
+        else if (L == 2) cp_async_wait<2>();
+        else cp_async_wait<3>();
+        fence_proxy_async();
+        mbar_arrive(&sh->full[(it - L - 1) % NSTAGE]);
+      }
+      if (it < my_tiles) {
+        const int s = it % NSTAGE;
+        const BdtTile tl = bdt_tile(p, (int)blockIdx.x + it * (int)gridDim.x);
+        mbar_wait_sleep(&sh->empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
+        const uint32_t dst0 = smem_u32(xs + s * TILE_BYTES) + (uint32_t)(l7 * 128 + jl * 4);
+        // element (b, d, t) of z at ((b * 64 + d) * T + t); this lane: b = (bb0 + bi) * 64 + jc * 4 + jl, t = t0 + 8 tc + l7
+        const float* src0 = p.z + ((size_t)((tl.bb0 * 64 + jl) * 64 + tl.d) * p.T + tl.t0 + l7);
+        for (int bi = 0; bi < p.GB; ++bi) {
+          for (int tc = 0; tc < ntc; ++tc) {
+            const int row8 = (bi << p.tt_shift) + tc * 8;           // tile row of this lane = row8 + l7 (row & 7 == l7)
+            const uint32_t ok = (tl.t0 + tc * 8 + l7 < p.T) ? 4u : 0u;
+            const float* src = src0 + (size_t)((uint32_t)(bi * 64) * colT) + tc * 8;
+            const uint32_t dst = dst0 + (uint32_t)(row8 * 128);
+#pragma unroll
+            for (int u = 0; u < 16 / PROD_WARPS; ++u) {
+              const int jc = pw + PROD_WARPS * u;                        // 16-byte chunk of the row: columns 4 jc .. 4 jc + 3
+              cp_async4_zfill(dst + (uint32_t)((jc >> 3) * XT) + (uint32_t)((((jc & 7) ^ l7)) << 4),
+                              ok ? src + (size_t)((uint32_t)(jc * 4) * colT) : p.z, ok);
+            }
+          }
+        }
+      }
+      cp_async_commit();
+    }
+  } else if (!BDT && warp == TMA_WARP) {
     // ================= TMA producer =================
     if (lane == 0) {
       for (int it = 0; it < my_tiles; ++it) {
@@ -341,9 +421,18 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
     for (int it = g; it < my_tiles; it += NGROUP) {
       const int s = it % NSTAGE;
       const uint32_t ph2 = (uint32_t)(it / NGROUP) & 1u;
-      const long long r0 = (long long)(blockIdx.x + it * gridDim.x) * TR;
-      const long long left = p.N - r0;
-      const int rows = left < TR ? (int)left : TR;
+      // this thread's row: its position in idx and whether it exists
+      long long grow;
+      bool valid;
+      if (BDT) {
+        const BdtTile tl = bdt_tile(p, (int)blockIdx.x + it * (int)gridDim.x);
+        const int t = tl.t0 + (r & (p.TT - 1));
+        valid = t < p.T;
+        grow = ((long long)tl.d * p.T + t) * p.Q + tl.bb0 + (r >> p.tt_shift);
+      } else {
+        grow = (long long)(blockIdx.x + it * gridDim.x) * TR + r;
+        valid = grow < p.N;
+      }
       const uint8_t* xt = xs + s * TILE_BYTES;
       mbar_wait_sleep(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);   // acquire the TMA writes for this thread's own reads
       // |x|^2 (any order: it only scales the bounds) while the MMAs run; lanes walk the 16-byte chunks of their row in a
@@ -530,8 +619,7 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
         }
         if (lane == rr) bk = bkk < K ? bkk : K - 1;
       }
-      const bool valid = r < rows;
-      if (valid) p.idx[r0 + r] = (int64_t)bk;
+      if (valid) p.idx[grow] = (int64_t)bk;
       // ---- counts: one integer atomic per distinct code of this warp ----
       const int kk = valid ? bk : 255;
       const unsigned same = __match_any_sync(0xffffffffu, kk);
@@ -545,7 +633,7 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
         mbar_arrive(&sh->empty[s]);                     // this warp no longer reads the row tile
       }
     }
-  } else {
+  } else if (warp < TMA_WARP) {
     // ================= statistics warps: 32 rows each, private bins, ordered read-add-write =================
     const int sw = warp - SCAN_WARPS;
     const uint32_t bins_a = smem_u32(bins) + (uint32_t)((sw * K * 64 + 2 * lane) * 4);
@@ -555,10 +643,11 @@ __global__ void __launch_bounds__(NT, 1) vq_assign_tma_kernel(const __grid_const
     const uint32_t lane_c = (uint32_t)((lane & 15) >> 1);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it % NSTAGE, a = it % NIDX;
-      const long long r0 = (long long)(blockIdx.x + it * gridDim.x) * TR;
-      const long long left = p.N - r0;
-      const int rows = left < TR ? (int)left : TR;
-      const int n = rows - sw * SROWS;                 // rows of this warp that exist (may be <= 0 or > SROWS)
+      int n = SROWS;                                   // (B, D, T): rows beyond T are zero rows with a valid code
+      if (!BDT) {
+        const long long left = p.N - (long long)(blockIdx.x + it * gridDim.x) * TR;
+        n = (left < TR ? (int)left : TR) - sw * SROWS;  // rows of this warp that exist (may be <= 0 or > SROWS)
+      }
       mbar_wait_sleep(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);
       // the row values do not depend on the indices: load them while the scan warps work (rows beyond N are zeros)
       const uint32_t x_a = smem_u32(xs + s * TILE_BYTES) + lane_base;
@@ -619,52 +708,105 @@ size_t smem_bytes_tma(int K, int Kpad) {
   return b + 1024 + 64;
 }
 
+// frames x batch groups of a (B, D, T) tile: the feasible power-of-two split of 128 rows that wastes the fewest frames
+bool bdt_tile_shape(int B, int T, int* TT_out, int* GB_out) {
+  if (B % 64 != 0) return false;
+  const int Q = B / 64;
+  int best = 0;
+  long long best_cost = 0;
+  const int order[5] = {32, 64, 16, 128, 8};                        // preference on equal cost (32 x 4 is the measured shape)
+  for (int i = 0; i < 5; ++i) {
+    const int TT = order[i];
+    const int GB = TR / TT;
+    if (Q % GB != 0) continue;
+    const long long cost = (long long)((T + TT - 1) / TT) * TT;     // frames processed per batch group
+    if (cost > 2ll * T) continue;                                   // more padding than data: leave it to the other engines
+    if (best == 0 || cost < best_cost) {
+      best = TT;
+      best_cost = cost;
+    }
+  }
+  if (best == 0) return false;
+  *TT_out = best;
+  *GB_out = TR / best;
+  return true;
+}
+
 }  // namespace
 
-// flat (N, 64) rows, codebook resident in shared memory, 16-byte aligned z
-bool assign_tma_supported(int layout, int K, int D, long long N) {
-  return layout == VQS_LAYOUT_FLAT_ND && D == 64 && K >= 1 && K <= KMAX && N >= 1 && N < (1ll << 31) - TR;
+// codebook resident in shared memory, D = 64: flat (N, 64) rows (16-byte aligned z) or (B, D, T) rows with B % 64 == 0
+bool assign_tma_supported(int layout, int B, int T, int K, int D) {
+  const long long N = (long long)B * T;
+  if (D != 64 || K < 1 || K > KMAX || N < 1 || N >= (1ll << 31) - TR) return false;
+  if (layout == VQS_LAYOUT_FLAT_ND) return true;
+  int TT, GB;
+  return layout == VQS_LAYOUT_BDT_AS_DTB && bdt_tile_shape(B, T, &TT, &GB);
 }
 
 // `partials` must hold grid * K*(D+1) floats; the grid size comes back through *grid_out.
-int launch_assign_tma(const float* z, long long N, const float* cb, int K, int64_t* idx, float* partials, int max_grid,
-                      int* grid_out, cudaStream_t st) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc) {
-    set_error("vq_assign: cuTensorMapEncodeTiled is not available from the driver");
-    return VQS_ERR_ARG;
-  }
-  CUtensorMap map;
-  const cuuint64_t dims[2] = {64, (cuuint64_t)N};
-  const cuuint64_t strides[1] = {64 * sizeof(float)};
-  const cuuint32_t box[2] = {32, TR};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(z), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) {
-    set_error("vq_assign: cuTensorMapEncodeTiled failed (%d) for N=%lld", (int)cr, N);
-    return VQS_ERR_ARG;
-  }
+int launch_assign_tma(const float* z, int layout, int B, int T, const float* cb, int K, int64_t* idx, float* partials,
+                      int max_grid, int* grid_out, cudaStream_t st) {
+  const long long N = (long long)B * T;
   AssignTmaParams p;
   p.cb = cb; p.idx = idx; p.partials = partials; p.N = N; p.K = K;
   p.Kpad = (K + 15) / 16 * 16;
-  p.ntiles = (int)((N + TR - 1) / TR);
+  p.z = z; p.T = T; p.Q = B / 64; p.TT = 0; p.GB = 0; p.tt_shift = 0;
   {
     const char* dbg = getenv("VQS_TMA_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+  {
+    const char* lg = getenv("VQS_TMA_LAG");
+    p.lag = lg ? atoi(lg) : 1;
+    if (p.lag < 1) p.lag = 1;
+    if (p.lag > 3) p.lag = 3;
+  }
+  const bool bdt = layout == VQS_LAYOUT_BDT_AS_DTB;
+  CUtensorMap map;
+  if (bdt) {
+    if (!bdt_tile_shape(B, T, &p.TT, &p.GB)) {
+      set_error("vq_assign: no (B, D, T) tile shape for B=%d T=%d", B, T);
+      return VQS_ERR_ARG;
+    }
+    while ((1 << p.tt_shift) < p.TT) ++p.tt_shift;
+    const int NTB = (T + p.TT - 1) / p.TT;
+    p.divNTB = FastDiv((uint32_t)NTB);
+    p.ntiles = (B / (64 * p.GB)) * 64 * NTB;
+    memset(&map, 0, sizeof(map));                  // unused by this instantiation
+  } else {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+      set_error("vq_assign: cuTensorMapEncodeTiled is not available from the driver");
+      return VQS_ERR_ARG;
+    }
+    const cuuint64_t dims[2] = {64, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {64 * sizeof(float)};
+    const cuuint32_t box[2] = {32, TR};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(z), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("vq_assign: cuTensorMapEncodeTiled failed (%d) for N=%lld", (int)cr, N);
+      return VQS_ERR_ARG;
+    }
+    p.ntiles = (int)((N + TR - 1) / TR);
+  }
   const size_t smem = smem_bytes_tma(K, p.Kpad);
-  static size_t configured = 0;
-  if (smem > configured) {
-    VQS_CUDA(cudaFuncSetAttribute(vq_assign_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[bdt]) {
+    if (bdt)
+      VQS_CUDA(cudaFuncSetAttribute(vq_assign_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      VQS_CUDA(cudaFuncSetAttribute(vq_assign_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[bdt] = smem;
   }
   int grid = num_sms();
   if (grid > p.ntiles) grid = p.ntiles;
   if (grid > max_grid) grid = max_grid;
   *grid_out = grid;
-  vq_assign_tma_kernel<<<grid, NT, smem, st>>>(map, p);
+  if (bdt) vq_assign_tma_kernel<true><<<grid, NT_BDT, smem, st>>>(map, p);
+  else vq_assign_tma_kernel<false><<<grid, NT, smem, st>>>(map, p);
   VQS_LAUNCH_CHECK();
   return 0;
 }
