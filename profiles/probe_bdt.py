@@ -52,4 +52,13 @@ for B, T in ((32768, 128), (1 << 16, 64), (43648, 96), (8192, 47), (256, 96)):
             b.record(); torch.cuda.synchronize()
             print('BDT B=%d T=%d assign VQS_TMA_LAG=%s %.4f ms same_idx=%s' % (B, T, lag, a.elapsed_time(b) / 10, bool(torch.equal(idx, i_cc))), flush=True)
         os.environ.pop('VQS_TMA_LAG')
+        for dbg in ('0', '8'):                         # 8: sector-wise gather (4 batch items x 8 frames per request)
+            os.environ['VQS_TMA_DEBUG'] = dbg
+            for _ in range(3): ops.vq_assign(z, W, LAYOUT_BDT_AS_DTB, ws, idx=idx, stats=st)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10): ops.vq_assign(z, W, LAYOUT_BDT_AS_DTB, ws, idx=idx, stats=st)
+            b.record(); torch.cuda.synchronize()
+            print('BDT B=%d T=%d assign VQS_TMA_DEBUG=%s %.4f ms' % (B, T, dbg, a.elapsed_time(b) / 10), flush=True)
+        os.environ.pop('VQS_TMA_DEBUG')
     del z, g, q, gz

@@ -340,6 +340,9 @@ __global__ void __launch_bounds__(BDT ? NT_BDT : NT, 1) vq_assign_tma_kernel(con
     const int l7 = lane & 7, jl = lane >> 3;                        // frame within a group of 8, column within a chunk
     const int ntc = p.TT >> 3;                                      // groups of 8 frames per tile
     const uint32_t colT = (uint32_t)(64 * p.T);                     // elements between consecutive batch items
+    const uint32_t lx = (uint32_t)((l7 ^ pw) << 4);
+    const size_t stepJ = (size_t)(PROD_WARPS * 4) * colT;           // elements between this warp's consecutive chunks
+    static_assert(PROD_WARPS == 2, "the chunk arithmetic below assumes jc = pw + 2u");
     const int L = p.lag;
     for (int it = 0; it < my_tiles + L + 1; ++it) {
       if (it >= L + 1) {                                            // tile it-L-1 has landed: publish its stage
@@ -353,22 +356,45 @@ __global__ void __launch_bounds__(BDT ? NT_BDT : NT, 1) vq_assign_tma_kernel(con
         const int s = it % NSTAGE;
         const BdtTile tl = bdt_tile(p, (int)blockIdx.x + it * (int)gridDim.x);
         mbar_wait_sleep(&sh->empty[s], ((uint32_t)(it / NSTAGE) & 1u) ^ 1u);
-        const uint32_t dst0 = smem_u32(xs + s * TILE_BYTES) + (uint32_t)(l7 * 128 + jl * 4);
-        // element (b, d, t) of z at ((b * 64 + d) * T + t); this lane: b = (bb0 + bi) * 64 + jc * 4 + jl, t = t0 + 8 tc + l7
-        const float* src0 = p.z + ((size_t)((tl.bb0 * 64 + jl) * 64 + tl.d) * p.T + tl.t0 + l7);
-        for (int bi = 0; bi < p.GB; ++bi) {
-          for (int tc = 0; tc < ntc; ++tc) {
-            const int row8 = (bi << p.tt_shift) + tc * 8;           // tile row of this lane = row8 + l7 (row & 7 == l7)
-            const uint32_t ok = (tl.t0 + tc * 8 + l7 < p.T) ? 4u : 0u;
-            const float* src = src0 + (size_t)((uint32_t)(bi * 64) * colT) + tc * 8;
-            const uint32_t dst = dst0 + (uint32_t)(row8 * 128);
+        const int tlast = p.T - 1 - tl.t0;                           // last frame of the tensor, relative to the tile
+        if (p.TT >= 32 && !(p.debug & 8)) {
+          // ---- whole lines: a warp request = 32 consecutive frames of ONE batch item (one 128-byte line of HBM; the 32 rows
+          //      collide four ways on the shared-memory banks, which have cycles to spare).  Warp pw owns k-block image pw:
+          //      columns j = 32 pw + u; column u sits at byte ((u >> 2) ^ (row & 7)) << 4 | (u & 3) << 2 of its row ----
+          const uint32_t dst0 = smem_u32(xs + s * TILE_BYTES) + (uint32_t)(pw * XT + lane * 128 + ((lane & 7) << 4));
+          const float* src0 = p.z + ((size_t)((tl.bb0 * 64 + pw * 32) * 64 + tl.d) * p.T + tl.t0);
+          const int nt32 = p.TT >> 5;
+          for (int bi = 0; bi < p.GB; ++bi) {
+            const float* srcb = src0 + (size_t)((uint32_t)(bi * 64) * colT);
+            for (int tc = 0; tc < nt32; ++tc) {
+              const int tt = tc * 32 + lane;
+              const uint32_t ok = tt <= tlast ? 4u : 0u;
+              const float* src = srcb + (tt <= tlast ? tt : tlast);
+              const uint32_t dst = dst0 + (uint32_t)(((bi << p.tt_shift) + tc * 32) * 128);   // tile row = that + lane
 #pragma unroll
-            for (int u = 0; u < 16 / PROD_WARPS; ++u) {
-              const int jc = pw + PROD_WARPS * u;                        // 16-byte chunk of the row: columns 4 jc .. 4 jc + 3
-              cp_async4_zfill(dst + (uint32_t)((jc >> 3) * XT) + (uint32_t)((((jc & 7) ^ l7)) << 4),
-                              ok ? src + (size_t)((uint32_t)(jc * 4) * colT) : p.z, ok);
+              for (int u = 0; u < 32; ++u)
+                cp_async4_zfill((dst ^ (uint32_t)((u >> 2) << 4)) + (uint32_t)((u & 3) << 2), src + (size_t)u * colT, ok);
             }
           }
+        } else {
+        // The producers share their schedulers with the scan warps (the kernel is issue-bound), so the inner loop is kept
+        // to ~3 instructions per copy: chunk jc = pw + 2u sits at byte ((jc & 7) ^ l7) << 4 = lx ^ ((u & 3) << 5) of its row
+        // with lx = (l7 ^ pw) << 4 (disjoint bits), its k-block image is u >> 2, and consecutive u lie 8 batch items apart.
+        const uint32_t dst0 = smem_u32(xs + s * TILE_BYTES) + (uint32_t)(l7 * 128 + jl * 4) + lx;
+        // element (b, d, t) of z at ((b * 64 + d) * T + t); this lane: b = (bb0 + bi) * 64 + jc * 4 + jl, t = t0 + 8 tc + l7
+        const float* src0 = p.z + ((size_t)((tl.bb0 * 64 + pw * 4 + jl) * 64 + tl.d) * p.T + tl.t0);
+        for (int bi = 0; bi < p.GB; ++bi) {
+          const float* srcb = src0 + (size_t)((uint32_t)(bi * 64) * colT);
+          for (int tc = 0; tc < ntc; ++tc) {
+            const int tt = tc * 8 + l7;
+            const uint32_t ok = tt <= tlast ? 4u : 0u;               // frames beyond T: zero rows (address clamped, 0 bytes read)
+            const float* src = srcb + (tt <= tlast ? tt : tlast);
+            const uint32_t dst = dst0 + (uint32_t)(((bi << p.tt_shift) + tc * 8) * 128);   // tile row = that + l7
+#pragma unroll
+            for (int u = 0; u < 16 / PROD_WARPS; ++u)
+              cp_async4_zfill((dst ^ (uint32_t)((u & 3) << 5)) + (uint32_t)((u >> 2) * XT), src + (size_t)u * stepJ, ok);
+          }
+        }
         }
       }
       cp_async_commit();
