@@ -13,16 +13,18 @@ fs = [('assign', lambda: ops.vq_assign(z, W, LAYOUT_FLAT_ND, ws, idx=idx, stats=
       ('ema', lambda: ops.vq_ema_update(cs, ew, W, st, 0.99, 1e-5)),
       ('quantize', lambda: ops.vq_quantize(z, idx, W, LAYOUT_FLAT_ND, ws, st[:K], N, 0.25, out=q, scalars=sc)),
       ('backward', lambda: ops.vq_backward(g, one, 2 * 0.25 / (N * D), z, idx, W, LAYOUT_FLAT_ND, out=gz))]
-for _ in range(3):
-    for n, f in fs: f()
-torch.cuda.synchronize()
-acc = dict((n, 0.0) for n, _ in fs); iters = 20; evs = []
-t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True); t0.record()
-for _ in range(iters):
-    for n, f in fs:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); f(); b.record(); evs.append((n, a, b))
-t1.record(); torch.cuda.synchronize()
-for n, a, b in evs: acc[n] += a.elapsed_time(b) / iters
-tot = t0.elapsed_time(t1) / iters
-print('FUSED %s  total %.4f ms  %.3f G rows/s  %.1f %% of 6536 GB/s' % (' '.join('%s %.4f' % (n, acc[n]) for n, _ in fs), tot, N / tot / 1e6, 1296 * N / tot / 1e6 / 6536.4 * 100))
+for mode in ('0', '1', '2'):       # VQS_EW_FLAT_TILE: 0 grid-stride kernels, 1 tiled forward, 2 tiled forward + backward (default)
+    os.environ['VQS_EW_FLAT_TILE'] = mode
+    for _ in range(3):
+        for n, f in fs: f()
+    torch.cuda.synchronize()
+    acc = dict((n, 0.0) for n, _ in fs); iters = 20; evs = []
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True); t0.record()
+    for _ in range(iters):
+        for n, f in fs:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); f(); b.record(); evs.append((n, a, b))
+    t1.record(); torch.cuda.synchronize()
+    for n, a, b in evs: acc[n] += a.elapsed_time(b) / iters
+    tot = t0.elapsed_time(t1) / iters
+    print('FUSED flat_tile=%s %s  total %.4f ms  %.3f G rows/s  %.1f %% of 6536 GB/s' % (mode, ' '.join('%s %.4f' % (n, acc[n]) for n, _ in fs), tot, N / tot / 1e6, 1296 * N / tot / 1e6 / 6536.4 * 100))

@@ -135,6 +135,8 @@ SWEEP = [  # (K, D, B, T, layout-name)  sizes the oracle finishes in seconds
     (44, 64, 260, 20, 'bdt'), (29, 64, 300, 12, 'bdt'), (10, 2, 64, 8, 'bdt'),
     # D = 64, B % 64 == 0, B >= 256: the tiled element-wise kernels (indices staged in shared memory); partial frame block
     (44, 64, 320, 40, 'bdt'), (29, 64, 256, 8, 'bdt'),
+    # flat rows, N >= 4096: tiled forward element-wise kernel, partial last tile
+    (44, 64, 1, 5000, 'flat'), (29, 64, 1, 4100, 'flat'),
 ]
 
 
@@ -381,6 +383,51 @@ def test_vq_streaming_engine_fuzz_matches_cuda_core_engine():
             assert torch.equal(i_tc, i_t2) and torch.equal(s_tc, s_t2), tag + ': not deterministic'
     finally:
         ops.vq_set_engine('auto')
+
+
+def test_elementwise_kernel_variants_agree_bitwise():
+    """The tiled / blocked element-wise kernels (staged indices) compute exactly what the grid-stride kernels compute:
+    quantised output and grad_z bit-identical, the loss (a differently ordered sum) within 1e-6."""
+    import os
+    dev = _dev()
+    from vq_vae_speech_b200 import ops, LAYOUT_BDT_AS_DTB, LAYOUT_FLAT_ND
+    gen = torch.Generator(device=dev).manual_seed(3)
+    K, D = 44, 64
+    W = torch.randn(K, D, device=dev, generator=gen)
+    ws = ops.vq_workspace(K, D, dev)
+    one = torch.ones(1, device=dev)
+    envs = ('VQS_EW_FLAT_TILE', 'VQS_EW_NO_TILE', 'VQS_EW_NO_BLK')
+    saved = dict((k, os.environ.get(k)) for k in envs)
+
+    def run(z, layout, env):
+        for k in envs:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        idx, stats = ops.vq_assign(z, W, layout, ws)
+        N = idx.numel()
+        out, sc = ops.vq_quantize(z, idx, W, layout, ws, stats[:K], N, 0.25)
+        g = torch.randn(z.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+        gz = ops.vq_backward(g, one, 2 * 0.25 / (N * D), z, idx, W, layout)
+        return out.clone(), sc[:5].clone(), gz.clone()       # slots 5-7 of the scalar block are unused
+
+    try:
+        z = torch.randn(9001, D, device=dev, generator=gen)
+        ref = run(z, LAYOUT_FLAT_ND, {'VQS_EW_FLAT_TILE': '0'})
+        for mode in ('1', '2'):
+            got = run(z, LAYOUT_FLAT_ND, {'VQS_EW_FLAT_TILE': mode})
+            assert torch.equal(got[0], ref[0]) and torch.equal(got[2], ref[2])
+            assert rel_err(got[1].cpu().numpy(), ref[1].cpu().numpy()) < 1e-6
+        z = torch.randn(320, D, 44, device=dev, generator=gen)
+        ref = run(z, LAYOUT_BDT_AS_DTB, {'VQS_EW_NO_TILE': '1', 'VQS_EW_NO_BLK': '1'})
+        for env in ({}, {'VQS_EW_NO_TILE': '1'}):
+            got = run(z, LAYOUT_BDT_AS_DTB, env)
+            assert torch.equal(got[0], ref[0]) and torch.equal(got[2], ref[2])
+            assert rel_err(got[1].cpu().numpy(), ref[1].cpu().numpy()) < 1e-6
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
 
 
 def test_vq_streaming_engine_bdt_fuzz_matches_cuda_core_engine():

@@ -655,6 +655,72 @@ __global__ void __launch_bounds__(256) vq_elementwise_bdt_tile_kernel(const EwPa
   }
 }
 
+// Flat (N, 64) rows, the same idea: CTA tile = 16 * RPT consecutive rows (RPT float4 per thread, a warp = two whole rows),
+// the tile's indices arrive as one coalesced load and are staged in shared memory, all loads of a tile are in flight before
+// the barrier.  Same arithmetic as vq_elementwise_kernel.
+template <bool BWD, int RPT>
+__global__ void __launch_bounds__(256) vq_elementwise_flat_tile_kernel(const EwParams p, const long long N, const int ntiles) {
+  extern __shared__ __align__(16) float cbs[];
+  __shared__ double wred[8];
+  __shared__ int sidx[2][16 * RPT];
+  constexpr int D = 64, Dp = D + 4;
+  for (int i = threadIdx.x; i < p.K * D; i += 256) cbs[(i >> 6) * Dp + (i & 63)] = __ldg(p.cb + i);
+  const int c4 = threadIdx.x & 15, rq = threadIdx.x >> 4;
+  float c = 0.f;
+  if (BWD) c = p.gl[0] * p.coef;
+  float sse = 0.f;
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const long long r0 = (long long)tile * (16 * RPT);
+    int kreg = 0;
+    if (threadIdx.x < 16 * RPT && r0 + threadIdx.x < N) kreg = (int)__ldg(p.idx + r0 + threadIdx.x);
+    float4 xv[RPT], gv[BWD ? RPT : 1];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const long long r = r0 + rq + 16 * i;
+      if (r < N) {
+        xv[i] = ldg_stream4(p.z + r * D + c4 * 4);
+        if (BWD) gv[i] = ldg_stream4(p.g + r * D + c4 * 4);
+      }
+    }
+    if (threadIdx.x < 16 * RPT) sidx[buf][threadIdx.x] = kreg;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const long long r = r0 + rq + 16 * i;
+      if (r < N) {
+        const float4 qv = *reinterpret_cast<const float4*>(&cbs[sidx[buf][rq + 16 * i] * Dp + c4 * 4]);
+        const float q[4] = {qv.x, qv.y, qv.z, qv.w};
+        const float x[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+        float o[4];
+        if (BWD) {
+          const float g[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = fmaf(c, __fsub_rn(x[e], q[e]), g[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float df = __fsub_rn(q[e], x[e]);
+            o[e] = __fadd_rn(x[e], df);                      // inputs + (quantized - inputs).detach()  (ema.py:169)
+            sse = fmaf(df, df, sse);
+          }
+        }
+        stg_stream4(p.out + r * D + c4 * 4, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+  }
+  if (!BWD) {
+    double sd = warp_sum((double)sse);
+    if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = sd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0;
+      for (int w = 0; w < 8; ++w) a += wred[w];
+      p.sse_partials[blockIdx.x] = a;
+    }
+  }
+}
+
 __global__ void gather_rows_kernel(const int64_t* __restrict__ idx, const float* __restrict__ cb, long long N, int D,
                                    float* __restrict__ out) {
   long long total = N * D;
@@ -939,6 +1005,32 @@ static int launch_elementwise(bool bwd, EwParams& p, size_t cb_bytes, int& grid_
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   // float4 path: 4 consecutive floats never leave a row (flat) or a (b, d) run (B, D, T)
   const bool vec = al16(p.z) && al16(p.out) && (!bwd || al16(p.g)) && (flat ? (p.D % 4 == 0) : (p.T % 4 == 0));
+  // flat (N, 64) rows: tiled kernels with staged indices (measured at 2^22 rows: forward 0.420 -> 0.350 ms = the HBM
+  // roofline, backward 0.526 -> 0.503 ms).  VQS_EW_FLAT_TILE = 0 / 1 selects the grid-stride kernels for both / backward.
+  {
+    const char* ft = getenv("VQS_EW_FLAT_TILE");
+    const int mode = ft ? atoi(ft) : 2;
+    const long long N = p.total / 64;
+    if (flat && vec && p.D == 64 && N >= 4096 && (size_t)p.K * 68 * sizeof(float) <= 96 * 1024 &&
+        (bwd ? mode >= 2 : mode >= 1)) {
+      const int RPT = bwd ? 4 : 8;
+      const long long nt = (N + 16 * RPT - 1) / (16 * RPT);
+      int grid = (int)(nt < EW_MAX_BLOCKS ? nt : EW_MAX_BLOCKS);
+      grid_out = grid;
+      const size_t smem = (size_t)p.K * 68 * sizeof(float);
+      if (bwd) {
+        auto kern = vq_elementwise_flat_tile_kernel<true, 4>;
+        if (smem > 48 * 1024) VQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, st>>>(p, N, (int)nt);
+      } else {
+        auto kern = vq_elementwise_flat_tile_kernel<false, 8>;
+        if (smem > 48 * 1024) VQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, st>>>(p, N, (int)nt);
+      }
+      VQS_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   // (B, 64, T) with whole 64-item batch groups: the tiled kernel (indices staged in shared memory, full-line accesses)
   if (!flat && vec && p.D == 64 && p.B % 64 == 0 && p.B >= 256 && (size_t)p.K * 65 * sizeof(float) <= 96 * 1024 &&
       getenv("VQS_EW_NO_TILE") == nullptr) {
