@@ -260,8 +260,9 @@ def vq_bench(dev, pk, rows, K=44, D=64, iters=20):
     out['peak_source'] = pk['src']
     out['bytes_per_row'] = 20 * D + 16
     out['K'], out['D'] = K, D
-    out['search_engine'] = ('auto: flat rows -> streaming engine (TMA tiles as raw tf32 tcgen05 operands + exact fp32 '
-                            'settlement, identical indices); (B,D,T) rows -> CUDA cores (exact fp32 FMA)')
+    out['search_engine'] = ('auto: streaming engine (row tiles as raw tf32 tcgen05 operands + exact fp32 settlement, '
+                            'identical indices): flat rows arrive by TMA, (B,D,T) rows (B % 64 == 0) by a cp.async gather '
+                            'into the same swizzled layout; element-wise kernels tiled with indices staged in smem')
     return out
 
 
