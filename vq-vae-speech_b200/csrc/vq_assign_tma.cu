@@ -15,6 +15,14 @@
 //     statistics warps owns 32 rows of every tile and a PRIVATE copy of the bins in shared memory (lane = column pair),
 //     so its read-add-write sequences are ordered and the final sum over warps / CTAs is fixed -> deterministic.  Counts
 //     are integers (match.any + one shared-memory atomic per distinct code and warp).
+// What the statistics pass costs and what did not make it cheaper (phase probe profiles/probe_tma_phases.py, 2^22 rows:
+// 0.393 ms complete, 0.316 ms without statistics, 0.329 ms without the settlement, 0.188 ms with neither = the HBM floor):
+//   * sums in REGISTERS of code-owning warps (warp sw owns k = sw mod 4, lane = column pair, rows prefetched one ahead):
+//     correct, but selecting the accumulator costs an indirect branch per row (LDC + BRX + reconvergence): 1.27 - 1.87 ms;
+//   * NO dedicated statistics warps (four groups of four warps scan a tile, exchange indices through a named barrier, and
+//     warp q of the group adds the rows of the codes k = q mod 4 into per-group bins): correct, 0.305 ms without and
+//     0.491 ms with statistics -- the read-add-write chains then sit on the critical path of every group.
+// Both are in the history (round-1 commits "register-resident statistics" / "fused statistics"), neither is built.
 // Warp roles (576 threads, one persistent CTA per SM): warps 0-11 scan (three groups taking tiles round-robin, TMEM lane
 // quarter = warp % 4), warps 12-15 statistics, warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer.
 //
@@ -56,20 +64,11 @@ namespace {
 constexpr int TR = 128;                  // rows per tile
 constexpr int XT = TR * 128;             // bytes of one k-block image (32 columns)
 constexpr int TILE_BYTES = 2 * XT;       // 32 KB
-// Statistics engine.  0 (default): each statistics warp owns 32 rows of a tile and a private copy of all bins in shared
-// memory (ordered LDS -> FADD -> STS chains; the phase probe of profiles/r01x prices the pass at 0.08 ms of 0.39 ms at 2^22
-// rows).  1 (-DVQS_STATS_REG=1, kept as a measured negative result): every statistics warp OWNS the codes k = sw (mod 4)
-// and keeps their sums in registers (lane = column pair, 12 codes x 2 columns), walking the rows of the whole tile that
-// chose one of its codes with the values prefetched one row ahead.  Same results (98 GPU tests green), but selecting the
-// accumulator needs an indirect branch per row (LDC + BRX + reconvergence): 1.27 - 1.87 ms instead of 0.39 ms.
-#ifndef VQS_STATS_REG
-#define VQS_STATS_REG 0
-#endif
-constexpr int NSTAGE = VQS_STATS_REG ? 6 : 5;   // the bins' 45 KB pay for a sixth stage
+constexpr int NSTAGE = 5;
 constexpr int NGROUP = 3;                // scan groups (4 warps each) taking tiles round-robin, one TMEM accumulator each
 constexpr int SCAN_WARPS = 4 * NGROUP, STAT_WARPS = 4;
 constexpr int NIDX = 4;                  // index buffers between the scan and the statistics warps
-[[maybe_unused]] constexpr int SROWS = TR / STAT_WARPS;   // rows of a tile per statistics warp (VQS_STATS_REG = 0)
+constexpr int SROWS = TR / STAT_WARPS;   // rows of a tile per statistics warp
 constexpr int TMA_WARP = SCAN_WARPS + STAT_WARPS, MMA_WARP = TMA_WARP + 1;
 constexpr int NT = (MMA_WARP + 1) * 32;
 // (B, D, T) instantiation: warp TMA_WARP and one more behind the MMA warp.  19 warps = at most 5 per SM sub-partition keeps
@@ -179,7 +178,6 @@ __device__ __forceinline__ void settle_chunk(uint32_t xa, uint32_t pc4, uint32_t
   }
 }
 
-#if !VQS_STATS_REG
 // 16 rows of a statistics warp (H = 0: rows 0-15, 1: rows 16-31): this lane's column pair of every row
 template <int H>
 __device__ __forceinline__ void stats_load_half(const uint32_t (&xrow)[8], float2 (&v)[16]) {
@@ -243,8 +241,6 @@ __device__ __forceinline__ void stats_rmw_half(uint32_t sidx_a, uint32_t bins_a,
   }
 }
 
-#endif
-
 // byte offset of element (row r, column j) of a 64-column tile stored as two k-block images of `rows` x 128 B
 __device__ __forceinline__ uint32_t elem_off64(int r, int j, int rows) {
   return (uint32_t)((j >> 5) * rows * 128) + sw128_off(r, j & 31);
@@ -295,12 +291,8 @@ __global__ void __launch_bounds__(BDT ? NT_BDT : NT, 1) vq_assign_tma_kernel(con
   const int K = p.K, Kpad = p.Kpad;
   uint8_t* xs = smem;                                               // [NSTAGE][2 k-blocks][128 rows][128 B], raw fp32
   uint8_t* cbs = xs + NSTAGE * TILE_BYTES;                          // [2 k-blocks][Kpad codes][128 B], raw fp32
-#if VQS_STATS_REG
-  float* se = reinterpret_cast<float*>(cbs + 2 * Kpad * 128);       // [KMAX]  |e_k|^2
-#else
   float* bins = reinterpret_cast<float*>(cbs + 2 * Kpad * 128);     // [STAT_WARPS][K][64] private dw bins
   float* se = bins + STAT_WARPS * K * 64;                           // [KMAX]  |e_k|^2
-#endif
   float* sea = se + KMAX;                                           // [KMAX]  |e_k|^2 (1 - EPSB), BIG beyond K
   float* sqa = sea + KMAX;                                          // [KMAX]  EPSA |e_k|
   int* cnt_s = reinterpret_cast<int*>(sqa + KMAX);                  // [KMAX]  this CTA's counts
@@ -330,9 +322,7 @@ __global__ void __launch_bounds__(BDT ? NT_BDT : NT, 1) vq_assign_tma_kernel(con
     const float v = (k < K) ? __ldg(p.cb + (size_t)k * 64 + j) : 0.f;
     *reinterpret_cast<float*>(cbs + elem_off64(k, j, Kpad)) = v;
   }
-#if !VQS_STATS_REG
   for (int e = tid; e < STAT_WARPS * K * 64; e += NT) bins[e] = 0.f;
-#endif
   for (int k = tid; k < KMAX; k += NT) {
     float s = 0.f;
     if (k < K)
@@ -678,78 +668,6 @@ __global__ void __launch_bounds__(BDT ? NT_BDT : NT, 1) vq_assign_tma_kernel(con
       }
     }
   } else if (warp < TMA_WARP) {
-#if VQS_STATS_REG
-    // ================= statistics warps: codes k = sw (mod 4) in registers, rows of the whole tile in row order =================
-    const int sw = warp - SCAN_WARPS;
-    const uint32_t sidx_a = smem_u32(sidx);
-    // this lane's column pair (2 lane, 2 lane + 1): k-block image, byte inside the 16-byte chunk; logical chunk index
-    const uint32_t lane_base = (uint32_t)((lane >> 4) * XT + ((lane & 1) << 3));
-    const uint32_t lane_c = (uint32_t)((lane & 15) >> 1);
-    float2 acc[12];                                    // sums of codes 4 c + sw, this lane's column pair
-#pragma unroll
-    for (int c = 0; c < 12; ++c) acc[c] = make_float2(0.f, 0.f);
-    for (int it = 0; it < my_tiles; ++it) {
-      const int s = it % NSTAGE, a = it % NIDX;
-      mbar_wait_sleep(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);
-      mbar_wait_sleep(&sh->idx_ready[a], (uint32_t)(it / NIDX) & 1u);
-      const uint32_t x_a = smem_u32(xs + s * TILE_BYTES) + lane_base;
-      const uint32_t sidx_t = sidx_a + (uint32_t)((a * TR + lane) * 4);
-      if (!(p.debug & 1)) {
-        int code[4];                                   // codes of rows lane, lane + 32, lane + 64, lane + 96
-#pragma unroll
-        for (int g = 0; g < 4; ++g) code[g] = lds_s32(sidx_t + (uint32_t)(g * 128)) >> 8;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          unsigned m = __ballot_sync(0xffffffffu, (code[g] & 3) == sw);     // rows beyond N are zero rows: harmless
-          if (m == 0u) continue;
-          int r = __ffs(m) - 1;
-          m &= m - 1;
-          int R = g * 32 + r;
-          float2 xc = lds_v2(x_a + (uint32_t)(R * 128) + ((lane_c ^ (uint32_t)(R & 7)) << 4));
-          int cc = __shfl_sync(0xffffffffu, code[g], r) >> 2;
-          for (;;) {
-            float2 xn = xc;
-            int cn = cc;
-            const bool more = m != 0u;                 // warp-uniform
-            if (more) {                                // prefetch the next row of this warp
-              r = __ffs(m) - 1;
-              m &= m - 1;
-              R = g * 32 + r;
-              xn = lds_v2(x_a + (uint32_t)(R * 128) + ((lane_c ^ (uint32_t)(R & 7)) << 4));
-              cn = __shfl_sync(0xffffffffu, code[g], r) >> 2;
-            }
-            switch (cc) {
-#define VQS_ACC(C) case C: acc[C].x += xc.x; acc[C].y += xc.y; break;
-              VQS_ACC(0) VQS_ACC(1) VQS_ACC(2) VQS_ACC(3) VQS_ACC(4) VQS_ACC(5)
-              VQS_ACC(6) VQS_ACC(7) VQS_ACC(8) VQS_ACC(9) VQS_ACC(10) VQS_ACC(11)
-#undef VQS_ACC
-              default: break;
-            }
-            if (!more) break;
-            xc = xn;
-            cc = cn;
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&sh->empty[s]);                    // the row tile and its indices can be overwritten
-        mbar_arrive(&sh->idx_free[a]);
-      }
-    }
-    // publish this warp's codes (fixed summation order: rows ascending within a tile, tiles in this CTA's order)
-    {
-      float* out = p.partials + (size_t)blockIdx.x * K * 65 + K;
-#pragma unroll
-      for (int c = 0; c < 12; ++c) {
-        const int k = 4 * c + sw;
-        if (k < K) {                                   // (K * 65 * blockIdx + K may be odd: no 8-byte stores)
-          out[k * 64 + 2 * lane] = acc[c].x;
-          out[k * 64 + 2 * lane + 1] = acc[c].y;
-        }
-      }
-    }
-#else
     // ================= statistics warps: 32 rows each, private bins, ordered read-add-write =================
     const int sw = warp - SCAN_WARPS;
     const uint32_t bins_a = smem_u32(bins) + (uint32_t)((sw * K * 64 + 2 * lane) * 4);
@@ -782,7 +700,6 @@ __global__ void __launch_bounds__(BDT ? NT_BDT : NT, 1) vq_assign_tma_kernel(con
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->idx_free[a]);
     }
-  #endif
   }
   tc_fence_before();
   __syncthreads();
@@ -790,14 +707,12 @@ __global__ void __launch_bounds__(BDT ? NT_BDT : NT, 1) vq_assign_tma_kernel(con
   {
     float* out = p.partials + (size_t)blockIdx.x * K * 65;
     for (int i = tid; i < K; i += NT) out[i] = (float)cnt_s[i];
-#if !VQS_STATS_REG
     for (int i = tid; i < K * 64; i += NT) {
       float a = 0.f;
 #pragma unroll
       for (int w = 0; w < STAT_WARPS; ++w) a += bins[w * K * 64 + i];
       out[K + i] = a;
     }
-#endif
   }
   if (warp == MMA_WARP) {
     tc_fence_after();
@@ -822,7 +737,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 size_t smem_bytes_tma(int K, int Kpad) {
-  size_t b = (size_t)NSTAGE * TILE_BYTES + (size_t)2 * Kpad * 128 + (VQS_STATS_REG ? 0 : (size_t)STAT_WARPS * K * 64 * 4);
+  size_t b = (size_t)NSTAGE * TILE_BYTES + (size_t)2 * Kpad * 128 + (size_t)STAT_WARPS * K * 64 * 4;
   b += (size_t)(4 * KMAX) * 4 + (size_t)(NIDX * TR) * 4 + sizeof(Sh);
   return b + 1024 + 64;
 }
