@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_gemm_kernel(const WgradParams 
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, long long n, float* __restrict__ out,
                                      int accumulate) {
+  pdl_prologue_done();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float a = accumulate ? out[i] : 0.f;
     for (int s = 0; s < S; ++s) a += partial[(size_t)s * n + i];
@@ -384,6 +385,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
                                                         float* __restrict__ db, int accumulate) {
   // one block per channel m; fixed-order tree reduction -> deterministic
   __shared__ float red[256];
+  pdl_prologue_done();
   const int m = blockIdx.x;
   float s = 0.f;
   const int per = B * L;
@@ -598,8 +600,8 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
   if (pl.splits > 1) {
     long long n = (long long)d->M * p.Nw;
     long long blocks = (n + 255) / 256;
-    splitk_reduce_kernel<<<(int)(blocks < 8 * num_sms() ? blocks : 8 * num_sms()), 256, 0, st>>>(
-        p.partial, pl.splits, n, d->dW, d->accumulate);
+    VQS_CUDA(launch_pdl(splitk_reduce_kernel, dim3((unsigned)(blocks < 8 * num_sms() ? blocks : 8 * num_sms())), dim3(256), 0,
+                        st, p.partial, pl.splits, n, d->dW, d->accumulate));
     VQS_LAUNCH_CHECK();
   }
   return 0;
@@ -607,7 +609,7 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
 
 extern "C" int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int accumulate, vqs_stream_t stream) {
   VQS_CHECK_ARG(g && db && B > 0 && M > 0 && L > 0, "vqs_bias_grad: bad arguments");
-  bias_grad_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(g, B, M, L, db, accumulate);
+  VQS_CUDA(launch_pdl(bias_grad_kernel, dim3(M), dim3(256), 0, (cudaStream_t)stream, g, B, M, L, db, accumulate));
   VQS_LAUNCH_CHECK();
   return 0;
 }

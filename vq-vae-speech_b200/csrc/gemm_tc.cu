@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+  pdl_prologue_done();
 
   if (warp < N_PROD_WARPS) {
     // ================= producers =================
@@ -523,7 +524,7 @@ int launch_tc_t(const TcParams<MODE>& prm, dim3 grid, cudaStream_t st) {
     VQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(prm);
+  VQS_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, prm));
   VQS_LAUNCH_CHECK();
   return 0;
 }
@@ -562,6 +563,7 @@ bool wgrad_tc_supported(const WgradParams& p) { return p.d.ksz >= 1 && p.d.ksz <
 // (vqs_b200.h: bias, add_pre (+relu), relu, mask_out, mask, add_post, out, out2 / mask2), coalesced along l.
 __global__ void __launch_bounds__(256) conv_splitk_epilogue_kernel(const float* __restrict__ partial, int splits,
                                                                    int Ntot, const vqs_conv_gemm_desc d) {
+  pdl_prologue_done();
   const long long total = (long long)d.M * Ntot;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int m = (int)(i / Ntot), n = (int)(i - (long long)m * Ntot);
@@ -628,8 +630,8 @@ int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
   if (prm.p.partial != nullptr) {
     const long long total = (long long)d.M * p.Ntot;
     const long long blocks = (total + 255) / 256;
-    conv_splitk_epilogue_kernel<<<(int)(blocks < 8 * sms ? blocks : 8 * sms), 256, 0, st>>>(prm.p.partial, prm.p.splits,
-                                                                                            p.Ntot, d);
+    VQS_CUDA(launch_pdl(conv_splitk_epilogue_kernel, dim3((unsigned)(blocks < 8 * sms ? blocks : 8 * sms)), dim3(256), 0, st,
+                        prm.p.partial, prm.p.splits, p.Ntot, d));
     VQS_LAUNCH_CHECK();
   }
   return 0;

@@ -5,6 +5,8 @@
 
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "vqs_common.cuh"
 
 namespace vqs {
@@ -19,6 +21,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("VQS_PDL");
+    cached = (e != nullptr && atoi(e) == 0) ? 0 : 1;   // on by default; VQS_PDL=0 restores plain stream order
+  }
+  return cached == 1;
+}
 
 int num_sms() {
   static int cached = 0;

@@ -43,6 +43,35 @@ int num_sms();
     vqs::count_launch();                                                                 \
   } while (0)
 
+// Programmatic dependent launch (on by default, VQS_PDL=0 disables; read once): the kernels of the GEMM family call pdl_prologue_done() after a
+// prologue that touches no global memory (barrier init, TMEM allocation), and are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so that prologue and launch latency overlap the tail of the kernel
+// before.  Without the attribute griddepcontrol.wait returns at once.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+// every global-memory access of the kernel comes after this; the next kernel of the stream may be scheduled from here on
+__device__ __forceinline__ void pdl_prologue_done() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+
 // unsigned division by a runtime constant, exact for n < 2^31:
 //   l = ceil(log2 d), s = l - 1, m = ceil(2^(32+s) / d) (< 2^32), n / d == umulhi(n, m) >> s
 struct FastDiv {

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tma_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
   const uint32_t smem_a = smem_u32(smem);
+  pdl_prologue_done();
 
   if (warp == WT_TMA_WARP) {
     // ================= TMA producer =================
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tma_kernel(const __grid_c
 __global__ void __launch_bounds__(256) wgrad_tma_reduce_kernel(const float* __restrict__ partial, int splits, int M,
                                                                int Cred, int ksz, int tiles_m, int tiles_n,
                                                                float* __restrict__ dW, int accumulate) {
+  pdl_prologue_done();
   const long long total = (long long)M * Cred * ksz;
   const int cpt = Cred / 128;
   const size_t split_stride = (size_t)tiles_m * tiles_n * 16384;
@@ -310,12 +312,12 @@ int launch_wgrad_tma(const WgradParams& p, float* workspace, cudaStream_t st) {
   }
   const int tiles_n = d.ksz * q.cpt, tiles_m = d.M / 128;
   dim3 grid(tiles_n, tiles_m, p.splits);
-  wgrad_tma_kernel<<<grid, WT_THREADS, WT_SMEM, st>>>(mapA, mapB, q);
+  VQS_CUDA(launch_pdl(wgrad_tma_kernel, grid, dim3(WT_THREADS), WT_SMEM, st, mapA, mapB, q));
   VQS_LAUNCH_CHECK();
   const long long n = (long long)d.M * p.Nw;
   const long long blocks = (n + 255) / 256;
-  wgrad_tma_reduce_kernel<<<(int)(blocks < 8 * num_sms() ? blocks : 8 * num_sms()), 256, 0, st>>>(
-      workspace, p.splits, d.M, d.Cred, d.ksz, tiles_m, tiles_n, d.dW, d.accumulate);
+  VQS_CUDA(launch_pdl(wgrad_tma_reduce_kernel, dim3((unsigned)(blocks < 8 * num_sms() ? blocks : 8 * num_sms())), dim3(256), 0,
+                      st, workspace, p.splits, d.M, d.Cred, d.ksz, tiles_m, tiles_n, d.dW, d.accumulate));
   VQS_LAUNCH_CHECK();
   return 0;
 }
