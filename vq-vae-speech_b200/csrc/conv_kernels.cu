@@ -323,6 +323,20 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, l
   }
 }
 
+// four elements per thread (n % 4 == 0, 16-byte aligned buffers): same summation order per element
+__global__ void splitk_reduce4_kernel(const float4* __restrict__ partial, int S, long long n4, float4* __restrict__ out,
+                                      int accumulate) {
+  pdl_prologue_done();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = accumulate ? out[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < S; ++s) {
+      const float4 v = partial[(size_t)s * n4 + i];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    out[i] = a;
+  }
+}
+
 template <int BM, int BN>
 int launch_wgrad(const WgradParams& p, cudaStream_t st) {
   dim3 grid((p.Nw + BN - 1) / BN, (p.d.M + BM - 1) / BM, p.splits);
@@ -382,16 +396,28 @@ WgradPlan plan_wgrad(int M, int Nw, int Kred, int bk = BK, bool tc = false) {
 }
 
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ g, int B, int M, int L,
-                                                        float* __restrict__ db, int accumulate) {
+                                                        float* __restrict__ db, int accumulate, const FastDiv divL,
+                                                        const int vec4) {   // divL: L / 4 (vec4) or L
   // one block per channel m; fixed-order tree reduction -> deterministic
   __shared__ float red[256];
   pdl_prologue_done();
   const int m = blockIdx.x;
   float s = 0.f;
-  const int per = B * L;
-  for (int i = threadIdx.x; i < per; i += 256) {
-    int b = i / L, l = i - b * L;
-    s += g[((size_t)b * M + m) * L + l];
+  if (vec4) {                                  // L % 4 == 0, 16-byte aligned g: whole 16-byte pieces of the (b, m) runs
+    const uint32_t per4 = (uint32_t)B * divL.d;
+    for (uint32_t i = threadIdx.x; i < per4; i += 256) {
+      uint32_t b, l4;
+      divL.divmod(i, b, l4);
+      const float4 v = *reinterpret_cast<const float4*>(g + ((size_t)b * M + m) * L + (size_t)l4 * 4);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    const uint32_t per = (uint32_t)B * L;
+    for (uint32_t i = threadIdx.x; i < per; i += 256) {
+      uint32_t b, l;
+      divL.divmod(i, b, l);
+      s += g[((size_t)b * M + m) * L + l];
+    }
   }
   red[threadIdx.x] = s;
   __syncthreads();
@@ -600,8 +626,15 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
   if (pl.splits > 1) {
     long long n = (long long)d->M * p.Nw;
     long long blocks = (n + 255) / 256;
-    VQS_CUDA(launch_pdl(splitk_reduce_kernel, dim3((unsigned)(blocks < 8 * num_sms() ? blocks : 8 * num_sms())), dim3(256), 0,
-                        st, p.partial, pl.splits, n, d->dW, d->accumulate));
+    if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(p.partial) | reinterpret_cast<uintptr_t>(d->dW)) & 15) == 0) {
+      const long long b4 = (n / 4 + 255) / 256;
+      VQS_CUDA(launch_pdl(splitk_reduce4_kernel, dim3((unsigned)(b4 < 8 * num_sms() ? b4 : 8 * num_sms())), dim3(256), 0, st,
+                          reinterpret_cast<const float4*>(p.partial), pl.splits, n / 4, reinterpret_cast<float4*>(d->dW),
+                          d->accumulate));
+    } else {
+      VQS_CUDA(launch_pdl(splitk_reduce_kernel, dim3((unsigned)(blocks < 8 * num_sms() ? blocks : 8 * num_sms())), dim3(256), 0,
+                          st, p.partial, pl.splits, n, d->dW, d->accumulate));
+    }
     VQS_LAUNCH_CHECK();
   }
   return 0;
@@ -609,7 +642,10 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
 
 extern "C" int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int accumulate, vqs_stream_t stream) {
   VQS_CHECK_ARG(g && db && B > 0 && M > 0 && L > 0, "vqs_bias_grad: bad arguments");
-  VQS_CUDA(launch_pdl(bias_grad_kernel, dim3(M), dim3(256), 0, (cudaStream_t)stream, g, B, M, L, db, accumulate));
+  const int vec4 = (L % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) ? 1 : 0;
+  VQS_CHECK_ARG((long long)B * L < (1ll << 31), "vqs_bias_grad: B * L too large");
+  VQS_CUDA(launch_pdl(bias_grad_kernel, dim3(M), dim3(256), 0, (cudaStream_t)stream, g, B, M, L, db, accumulate,
+                      FastDiv((uint32_t)(vec4 ? L / 4 : L)), vec4));
   VQS_LAUNCH_CHECK();
   return 0;
 }

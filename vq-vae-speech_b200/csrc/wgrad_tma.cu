@@ -226,6 +226,21 @@ __global__ void __launch_bounds__(256) wgrad_tma_reduce_kernel(const float* __re
   const long long total = (long long)M * Cred * ksz;
   const int cpt = Cred / 128;
   const size_t split_stride = (size_t)tiles_m * tiles_n * 16384;
+  if (ksz == 1 && (Cred & 127) == 0 && ((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0) {
+    // 1 x 1 layers (the only users today): four consecutive channels per thread, shifts instead of divisions
+    const uint32_t c4n = (uint32_t)Cred >> 2, total4 = (uint32_t)M * c4n;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total4; i += gridDim.x * 256u) {
+      const uint32_t m = i / c4n, c = (i - m * c4n) << 2;
+      const size_t o = ((size_t)(m >> 7) * tiles_n + (size_t)(c >> 7)) * 16384 + (size_t)(m & 127) * 128 + (c & 127);
+      float4 a = accumulate ? *reinterpret_cast<const float4*>(dW + (size_t)i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < splits; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(partial + (size_t)s * split_stride + o);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      *reinterpret_cast<float4*>(dW + (size_t)i * 4) = a;
+    }
+    return;
+  }
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int n = (int)(i % ((long long)Cred * ksz)), m = (int)(i / ((long long)Cred * ksz));
     const int c = n / ksz, j = n - c * ksz;
