@@ -22,7 +22,10 @@
 //   * NO dedicated statistics warps (four groups of four warps scan a tile, exchange indices through a named barrier, and
 //     warp q of the group adds the rows of the codes k = q mod 4 into per-group bins): correct, 0.305 ms without and
 //     0.491 ms with statistics -- the read-add-write chains then sit on the critical path of every group.
-// The first is in the round-1 history (commit "register-resident statistics"); neither is built.
+//   * the dedicated warps' read-add-write steps SOFTWARE-PIPELINED (bit masks of the codes decide whether the next step's
+//     bins may be fetched before this step's stores): correct, 0.50 ms -- the extra mask arithmetic costs more issue slots
+//     than the hidden shared-memory latency gives back.
+// The first is in the round-1 history (commit "register-resident statistics"); none of them is built.
 // Warp roles (576 threads, one persistent CTA per SM): warps 0-11 scan (three groups taking tiles round-robin, TMEM lane
 // quarter = warp % 4), warps 12-15 statistics, warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer.
 //
