@@ -73,10 +73,12 @@ int vqs_vq_assign(const float* z, int layout, int B, int D, int T, const float* 
                   void* workspace, size_t workspace_bytes, vqs_stream_t stream);
 
 /* Search engine of vqs_vq_assign (process-wide).  All engines return identical indices and counts (tests/test_vq_gpu.py).
- *   1 = automatic (default): exact-fp32 CUDA-core search while the codebook is shared-memory resident (K = 10/29/44...:
- *       HBM/FMA-bound, the tensor-core variant is not faster there: 0.96 vs 1.08 ms at 2^20 rows but slower at 2^22),
- *       streamed tcgen05 distance GEMM (3xTF32 scores + exact fp32 settlement of near-ties) for large codebooks
- *       (D = 32/64; K = 512: 1.9x, K = 4096: 4x faster than the CUDA-core search);
+ *   1 = automatic (default): for D = 64, K <= 48 and at least 4096 rows the streaming engine (row tiles as raw tf32 tcgen05
+ *       operands + exact fp32 settlement of every row the filter cannot decide): flat rows arrive by TMA, the reference's
+ *       (B, 64, T) rows with B % 64 == 0 by a cp.async gather (2^22 rows: 0.42 / 0.58 ms against 1.23 / 3.7 ms on CUDA
+ *       cores); the exact-fp32 CUDA-core search for every other shape with a shared-memory resident codebook; the streamed
+ *       tcgen05 distance GEMM (3xTF32 scores + exact fp32 settlement of near-ties) for large codebooks (D = 32/64;
+ *       K = 512: 1.9x, K = 4096: 4x faster than the CUDA-core search);
  *   0 = tensor cores wherever a tensor-core kernel exists (also the resident-codebook one);
  *   2 = CUDA cores only. */
 int vqs_vq_set_engine(int engine);
