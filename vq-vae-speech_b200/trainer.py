@@ -13,6 +13,8 @@ last, smallest one -- encoder conv_1..3, 14 MB -- is not hidden under backward c
 Parity contract: per rank, the step equals the reference step on that rank's shard with the same
 codebook; EMA statistics are the sum over shards; gradients are the average over shards.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -123,15 +125,23 @@ class FusedTrainStep(object):
                 self.weight_names.append(base)
         self.bucket_split = first_decoder if first_decoder is not None else total
         # gradient allreduce buckets, in the order the backward pass completes them (flat order is encoder, pre_vq, [vq],
-        # decoder): decoder transposed convs | rest of the decoder | encoder conv_4 .. pre_vq (+ codebook) | conv_1 .. conv_3
+        # decoder): decoder transposed convs | rest of the decoder | encoder conv_4 .. pre_vq (+ codebook) | conv_1 .. conv_3.
+        # VQS_DP_FINE=1 sends conv_3, conv_2 and conv_1 one by one instead (only conv_1's 0.4 MB then travel after the
+        # backward pass has ended); measured at 2 GPUs that is 0.3 % SLOWER (3.435 vs 3.424 ms: two more collectives for
+        # 17 MB that NVLink moves in ~25 us), at 4 / 8 GPUs it is unmeasured -- hence opt-in
         def first_of(prefix, default):
             o = [off for n, off in offs_by_name.items() if n.startswith(prefix)]
             return min(o) if o else default
 
         cut_t = first_of('_decoder._conv_trans_1.', total)
         cut_e = first_of('_encoder._conv_4.', 0)
+        cut_3 = min(first_of('_encoder._conv_3.', 0), cut_e)
+        cut_2 = min(first_of('_encoder._conv_2.', 0), cut_3)
+        if os.environ.get('VQS_DP_FINE') != '1':         # default: conv_1 .. conv_3 as ONE trailing bucket
+            cut_3 = cut_2 = cut_e
         self.buckets = {'dec_convT': (cut_t, total), 'dec_rest': (self.bucket_split, cut_t),
-                        'enc_hi': (cut_e, self.bucket_split), 'enc_lo': (0, cut_e)}
+                        'enc_hi': (cut_e, self.bucket_split), 'enc_c3': (cut_3, cut_e), 'enc_c2': (cut_2, cut_3),
+                        'enc_c1': (0, cut_2)}
         self.n_params = sum(p.numel() for _, p in params)
 
     def _p(self, name):
@@ -424,10 +434,16 @@ class FusedTrainStep(object):
         F.conv1d_wgrad(gp3, b['h2'], G[E + '_conv_3.weight'], 2, 2, ws)
         ops.bias_grad(gp3, G[E + '_conv_3.bias'])
         gh2, gp2 = b['gT_a'], b['gT_b']
+        self._emit_wn_fold(*self.buckets['enc_c3'])
+        if self.world > 1:
+            ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_c3']))
         cdgrad(gp3, E + '_conv_3.weight', T, 2, 2, out=gh2, out2=gp2, mask2=b['m2'], mask2_kind=MASK_U8)
         # conv_2: h2 = relu(p2) + a1 ; a1 = relu(p1)
         F.conv1d_wgrad(gp2, b['a1'], G[E + '_conv_2.weight'], 1, 1, ws)
         ops.bias_grad(gp2, G[E + '_conv_2.bias'])
+        self._emit_wn_fold(*self.buckets['enc_c2'])
+        if self.world > 1:
+            ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_c2']))
         gp1 = self._view('gA2', C, T)
         cdgrad(gp2, E + '_conv_2.weight', T, 1, 1, out=gp1, add_pre=gh2, mask=b['a1'],
                        mask_kind=MASK_FLOAT)
@@ -436,9 +452,9 @@ class FusedTrainStep(object):
 
         # ---- 8. gradient allreduce (average) + fused AMSGrad over the flat buffers (trainer.py:41-42,68) ----
         g_scale = 1.0
-        self._emit_wn_fold(*self.buckets['enc_lo'])
+        self._emit_wn_fold(*self.buckets['enc_c1'])
         if self.world > 1:
-            ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_lo']))
+            ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_c1']))
             ops.record_callable(self._wait_buckets)
             g_scale = self.comm.grad_scale
         ops.amsgrad_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_vmax, self.opt_step, self.lr,
