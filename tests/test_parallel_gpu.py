@@ -48,14 +48,23 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_fused_step_data_parallel_two_ranks():
+@pytest.mark.parametrize('fine_buckets', [False, True])
+def test_fused_step_data_parallel_two_ranks(fine_buckets):
+    """fine_buckets: VQS_DP_FINE=1 sends the gradients of conv_3 / conv_2 / conv_1 as separate trailing buckets."""
     if not torch.cuda.is_available():
         pytest.skip('needs a CUDA device')
     world = 2
     g = load_golden('model_ema_k44')
     avg, states, _ = emulate_dp(g, world)
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    saved = os.environ.get('VQS_DP_FINE')
+    os.environ['VQS_DP_FINE'] = '1' if fine_buckets else '0'      # the spawned workers inherit the environment
+    try:
+        mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    finally:
+        os.environ.pop('VQS_DP_FINE', None)
+        if saved is not None:
+            os.environ['VQS_DP_FINE'] = saved
     for r in range(world):
         res = ret[r]
         cs, ew, W, vq_loss, idx = states[r]
