@@ -13,7 +13,12 @@ Prints ONE JSON line (rank 0).  A "step" is one full training iteration on one b
   e2e        the same through FusedTrainStep.step() with HOST (pinned) batches: H2D copy + step + D2H of the losses
   roofline   the dominant kernel family of the timed region (per-launch CUDA events recorded inside the timed region)
   vq         the fused VQ fwd+bwd+EMA metric of BASELINE.json on N = 2^22 rows against the HBM roofline
-  cpu_baseline  oracle/torch_port.py (torch CPU operators = the reference's own backend) on the box's host cores
+  cpu_baseline  the reference's own modules + ConvolutionalTrainer.iterate (oracle/_ref, copied unmodified from
+                /root/reference/src by oracle/build_ref.py) on the box's host cores (kind "reference"); the torch-CPU port
+                oracle/torch_port.py (kind "port") only when oracle/_ref is absent
+  gpu_eager_baseline  context only: the same unmodified reference modules on cuda:0 (cuDNN / cuBLAS eager), allow_tf32 off / on
+  parity_check  (N > 1) replicated parameters / codebook bit-identical across ranks after the timed region, loss of every
+                rank finite and equal to what the rank's own shard gives
 """
 import argparse
 import json
@@ -128,12 +133,22 @@ def flops_of(entry):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: oracle/torch_port.py on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_train_throughput(cfg, batch, frames, seconds, warmup=2, min_steps=3, max_steps=200, fixed_steps=None):
-    import torch
+def cpu_trainer(cfg, seed=1234, device='cpu'):
+    """(trainer, kind): the unmodified reference (oracle/_ref or /root/reference) when present, else the torch-CPU port."""
+    from oracle import ref_harness
+    if ref_harness.available():
+        return ref_harness.RefTrainer(cfg, seed=seed, device=device), 'reference'
+    if device != 'cpu':
+        return None, None
     from oracle.torch_port import PortTrainer
+    return PortTrainer(cfg, seed=seed), 'port'
+
+
+def cpu_train_throughput(cfg, batch, frames, seconds, warmup=2, min_steps=3, max_steps=200, fixed_steps=None, threads=None):
+    import torch
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    tr = PortTrainer(cfg, seed=1234)
+    torch.set_num_threads(threads or cores)
+    tr, kind = cpu_trainer(cfg)
     gen = torch.Generator().manual_seed(1234)
     xs = [torch.randn(batch, frames, 39, generator=gen) for _ in range(4)]
     for i in range(warmup):
@@ -149,12 +164,59 @@ def cpu_train_throughput(cfg, batch, frames, seconds, warmup=2, min_steps=3, max
         elif (el >= seconds and n >= min_steps) or n >= max_steps:
             break
     el = time.perf_counter() - t0
-    return dict(value=batch * n / el, ms_per_step=1e3 * el / n, steps=n, cores=cores, threads=torch.get_num_threads())
+    r = dict(value=batch * n / el, ms_per_step=1e3 * el / n, steps=n, cores=cores, threads=torch.get_num_threads(), kind=kind)
+    torch.set_num_threads(cores)
+    return r
+
+
+def cpu_sample_text(kind, r, batch, frames):
+    what = {'reference': 'the UNMODIFIED reference (oracle/_ref: models/*.py + ConvolutionalTrainer.iterate, '
+                         'convolutional_trainer.py:44-74) on torch CPU',
+            'port': 'torch-CPU port of the reference step (oracle/torch_port.py; oracle/_ref absent)'}[kind]
+    return '%s, %d threads, %d steps of batch %d x %d frames (%.1f ms/step)' % (what, r['threads'], r['steps'], batch,
+                                                                               frames, r['ms_per_step'])
+
+
+def gpu_eager_baseline(cfg, batch, frames, dev, steps=10, warmup=3):
+    """Context numbers, not the baseline: the unmodified reference modules on the SAME B200 through stock PyTorch eager
+    (cuDNN convolutions, cuBLAS matmuls), once with TF32 off (fp32 parity numerics) and once with torch's TF32 switches on."""
+    import torch
+    from oracle import ref_harness
+    if not ref_harness.available():
+        return None
+    out = {}
+    gen = torch.Generator().manual_seed(1234)
+    xs = [torch.randn(batch, frames, 39, generator=gen).to(dev) for _ in range(4)]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, tf32 in (('allow_tf32_false', False), ('allow_tf32_true', True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            tr = ref_harness.RefTrainer(cfg, seed=1234, device=str(dev))
+            sid = torch.zeros(batch, dtype=torch.long, device=dev)
+            for i in range(warmup):
+                tr.step(xs[i % 4], speaker_id=sid)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                tr.step(xs[i % 4], speaker_id=sid)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {'ms_per_step': ms, 'utterances_per_s': batch / (ms * 1e-3)}
+            del tr
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out['what'] = ('unmodified reference modules + ConvolutionalTrainer.iterate on cuda (torch %s eager: cuDNN / cuBLAS, '
+                   '3 .item() syncs per step), batch %d x %d frames, %d steps' % (torch.__version__, batch, frames, steps))
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (torch CPU operators) on the host cores.
-    Rank 0 alone runs; each step is a bounded sample (a smaller batch when needed) of the same workload."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: unmodified modules + trainer; the
+    port only if those files are absent) on the host cores, all threads.  Rank 0 alone runs; each step is a bounded sample
+    (a smaller batch when needed) of the same workload."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -168,14 +230,13 @@ def run_reference(args):
         batch = max(2, batch // 2)
         need /= 2
     r = cpu_train_throughput(cfg, batch, args.frames, 0.0, warmup=args.warmup, fixed_steps=args.steps)
-    sample = 'torch-CPU port of the reference step (oracle/torch_port.py), %d threads, batch %d x %d frames per step' % (
-        r['threads'], batch, args.frames)
+    sample = cpu_sample_text(r['kind'], r, batch, args.frames)
     line = {
         'impl': 'reference', 'metric': 'train_utterances_per_sec', 'value': r['value'], 'unit': 'utterances/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, 1, batch_override=batch),
-        'cpu_baseline': {'value': r['value'], 'unit': 'utterances/s', 'cores': r['cores'], 'kind': 'port',
+        'cpu_baseline': {'value': r['value'], 'unit': 'utterances/s', 'cores': r['threads'], 'kind': r['kind'],
                          'sample': sample},
         'e2e': {'value': r['value'], 'unit': 'utterances/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -303,8 +364,8 @@ def run_b200(args):
         eng.load_batch(devb[i % 8])
         eng.step()
     eng.losses()
-    # ---- timed region: K steps of the product path (FusedTrainStep.step(): one CUDA-graph replay per step on a single
-    # GPU, launch-by-launch replay under data parallelism), inputs resident in HBM ----
+    # ---- timed region: K steps of the product path (FusedTrainStep.step(): one CUDA-graph replay per step; under data
+    # parallelism the NCCL allreduces are captured into the same graph), inputs resident in HBM ----
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     lc0 = _lib.launch_count()
@@ -413,10 +474,11 @@ def run_b200(args):
     cpu = None
     if not args.skip_cpu and world == 1:
         r = cpu_train_throughput(cfg, B, T, args.cpu_seconds)
-        cpu = {'value': r['value'], 'unit': 'utterances/s', 'cores': r['cores'], 'kind': 'port',
-               'sample': 'torch-CPU port of the reference step (oracle/torch_port.py: the reference\'s own ATen/oneDNN/MKL '
-                         'operators), %d threads, %d steps of batch %d x %d frames (%.1f ms/step)' % (
-                             r['threads'], r['steps'], B, T, r['ms_per_step'])}
+        cpu = {'value': r['value'], 'unit': 'utterances/s', 'cores': r['threads'], 'kind': r['kind'],
+               'sample': cpu_sample_text(r['kind'], r, B, T)}
+        r1 = cpu_train_throughput(cfg, B, T, 0.0, warmup=1, fixed_steps=2, threads=1)     # also one thread
+        cpu['single_thread'] = {'value': r1['value'], 'unit': 'utterances/s', 'cores': 1,
+                                'sample': cpu_sample_text(r1['kind'], r1, B, T)}
     line = {
         'metric': 'train_utterances_per_sec', 'value': value, 'unit': 'utterances/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',

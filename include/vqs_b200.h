@@ -48,6 +48,14 @@ int vqs_version(void);
 const char* vqs_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 long long vqs_launch_count(void);
+/* how many GEMM calls of the calling process were dispatched to each engine (parity tests assert that an eligible layer
+ * really ran on tcgen05, and that nothing silently fell back to the CUDA-core kernel).  Unknown id -> -1. */
+#define VQS_ENGINE_CONV_CUDACORE 0   /* vqs_conv_gemm on the exact-fp32 CUDA-core implicit GEMM */
+#define VQS_ENGINE_CONV_TC 1         /* vqs_conv_gemm on tcgen05 (gemm_tc_kernel, conv mode) */
+#define VQS_ENGINE_WGRAD_CUDACORE 2  /* vqs_wgrad_gemm on CUDA cores */
+#define VQS_ENGINE_WGRAD_TC 3        /* vqs_wgrad_gemm on tcgen05, thread-gathered operands */
+#define VQS_ENGINE_WGRAD_TMA 4       /* vqs_wgrad_gemm on tcgen05, both operands by TMA */
+long long vqs_engine_count(int engine);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* VQ bottleneck                                                                                    */

@@ -187,6 +187,11 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == '--only-speaker':
         model_case('ema_k29_speaker', decay=0.99, num_embeddings=29, use_speaker_conditioning=True, speakers=5, seed=99)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == '--only-h64':          # round 2: num_hiddens % 32 == 0 -> the conv-mode tcgen05
+        # GEMMs of the fused step are eligible for every layer (the 48-wide fixtures run them on the CUDA-core kernel)
+        model_case('ema_k44_h64', decay=0.99, num_hiddens=64, residual_channels=64, B=4, seed=2024)
+        model_case('noema_jitter_k44_h96', decay=0.0, num_hiddens=96, residual_channels=64, B=3, use_jitter=True, seed=2025)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == '--only-kaiming':      # added after the other fixtures were committed
         model_case('ema_k29_kaiming', decay=0.99, num_embeddings=29, use_kaiming_normal=True, seed=777)
         sys.exit(0)
@@ -213,3 +218,6 @@ if __name__ == '__main__':
     model_case('ema_k29_speaker', decay=0.99, num_embeddings=29, use_speaker_conditioning=True, speakers=5, seed=99)
     # weight-normalised convs (use_kaiming_normal: conv1d_builder.py:41-43, residual.py:45-47,57-59)
     model_case('ema_k29_kaiming', decay=0.99, num_embeddings=29, use_kaiming_normal=True, seed=777)
+    # widths that are multiples of 32: every conv-mode GEMM of the fused step is tcgen05-eligible
+    model_case('ema_k44_h64', decay=0.99, num_hiddens=64, residual_channels=64, B=4, seed=2024)
+    model_case('noema_jitter_k44_h96', decay=0.0, num_hiddens=96, residual_channels=64, B=3, use_jitter=True, seed=2025)

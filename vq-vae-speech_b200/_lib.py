@@ -56,6 +56,7 @@ PROTOTYPES = {
     'vqs_version': (c_int, []),
     'vqs_last_error': (c_char_p, []),
     'vqs_launch_count': (c_longlong, []),
+    'vqs_engine_count': (c_longlong, [c_int]),
     'vqs_vq_workspace_bytes': (c_size_t, [c_int, c_int]),
     'vqs_vq_assign': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -121,3 +122,12 @@ def check(code):
 
 def launch_count():
     return int(load().vqs_launch_count())
+
+
+ENGINES = {'conv_cudacore': 0, 'conv_tc': 1, 'wgrad_cudacore': 2, 'wgrad_tc': 3, 'wgrad_tma': 4}
+
+
+def engine_counts():
+    """{engine name: GEMM calls dispatched to it so far in this process} (include/vqs_b200.h: VQS_ENGINE_*)."""
+    lib = load()
+    return dict((k, int(lib.vqs_engine_count(v))) for k, v in ENGINES.items())

@@ -559,9 +559,14 @@ extern "C" int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream) {
   if (d->a_tap_major == 2) {
     VQS_CHECK_ARG(d->precision != VQS_PREC_FP32 && conv_tc_supported(p),
                   "vqs_conv_gemm: an operand image (a_tap_major = 2) needs a tensor-core precision and Cred %% 32 == 0");
+    count_engine(VQS_ENGINE_CONV_TC);
     return launch_conv_tc(p, d->precision, st);
   }
-  if (d->precision != VQS_PREC_FP32 && conv_tc_supported(p)) return launch_conv_tc(p, d->precision, st);
+  if (d->precision != VQS_PREC_FP32 && conv_tc_supported(p)) {
+    count_engine(VQS_ENGINE_CONV_TC);
+    return launch_conv_tc(p, d->precision, st);
+  }
+  count_engine(VQS_ENGINE_CONV_CUDACORE);
   // tile choice: big tiles once they fill the machine, small tiles otherwise
   long long big = (long long)((d->M + 127) / 128) * ((p.Ntot + 127) / 128);
   if (d->M > 64 && p.Ntot > 64 && big >= num_sms()) return launch_conv<128, 128>(p, st);
@@ -603,6 +608,7 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
       set_error("vqs_wgrad_gemm: workspace %zu < %zu", workspace_bytes, need_t);
       return VQS_ERR_WORKSPACE;
     }
+    count_engine(VQS_ENGINE_WGRAD_TMA);
     return launch_wgrad_tma(p, (float*)workspace, st);
   }
   const bool tc = d->precision != VQS_PREC_FP32 && wgrad_tc_supported(p);
@@ -617,6 +623,7 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
   }
   p.partial = pl.splits > 1 ? (float*)workspace : nullptr;
   int e;
+  count_engine(tc ? VQS_ENGINE_WGRAD_TC : VQS_ENGINE_WGRAD_CUDACORE);
   if (tc) e = launch_wgrad_tc(p, d->precision, st);
   else if (pl.bm == 128 && pl.bn == 128) e = launch_wgrad<128, 128>(p, st);
   else if (pl.bm == 128) e = launch_wgrad<128, 64>(p, st);

@@ -18,9 +18,10 @@
 //      Ah*Bh round-robin over three TMEM accumulators and keeps the small correction terms in a fourth; the epilogue adds
 //      the four in fp32 round-to-nearest.  All 512 TMEM columns are used (BN = 128).
 //
-// Warp roles (544 threads): warps 0-15 producers (warps 0-3 double as the epilogue: TMEM lane quarter = warp id),
-// warp 16 = TMEM allocator + MMA issuer.  Pipelines: full[stage] (one arrival per producer warp) / empty[stage]
-// (tcgen05.commit), tmem_full (tcgen05.commit after the last k-block).
+// Warp roles (576 threads): warps 0-15 producers (all of them drain the epilogue: TMEM lane quarter = warp id % 4),
+// warp 16 = TMEM allocator + MMA issuer, warp 17 = second MMA issuer of the 3xTF32 split (see issue_mmas).  Pipelines:
+// full[stage] (one arrival per producer warp) / empty[stage] (one tcgen05.commit per issuer), tmem_full (one
+// tcgen05.commit per issuer after the last k-block).
 //
 // K order of the conv-like GEMM is TAP-MAJOR: kk = j*Cred + c, A = [M][ksz][Cred] (vqs_permute_weight modes 1/2), so a
 // 32-wide k-block has ONE tap j and 32 consecutive channels: the padding / stride / bounds arithmetic of the gather is
@@ -40,17 +41,21 @@ constexpr int BM = 128;
 constexpr int BKF = 32;                    // k-elements (floats) per stage row = one 128-byte swizzle atom
 constexpr int N_PROD_WARPS = 16;
 constexpr int N_PROD = N_PROD_WARPS * 32;
-constexpr int TC_THREADS = N_PROD + 32;
+constexpr int TC_THREADS = N_PROD + 64;   // + warp 16 (TMEM allocator, MMA issuer) + warp 17 (second MMA issuer, 3xTF32)
 
 template <int BN, int PASSES>
 struct TcCfg {
   static constexpr int NOPS = (PASSES == 3) ? 2 : 1;                // hi (+ lo) copies per operand
   static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 4 ? 4 : (200 * 1024) / STAGE_BYTES;
+  // (3-pass, BN = 64: a ring of 3 x 48 KB measured faster than 4 -- 584 vs 743 cycles per k-block in the protocol
+  // microbenchmark profiles/mma_pipe.cu)
+  static constexpr int STAGES_MAX = (PASSES == 3) ? 3 : 4;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > STAGES_MAX ? STAGES_MAX : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int NACC = (PASSES == 3) ? 4 : 1;                // TMEM accumulators of BN columns each
   static constexpr int TMEM_COLS = NACC * BN;
+  static constexpr int N_ISSUERS = (PASSES == 3) ? 2 : 1;           // threads that issue tcgen05.mma (see issue_mmas)
   static_assert(STAGES >= 2, "need at least a double buffer");
 };
 
@@ -216,6 +221,59 @@ __device__ __forceinline__ bool tc_mask_on(const void* m, int kind, size_t i) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// MMA issue loop, executed by a whole converged warp with the MMAs guarded by elect_one().  role 0: single-pass (one
+// accumulator); role 1: main term of the 3xTF32 split; role 2: its correction terms.  The stage ring is unrolled: k-block i0 + j lives in stage j, so all descriptors are base + constant
+// and the round-robin accumulator of a k-step is a compile-time constant.
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int PASSES, int ROLE>
+__device__ __forceinline__ void issue_mmas(TcShared* sh, uint32_t smem_base, uint32_t tmem_base, int nkb) {
+  using Cfg = TcCfg<BN, PASSES>;
+  constexpr uint32_t idesc = make_idesc_tf32(BN);
+  constexpr int S = Cfg::STAGES;
+  const uint64_t d0 = make_desc_sw128(smem_base);
+  const bool elected = elect_one();
+  uint32_t par = 0;
+#pragma unroll 1
+  for (int i0 = 0; i0 < nkb; i0 += S) {
+    const uint32_t nz = i0 > 0 ? 1u : 0u;      // accumulate flag of the first MMA into each accumulator
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      if (i0 + j < nkb) {
+        mbar_wait(&sh->full[j], par);
+        tc_fence_after();
+        const uint64_t a_hi = d0 + (uint64_t)((j * Cfg::STAGE_BYTES) >> 4);
+        const uint64_t b_hi = a_hi + (uint64_t)(Cfg::A_BYTES >> 4);
+        const uint64_t a_lo = a_hi + (uint64_t)((Cfg::A_BYTES + Cfg::B_BYTES) >> 4);
+        const uint64_t b_lo = a_lo + (uint64_t)(Cfg::A_BYTES >> 4);
+#pragma unroll
+        for (int k = 0; k < BKF / 8; ++k) {
+          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // +32 bytes per K = 8 step inside the swizzle atom
+          const int g = j * (BKF / 8) + k;                    // k-step within the unrolled ring pass
+          if (!elected) continue;
+          if (PASSES == 3) {
+            if (ROLE == 1) {
+              // main term: accumulators 1..3 round-robin (the tensor core truncates when it accumulates: one accumulator
+              // drifts 1.8e-5 relative over 864 MMAs, see the file header)
+              umma_tf32(tmem_base + (uint32_t)((1 + g % 3) * BN), a_hi + adv, b_hi + adv, idesc, g < 3 ? nz : 1u);
+            } else {
+              umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, g == 0 ? nz : 1u);
+              umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+            }
+          } else {
+            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, g == 0 ? nz : 1u);
+          }
+        }
+        if (elected) umma_commit(&sh->empty[j]);  // frees the smem slot once this thread's MMAs have read it
+        __syncwarp();
+      }
+    }
+    par ^= 1u;
+  }
+  if (elected) umma_commit(&sh->tmem_full);       // this thread's share of the accumulators is complete
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
 template <int MODE, int BN, int PASSES, int KSZ>
@@ -248,9 +306,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&sh->full[s], N_PROD_WARPS + (a_image ? 1 : 0));
-      mbar_init(&sh->empty[s], 1);
+      mbar_init(&sh->empty[s], Cfg::N_ISSUERS);
     }
-    mbar_init(&sh->tmem_full, 1);
+    mbar_init(&sh->tmem_full, Cfg::N_ISSUERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == N_PROD_WARPS) tmem_alloc(&sh->tmem_base, Cfg::TMEM_COLS);
@@ -363,38 +421,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
       stage(i + 2, r2);
     }
   } else {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BN);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
-        mbar_wait(&sh->full[s], ph);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint64_t a_hi = make_desc_sw128(st);
-        const uint64_t b_hi = make_desc_sw128(st + Cfg::A_BYTES);
-        const uint64_t a_lo = make_desc_sw128(st + Cfg::A_BYTES + Cfg::B_BYTES);
-        const uint64_t b_lo = make_desc_sw128(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
-#pragma unroll
-        for (int k = 0; k < BKF / 8; ++k) {
-          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // +32 bytes per K = 8 step inside the swizzle atom
-          const uint32_t first = (i == 0 && k == 0) ? 0u : 1u;
-          if (PASSES == 3) {
-            // accumulator 0: correction terms; accumulators 1..3: the main term, round-robin per K = 8 step
-            const int g = i * (BKF / 8) + k;
-            umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, first);
-            umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_tf32(tmem_base + (uint32_t)((1 + g % 3) * BN), a_hi + adv, b_hi + adv, idesc, g < 3 ? 0u : 1u);
-          } else {
-            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
-          }
-        }
-        umma_commit(&sh->empty[s]);  // frees the smem slot once these MMAs have read it
-      }
-      umma_commit(&sh->tmem_full);   // accumulator complete
+    // ================= MMA issuers =================
+    // Measured with profiles/mma_rate.cu: the tensor core retires a 128 x 128 x 8 TF32 MMA every 64 cycles, but the round-1
+    // issue loop (under `if (lane == 0)`: an ELECT / BRA.U.ANY loop per MMA, descriptors and the accumulator rotation
+    // computed per k-block at run time, ~190 serially dependent instructions for 12 MMAs) needed well over the 768 cycles
+    // of MMA time per k-block.  Now: whole converged warps run the loop with the MMAs guarded by elect_one() (bare
+    // UTCHMMA), the ring is unrolled over all stages so that every descriptor is `base + constant`, and the 3xTF32 split
+    // is issued by two warps with
+    // DISJOINT accumulators (warp 16: main term Ah*Bh into accumulators 1..3 round-robin; warp 17: correction terms
+    // Al*Bh + Ah*Bl into accumulator 0), so the order of additions into every accumulator stays fixed (deterministic) while
+    // the issue rate doubles.  Both commit to empty[s] / tmem_full (barrier count = 2).
+    if (PASSES == 3) {
+      if (warp == N_PROD_WARPS) issue_mmas<BN, PASSES, 1>(sh, smem_u32(smem), tmem_base, nkb);
+      else issue_mmas<BN, PASSES, 2>(sh, smem_u32(smem), tmem_base, nkb);
+    } else if (warp == N_PROD_WARPS) {
+      issue_mmas<BN, PASSES, 0>(sh, smem_u32(smem), tmem_base, nkb);
     }
-    __syncwarp();
   }
 
   // ================= epilogue: every producer warp takes part =================

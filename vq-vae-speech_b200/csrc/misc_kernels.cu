@@ -21,6 +21,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static std::atomic<long long> g_engine[5];
+void count_engine(int engine) {
+  if (engine >= 0 && engine < 5) g_engine[engine].fetch_add(1, std::memory_order_relaxed);
+}
+long long engine_count(int engine) { return (engine >= 0 && engine < 5) ? g_engine[engine].load() : -1; }
 
 bool pdl_enabled() {
   static int cached = -1;
@@ -310,6 +315,7 @@ using namespace vqs;
 extern "C" int vqs_version(void) { return 100; }
 extern "C" const char* vqs_last_error(void) { return g_err; }
 extern "C" long long vqs_launch_count(void) { return g_launches.load(); }
+extern "C" long long vqs_engine_count(int engine) { return engine_count(engine); }
 
 extern "C" int vqs_upsample2_fwd(const float* in, long long rows, int L, float* out, vqs_stream_t stream) {
   VQS_CHECK_ARG(in && out && rows > 0 && L > 0, "vqs_upsample2_fwd: bad arguments");

@@ -46,6 +46,15 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
     if (++n > (1u << 22)) __trap();
   }
 }
+// One lane of a CONVERGED warp (all 32 lanes must execute this).  tcgen05.mma / tcgen05.commit guarded by this predicate
+// inside warp-converged code compile to bare UTCHMMA / UTCBAR instructions (2-3 SASS instructions per MMA); the same
+// instructions under a divergent `if (lane == 0)` cost an ELECT / R2UR.BROADCAST / BRA.U.ANY loop of ~11 serially
+// dependent instructions per MMA, which made the ISSUING THREAD the limiter of the round-1 GEMMs (profiles/mma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(e));
+  return e != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -14,6 +14,7 @@ namespace vqs {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void count_engine(int engine);
 int num_sms();
 
 #define VQS_CHECK_ARG(cond, ...)            \

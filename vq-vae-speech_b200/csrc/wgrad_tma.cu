@@ -35,7 +35,7 @@ constexpr int WT_STAGE = 4 * WT_T16;         // A raw | B raw | A lo | B lo
 constexpr int WT_STAGES = 3;
 constexpr int WT_LO_WARPS = 8;
 constexpr int WT_TMA_WARP = WT_LO_WARPS, WT_MMA_WARP = WT_LO_WARPS + 1;
-constexpr int WT_THREADS = (WT_LO_WARPS + 2) * 32;
+constexpr int WT_THREADS = (WT_LO_WARPS + 3) * 32;   // lo warps | TMA warp | MMA issuer (main term) | MMA issuer (corrections)
 constexpr int WT_SMEM = WT_STAGES * WT_STAGE + 1024 + 256;
 
 struct WtShared {
@@ -94,9 +94,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tma_kernel(const __grid_c
     for (int s = 0; s < WT_STAGES; ++s) {
       mbar_init(&sh->full_raw[s], 1);
       mbar_init(&sh->full_lo[s], WT_LO_WARPS);
-      mbar_init(&sh->empty[s], 1);
+      mbar_init(&sh->empty[s], 2);       // one tcgen05.commit per MMA issuer
     }
-    mbar_init(&sh->tmem_full, 1);
+    mbar_init(&sh->tmem_full, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WT_MMA_WARP) tmem_alloc(&sh->tmem_base, 512);
@@ -129,31 +129,51 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tma_kernel(const __grid_c
       }
     }
     __syncwarp();
-  } else if (warp == WT_MMA_WARP) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+  } else if (warp == WT_MMA_WARP || warp == WT_MMA_WARP + 1) {
+    // ================= MMA issuers (gemm_tc.cu::issue_mmas: the issuing thread, not the operand feed, limited the round-1
+    // kernel): ring unrolled over the stages -> every descriptor is base + constant; warp WT_MMA_WARP issues the main
+    // term into accumulators 1..3 (round-robin), warp WT_MMA_WARP + 1 the two correction terms into accumulator 0 =================
+    {
       constexpr uint32_t idesc = make_idesc_tf32(128);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % WT_STAGES;
-        const uint32_t ph = (uint32_t)(i / WT_STAGES) & 1u;
-        mbar_wait_sleep(&sh->full_raw[s], ph);
-        mbar_wait_sleep(&sh->full_lo[s], ph);
-        tc_fence_after();
-        const uint32_t st = smem_a + (uint32_t)(s * WT_STAGE);
-        const uint64_t a_hi = make_desc_sw128(st), b_hi = make_desc_sw128(st + WT_T16);
-        const uint64_t a_lo = make_desc_sw128(st + 2 * WT_T16), b_lo = make_desc_sw128(st + 3 * WT_T16);
+      const bool main_role = warp == WT_MMA_WARP;
+      const bool elected = elect_one();      // whole converged warp runs the loop, MMAs guarded (bare UTCHMMA)
+      const uint64_t d0 = make_desc_sw128(smem_a);
+      uint32_t par = 0;
+#pragma unroll 1
+      for (int i0 = 0; i0 < nkb; i0 += WT_STAGES) {
+        const uint32_t nz = i0 > 0 ? 1u : 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t adv = (uint64_t)((k * 32) >> 4);
-          const int g = i * 4 + k;
-          // accumulator 0: correction terms; accumulators 1..3: the main term, round-robin per K = 8 step
-          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, g == 0 ? 0u : 1u);
-          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-          umma_tf32(tmem_base + (uint32_t)((1 + g % 3) * 128), a_hi + adv, b_hi + adv, idesc, g < 3 ? 0u : 1u);
+        for (int s = 0; s < WT_STAGES; ++s) {
+          if (i0 + s < nkb) {
+            mbar_wait(&sh->full_raw[s], par);
+            mbar_wait(&sh->full_lo[s], par);
+            tc_fence_after();
+            const uint64_t a_hi = d0 + (uint64_t)((s * WT_STAGE) >> 4), b_hi = a_hi + (uint64_t)(WT_T16 >> 4);
+            const uint64_t a_lo = a_hi + (uint64_t)((2 * WT_T16) >> 4), b_lo = a_hi + (uint64_t)((3 * WT_T16) >> 4);
+            if (main_role) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                const int g = s * 4 + k;
+                if (elected) umma_tf32(tmem_base + (uint32_t)((1 + g % 3) * 128), a_hi + adv, b_hi + adv, idesc, g < 3 ? nz : 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                if (elected) {
+                  umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (s == 0 && k == 0) ? nz : 1u);
+                  umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                }
+              }
+            }
+            if (elected) umma_commit(&sh->empty[s]);
+            __syncwarp();
+          }
         }
-        umma_commit(&sh->empty[s]);
+        par ^= 1u;
       }
-      umma_commit(&sh->tmem_full);
+      if (elected) umma_commit(&sh->tmem_full);
     }
     __syncwarp();
   } else {
