@@ -48,6 +48,9 @@ def parse():
     ap.add_argument('--vq-rows', type=int, default=1 << 22)
     ap.add_argument('--skip-vq', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-eager', action='store_true', help='skip the gpu_eager_baseline context numbers')
+    ap.add_argument('--nccl-max-ctas', type=int, default=None,
+                    help='CTA cap of the NCCL communicator (default: parallel.NCCL_MAX_CTAS = 4; 0 = NCCL default)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     return ap.parse_args()
 
@@ -338,8 +341,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        from vq_vae_speech_b200 import parallel
+        parallel.init_nccl(dev, parallel.NCCL_MAX_CTAS if args.nccl_max_ctas is None else args.nccl_max_ctas)
     from vq_vae_speech_b200 import _lib, ops
     from vq_vae_speech_b200.convolutional_vq_vae import ConvolutionalVQVAE
     from vq_vae_speech_b200.trainer import FusedTrainStep
@@ -465,12 +468,16 @@ def run_b200(args):
            'h2d_bytes_per_step': B * T * 39 * 4, 'd2h_bytes_per_step': 16, 'ms_per_step': ems / args.steps,
            'last_losses': last}
 
+    parity = dp_parity_check(eng, devb, world) if world > 1 else None
     if rank != 0:
         finish(world)
         return
     vq = None
     if not args.skip_vq and world == 1:
         vq = vq_bench(dev, pk, args.vq_rows, K=args.codes)
+    eager = None
+    if not args.skip_eager and not args.skip_cpu and world == 1:
+        eager = gpu_eager_baseline(cfg, B, T, dev)
     cpu = None
     if not args.skip_cpu and world == 1:
         r = cpu_train_throughput(cfg, B, T, args.cpu_seconds)
@@ -485,11 +492,56 @@ def run_b200(args):
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
         'ms_per_step_cuda_graph': graph_ms, 'ms_per_step_instrumented': instr_ms, 'kernel_breakdown': breakdown,
-        'gemm_launches': gemm_launches, 'vq': vq,
+        'gemm_launches': gemm_launches, 'vq': vq, 'gpu_eager_baseline': eager, 'parity_check': parity,
         'params': eng.n_params, 'flops_per_step': sum(flops_of(e) for e in eng.schedule if e[0] is not None),
     }
     emit(line)
     finish(world)
+
+
+def dp_parity_check(eng, devb, world):
+    """Self-check of the data-parallel path that was just timed (N > 1; every rank takes part):
+      * the replicated state -- flat parameters, AMSGrad moments, codebook, EMA state -- is BIT-identical on all ranks after
+        the timed steps (DataParallelComm.assert_replicated: MIN- and MAX-allreduce agree);
+      * one more step from the same state gives bit-identical parameters whether it is replayed from the captured CUDA graph
+        (NCCL allreduces inside the graph) or issued launch by launch with eager NCCL calls -- the eager path is the one the
+        2-rank oracle test pins to the per-shard contract (tests/test_parallel_gpu.py, SURVEY 8e);
+      * every rank's losses are finite and the EMA statistics of the step sum to world x rows (global counts).
+    Raises on failure; returns the summary that goes into the JSON line."""
+    import torch
+    import torch.distributed as dist
+    comm, vq = eng.comm, eng.model._vq
+    state = [eng.flat_p, eng.flat_m, eng.flat_v, eng.flat_vmax, eng.opt_step]
+    if eng.is_ema:
+        state += [vq._embedding.weight.data, vq._ema_w.data, vq._ema_cluster_size]
+    for i, t in enumerate(state):
+        comm.assert_replicated(t.float() if t.dtype != torch.float32 else t, 'replicated state %d' % i)
+    saved = [t.clone() for t in state]
+    eng.load_batch(devb[0])
+    eng.step()                                    # (a) the product path: graph replay when the graph is in use
+    via_graph = eng.graph is not None
+    a = [t.clone() for t in state]
+    la = eng.losses()
+    counts = eng.buf['stats'][:eng.dims['K']].sum().item()
+    for t, sv in zip(state, saved):
+        t.copy_(sv)
+    eng.load_batch(devb[0])
+    eng._run_schedule()                           # (b) the same schedule, launch by launch, eager NCCL
+    lb = eng.losses()
+    same = all(torch.equal(x, y) for x, y in zip(a, state))
+    flag = torch.tensor([1.0 if same else 0.0, 1.0 if all(map(lambda v: v == v and abs(v) < 1e30, la.values())) else 0.0],
+                        device=eng.dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok_same, ok_finite = bool(flag[0].item() == 1.0), bool(flag[1].item() == 1.0)
+    rows = eng.B * eng.dims['Tq'] * (world if eng.is_ema else 1)     # the statistics are allreduced for the EMA update only
+    out = {'replicated_state_bit_identical': True, 'graph_replay_equals_eager_nccl': ok_same, 'via_cuda_graph': via_graph,
+           'losses_finite_all_ranks': ok_finite, 'global_counts': counts, 'global_rows': rows,
+           'rank0_losses_graph': la, 'rank0_losses_eager': lb}
+    if not (ok_same and ok_finite and counts == rows):
+        raise RuntimeError('data-parallel parity check failed: %r' % (out,))
+    for i, t in enumerate(state):
+        comm.assert_replicated(t.float() if t.dtype != torch.float32 else t, 'replicated state %d after the check' % i)
+    return out
 
 
 _REAL_STDOUT = None

@@ -256,6 +256,12 @@ int vqs_relu_bwd(const float* g, const float* act, long long n, float* gin, vqs_
 int vqs_add(const float* a, const float* b, long long n, float* out, vqs_stream_t stream);
 /* strided (B, L, C) -> NCL (B, C, L) copy: the `.permute(0, 2, 1).contiguous().float()` of convolutional_vq_vae.py:118. */
 int vqs_blc_to_ncl(const float* in, int B, int L, int C, float* out, vqs_stream_t stream);
+/* Speaker conditioning of the decoder input (deconvolutional_decoder.py:108-111; global_conditioning.py:52-57 repeats the
+ * per-utterance feature vector over time and `torch.cat([x, speaker_embedding], dim=1)` appends it to the channels):
+ * out (B, Ca + Cb, L) = [ a (B, Ca, L) | v (B, Cb) repeated over L ];  vqs_slice_channels is its gradient with respect to
+ * a: the first Ca channels of g (B, C, L). */
+int vqs_concat_channels(const float* a, const float* v, int B, int Ca, int Cb, int L, float* out, vqs_stream_t stream);
+int vqs_slice_channels(const float* g, int B, int C, int Ca, int L, float* out, vqs_stream_t stream);
 
 /* Eval-mode distance tables of the bottleneck (src/models/vector_quantizer.py:108-127; the EMA class raises NameError on
  * the same lines): Euclidean distances torch.dist(x, y, 2) between VQ rows, in itertools order.

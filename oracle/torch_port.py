@@ -105,7 +105,7 @@ class PortVQVAE(nn.Module):
         W = self.emb.weight
         dist = (flat.pow(2).sum(1, keepdim=True) + W.pow(2).sum(1)) - 2 * flat @ W.t()
         idx = dist.argmin(1, keepdim=True)
-        enc = torch.zeros(idx.shape[0], cfg['num_embeddings']).scatter_(1, idx, 1)
+        enc = torch.zeros(idx.shape[0], cfg['num_embeddings'], dtype=flat.dtype).scatter_(1, idx, 1)
         if self.ema and self.training:
             g, eps, K = cfg['decay'], cfg.get('epsilon', 1e-5), cfg['num_embeddings']
             with torch.no_grad():
@@ -128,7 +128,7 @@ class PortVQVAE(nn.Module):
 
     def forward(self, x_btf, jitter_src=None, speaker_features=None):
         nl = self.cfg['num_residual_layers']
-        x = x_btf.permute(0, 2, 1).contiguous().float()
+        x = x_btf.permute(0, 2, 1).contiguous().to(self.emb.weight.dtype)   # .float() in the reference (vq_vae.py:118)
         a1 = F.relu(self.e1(x))
         h = F.relu(self.e2(a1)) + a1
         a3 = F.relu(self.e3(h))
@@ -171,7 +171,7 @@ class PortTrainer(object):
             src = jitter_plan(x_btf.shape[1] // 2 + 1, cfg['jitter_probability'])
         self.opt.zero_grad()
         recon, vq_loss, ppl, idx = self.model(x_btf, src, speaker_features)
-        target = x_btf.permute(0, 2, 1).contiguous().float()
+        target = x_btf.permute(0, 2, 1).contiguous().to(recon.dtype)         # .float() in the reference (trainer.py:47)
         recon_loss = F.mse_loss(recon, target)
         loss = vq_loss + recon_loss
         loss.backward()

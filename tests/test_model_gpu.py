@@ -128,16 +128,20 @@ def test_fused_step_matches_reference(case, use_graph, precision):
     g = load_golden(case)
     model, cfg = _build(g, dev)
     B, T = int(g['B']), int(g['T'])
-    if cfg['use_speaker_conditioning']:      # host RNG inside forward: module path only
-        with pytest.raises(NotImplementedError):
-            FusedTrainStep(model, B, T, cfg['learning_rate'], use_graph=use_graph, precision=precision)
-        return
     eng = FusedTrainStep(model, B, T, cfg['learning_rate'], use_graph=use_graph, precision=precision)
     if cfg['use_jitter']:
         np.random.seed(int(g['seed']))
     steps = int(g['steps'])
     for s in range(steps):
-        eng.step(torch.from_numpy(g[f'x{s}']))
+        if cfg['use_speaker_conditioning']:
+            # the reference draws a fresh random speaker embedding on the host RNG inside forward (global_conditioning.py:34);
+            # make_golden.py pinned the RNG to 1000 + s right before the call, the fused step draws the same one
+            speaker_dic = {'p%03d' % i: i for i in range(int(g['speakers']))}
+            torch.manual_seed(1000 + s)
+            eng.step(torch.from_numpy(g[f'x{s}']), speaker_dic=speaker_dic, speaker_id=torch.from_numpy(g[f'speaker_id{s}']))
+            assert np.array_equal(eng.buf['spk'].cpu().numpy(), g[f'speaker_features{s}'])
+        else:
+            eng.step(torch.from_numpy(g[f'x{s}']))
         out = eng.losses()
         if cfg['use_jitter']:
             assert np.array_equal(eng.last_plan, g[f'jitter_src{s}'])
@@ -220,6 +224,92 @@ def test_checkpoint_roundtrip_and_torch_adam_compat(tmp_path):
         assert torch.equal(v, want[k]), k
 
 
+def test_checkpoint_roundtrip_weight_normalised_model(tmp_path):
+    """use_kaiming_normal (weight_g / weight_v parameters, effective-weight scratch buffers in the step): the optimizer
+    state dict covers exactly the named parameters, torch Adam accepts it, and save -> load -> step is bit-exact."""
+    dev = _dev()
+    from vq_vae_speech_b200 import trainer as tr
+    g = load_golden('model_ema_k29_kaiming')
+    model, cfg = _build(g, dev)
+    eng = tr.FusedTrainStep(model, int(g['B']), int(g['T']), cfg['learning_rate'], use_graph=False)
+    eng.step(torch.from_numpy(g['x0']))
+    path = str(tmp_path / 'wn_1_checkpoint.pth')
+    tr.save_checkpoint(eng, path, 'wn', 0)
+    ck = torch.load(path, weights_only=False)
+    names = [n for n, _ in model.named_parameters()]
+    assert any(n.endswith('weight_g') for n in names)
+    stepped = [names[i] for i in sorted(ck['optimizer']['state'])]
+    assert stepped == [n for n in names if not n.startswith('_vq.')]          # EMA codebook: no optimizer state
+    ref_opt = torch.optim.Adam(model.parameters(), lr=cfg['learning_rate'], amsgrad=True)
+    ref_opt.load_state_dict(ck['optimizer'])
+    eng.step(torch.from_numpy(g['x1']))
+    want = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model2, _ = _build(g, dev)
+    eng2 = tr.FusedTrainStep(model2, int(g['B']), int(g['T']), cfg['learning_rate'], use_graph=False)
+    tr.load_checkpoint(eng2, path)
+    eng2.step(torch.from_numpy(g['x1']))
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v, want[k]), k
+
+
+def test_load_optimizer_state_restores_hyper_parameters():
+    """The reference resumes through optimizer.load_state_dict, which restores lr / betas / eps of the checkpoint
+    (pipeline_factory.py:118-120): a step built with another learning rate must continue with the checkpoint's."""
+    dev = _dev()
+    from vq_vae_speech_b200 import trainer as tr
+    g = load_golden('model_ema_k44')
+    B, T = int(g['B']), int(g['T'])
+    model, cfg = _build(g, dev)
+    eng = tr.FusedTrainStep(model, B, T, cfg['learning_rate'], use_graph=True)
+    eng.step(torch.from_numpy(g['x0']))
+    sd = tr.optimizer_state_dict(eng)
+    after0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    eng.step(torch.from_numpy(g['x1']))
+    want = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model2, _ = _build(g, dev)
+    eng2 = tr.FusedTrainStep(model2, B, T, 10 * cfg['learning_rate'], use_graph=True)
+    with torch.no_grad():
+        sd2 = model2.state_dict()
+        for k, v in after0.items():
+            sd2[k].copy_(v)
+    tr.load_optimizer_state_dict(eng2, sd)
+    assert abs(eng2.lr - cfg['learning_rate']) < 1e-12
+    eng2.step(torch.from_numpy(g['x1']))
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v, want[k]), k
+
+
+def test_fused_step_separate_target_matches_reference_formula():
+    """convolutional_trainer.py:47,54: the reconstruction loss is taken against data['output_features'].  With a target
+    different from the input, losses and the gradient of the decoder's last layer must equal the numpy oracle's."""
+    dev = _dev()
+    from oracle import model_oracle as mo
+    from vq_vae_speech_b200.trainer import FusedTrainStep
+    g = load_golden('model_ema_k44')
+    model, cfg = _build(g, dev)
+    B, T = int(g['B']), int(g['T'])
+    p = {k[5:]: v.astype(np.float64) for k, v in g.items() if k.startswith('init.')}
+    eng = FusedTrainStep(model, B, T, cfg['learning_rate'], use_graph=False, separate_target=True)
+    x, target = g['x0'], g['x1']
+    with pytest.raises(ValueError):
+        eng.step(torch.from_numpy(x))                                    # target missing
+    eng.step(torch.from_numpy(x), torch.from_numpy(target))
+    got = eng.losses()
+    ocfg = dict(commitment_cost=cfg['commitment_cost'], decay=cfg['decay'], num_residual_layers=cfg['num_residual_layers'],
+                learning_rate=cfg['learning_rate'], epsilon=1e-5)
+    out, c = mo.model_forward(dict(p), x, ocfg)
+    grads, _ = mo.model_backward(p, c, out, target.transpose(0, 2, 1), ocfg)
+    recon_loss = float(np.mean((out['reconstructed_x'] - target.transpose(0, 2, 1)) ** 2))
+    assert rel_err(got['reconstruction_loss'], recon_loss) < TOL
+    assert rel_err(got['vq_loss'], float(out['vq_loss'])) < TOL
+    mine = eng.gradients()
+    for n in ('_decoder._conv_trans_3.weight', '_decoder._conv_trans_3.bias', '_encoder._conv_1.weight', '_pre_vq_conv.weight'):
+        assert rel_err(mine[n].cpu().numpy(), grads[n]) < 2e-5, n
+    eng_same = FusedTrainStep(_build(g, dev)[0], B, T, cfg['learning_rate'], use_graph=False)
+    with pytest.raises(ValueError):
+        eng_same.step(torch.from_numpy(x), torch.from_numpy(target))     # built without separate_target
+
+
 def test_feature_batcher_matches_reference_normalisation():
     """on-GPU normalisation == the reference's numpy float64 `(x - mean) / std` followed by .float()."""
     dev = _dev()
@@ -235,3 +325,37 @@ def test_feature_batcher_matches_reference_normalisation():
     assert np.array_equal(got, ref)
     with pytest.raises(ValueError):
         fb.collate(mine[:2])
+
+
+def test_feature_loader_reads_pickles_and_survives_a_pipelined_loop(tmp_path):
+    """SURVEY 8f N3 end to end: per-utterance pickles -> epoch order -> rank shard -> pinned staging -> GPU normalisation.
+    The consumer never synchronises between batches (as FusedTrainStep.step() does not): every batch must still equal the
+    reference's numpy normalisation of exactly its own utterances (the pinned staging slots rotate behind CUDA events)."""
+    dev = _dev()
+    from test_data_cpu import _write_features
+    from vq_vae_speech_b200.data import FeatureLoader, FeaturePickleDataset
+    n, B, T = 40, 4, 47
+    _write_features(str(tmp_path), 'train', n, T=T, seed=5)
+    ds = FeaturePickleDataset(str(tmp_path), 'train')
+    rng = np.random.RandomState(1)
+    norm = {'train_mean': rng.randn(39) * 5, 'train_std': np.abs(rng.randn(39)) * 3 + 0.5}
+    for rank in range(2):
+        torch.manual_seed(21)
+        loader = FeatureLoader(ds, B, T, dev, normalizer=norm, rank=rank, world_size=2)
+        assert len(loader) == n // (2 * B)
+        kept, want = [], []
+        for x, target, items in loader:                    # no synchronisation inside the loop
+            assert target is x                              # output_features is input_features in these pickles
+            kept.append(x.clone())
+            want.append(np.stack([(it['input_features'] - norm['train_mean']) / norm['train_std'] for it in items]
+                                 ).astype(np.float32))
+        assert len(kept) == len(loader)
+        for a, b in zip(kept, want):
+            assert np.array_equal(a.cpu().numpy(), b)
+    # the two ranks of one epoch see disjoint utterances
+    seen = []
+    for rank in range(2):
+        torch.manual_seed(21)
+        for _, _, items in FeatureLoader(ds, B, T, dev, rank=rank, world_size=2):
+            seen += [it['index'] for it in items]
+    assert len(seen) == len(set(seen)) == n

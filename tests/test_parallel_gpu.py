@@ -79,3 +79,96 @@ def test_fused_step_data_parallel_two_ranks(fine_buckets):
     assert np.array_equal(ret[0]['cs'], ret[1]['cs'])
     for n in ret[0]['grads']:
         assert np.array_equal(ret[0]['grads'][n], ret[1]['grads'][n]), n
+
+
+def _nccl_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    os.environ['RANK'], os.environ['WORLD_SIZE'], os.environ['LOCAL_RANK'] = str(rank), str(world), str(rank)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    from vq_vae_speech_b200 import parallel
+    try:
+        comm = parallel.init_nccl(dev)
+        from test_model_gpu import _build
+        from vq_vae_speech_b200.trainer import FusedTrainStep
+        from conftest import load_golden as lg
+        g = lg('model_ema_k44_h64')                       # num_hiddens 64: every conv GEMM is tcgen05-eligible
+        model, cfg = _build(g, dev)
+        x = torch.from_numpy(g['x0'])                      # global batch of 4 utterances
+        eng = FusedTrainStep(model, x.shape[0] // world, x.shape[1], cfg['learning_rate'], precision='3xtf32',
+                             use_graph=True)
+        assert eng.world == world and eng.use_graph
+        res = []
+        for s in range(3):                                 # step 0 eager, step 1 captures the graph (NCCL inside), step 2 replays
+            eng.step(comm.shard(torch.from_numpy(g[f'x{s}'])))
+            out = eng.losses()
+            res.append(dict(vq_loss=out['vq_loss'], recon_loss=out['reconstruction_loss'],
+                            idx=eng.encoding_indices().cpu().numpy().reshape(-1)))
+            if s == 0:
+                grads0 = {k: (v * eng.comm.grad_scale).cpu().numpy() for k, v in eng.gradients().items()}
+        assert eng.graph is not None
+        vq = model._vq
+        for t, what in ((eng.flat_p, 'parameters'), (eng.flat_m, 'exp_avg'), (eng.flat_vmax, 'max_exp_avg_sq'),
+                        (vq._embedding.weight.data, 'codebook'), (vq._ema_cluster_size, 'cluster sizes')):
+            comm.assert_replicated(t, what)
+        ret[rank] = dict(steps=res, grads0=grads0, cs=vq._ema_cluster_size.cpu().numpy(),
+                         W=vq._embedding.weight.detach().cpu().numpy())
+        dist.barrier()
+        torch.cuda.synchronize()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
+    # destroy_process_group can block after collectives were captured into a CUDA graph (seen in bench.py): leave directly
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
+def test_fused_step_data_parallel_nccl_in_cuda_graph():
+    """The path bench.py times under torch.distributed.run: NCCL allreduces captured into the step's CUDA graph, tcgen05
+    3xTF32 GEMMs, two GPUs.  Step 0 (eager) is checked against the per-shard oracle emulation of the contract (SURVEY 8e);
+    steps 1-2 (capture + replay) must keep the replicated state bit-identical on both ranks and finite (bench.py's
+    parity_check additionally asserts on every multi-GPU run that a graph replay equals the eager-NCCL replay bit for bit)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs two CUDA devices (run with gpurun --gpus 2)')
+    from oracle import model_oracle as mo
+    from test_parallel_cpu import _oracle_cfg
+    world = 2
+    g = load_golden('model_ema_k44_h64')
+    # per-shard emulation of step 0 on the 4-utterance batch x0: statistics summed, gradients averaged
+    cfg = _oracle_cfg(g)
+    p = {k[5:]: v.astype(np.float64) for k, v in g.items() if k.startswith('init.')}
+    x = g['x0']
+    per = x.shape[0] // world
+    shards = [x[r * per:(r + 1) * per] for r in range(world)]
+    local = []
+    for xs in shards:
+        out, c = mo.model_forward(dict(p), xs, cfg)
+        local.append((c['vq']['counts'], c['vq']['dw'], c['vq']['N']))
+    tot = (sum(l[0] for l in local), sum(l[1] for l in local), sum(l[2] for l in local))
+    cfg2 = dict(cfg, stats_allreduce=lambda c_, d_, n_: tot)
+    grads, states = [], []
+    for xs in shards:
+        out, c = mo.model_forward(dict(p), xs, cfg2)
+        gr, _ = mo.model_backward(p, c, out, xs.transpose(0, 2, 1), cfg2)
+        grads.append(gr)
+        states.append((out['vq_loss'], c['vq']['idx']))
+    avg = {k: sum(gr[k] for gr in grads) / world for k in grads[0]}
+    ret = mp.Manager().dict()
+    mp.spawn(_nccl_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        vq_loss, idx = states[r]
+        assert np.array_equal(ret[r]['steps'][0]['idx'], idx)
+        assert rel_err(ret[r]['steps'][0]['vq_loss'], vq_loss) < 1e-5
+        for n, ref in avg.items():
+            if '_layers.1.' in n:
+                continue
+            assert rel_err(ret[r]['grads0'][n], ref) < 2e-5, n
+        for s in range(3):
+            assert np.isfinite(ret[r]['steps'][s]['vq_loss']) and np.isfinite(ret[r]['steps'][s]['recon_loss'])
+    assert np.array_equal(ret[0]['W'], ret[1]['W']) and np.array_equal(ret[0]['cs'], ret[1]['cs'])

@@ -561,11 +561,9 @@ template <int MODE, int BN, int PASSES, int KSZ>
 int launch_tc_t(const TcParams<MODE>& prm, dim3 grid, cudaStream_t st) {
   using Cfg = TcCfg<BN, PASSES>;
   auto kern = gemm_tc_kernel<MODE, BN, PASSES, KSZ>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static DevCache configured;  // per instantiation and device
+  if (dev_needs(configured, Cfg::SMEM_BYTES))
     VQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
   VQS_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, prm));
   VQS_LAUNCH_CHECK();
   return 0;

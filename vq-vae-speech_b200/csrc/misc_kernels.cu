@@ -37,13 +37,14 @@ bool pdl_enabled() {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  static int cached[16] = {0};                 // per device
   int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess &&
-      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
-    cached = n;
-    return n;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    if (dev >= 0 && dev < 16 && cached[dev] > 0) return cached[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+      if (dev >= 0 && dev < 16) cached[dev] = n;
+      return n;
+    }
   }
   (void)cudaGetLastError();
   return 148;  // B200; used only for workspace sizing when no device is visible
@@ -121,6 +122,31 @@ __global__ void blc_to_ncl_kernel(const float* __restrict__ in, int B, int L, in
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int c = c0 + i, l = l0 + threadIdx.x;
     if (c < C && l < L) dst[(size_t)c * L + l] = tile[threadIdx.x][i];
+  }
+}
+
+// out[b, c, l] = c < Ca ? a[b, c, l] : v[b, c - Ca]: a per-utterance feature vector repeated over time and appended to the
+// channels (speaker conditioning, deconvolutional_decoder.py:108-111 / global_conditioning.py:52-57)
+__global__ void __launch_bounds__(EW_T) concat_channels_kernel(const float* __restrict__ a, const float* __restrict__ v,
+                                                              int Ca, int Cb, int L, long long n, float* __restrict__ out) {
+  const int C = Ca + Cb;
+  for (long long i = blockIdx.x * (long long)EW_T + threadIdx.x; i < n; i += (long long)gridDim.x * EW_T) {
+    const long long bc = i / L;
+    const int l = (int)(i - bc * L);
+    const long long b = bc / C;
+    const int c = (int)(bc - b * C);
+    out[i] = c < Ca ? a[(b * Ca + c) * L + l] : __ldg(v + b * Cb + (c - Ca));
+  }
+}
+// out[b, c, l] = g[b, c, l] for c < Ca: the first Ca channels of a (B, C, L) tensor (gradient of the concatenation above)
+__global__ void __launch_bounds__(EW_T) slice_channels_kernel(const float* __restrict__ g, int C, int Ca, int L, long long n,
+                                                             float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)EW_T + threadIdx.x; i < n; i += (long long)gridDim.x * EW_T) {
+    const long long bc = i / L;
+    const int l = (int)(i - bc * L);
+    const long long b = bc / Ca;
+    const int c = (int)(bc - b * Ca);
+    out[i] = g[(b * C + c) * L + l];
   }
 }
 
@@ -363,6 +389,22 @@ extern "C" int vqs_blc_to_ncl(const float* in, int B, int L, int C, float* out, 
   VQS_CHECK_ARG(in && out && B > 0 && L > 0 && C > 0 && B <= 65535, "vqs_blc_to_ncl: bad arguments");
   dim3 grid((L + 31) / 32, (C + 31) / 32, B), block(32, 8);
   blc_to_ncl_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, B, L, C, out);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vqs_concat_channels(const float* a, const float* v, int B, int Ca, int Cb, int L, float* out,
+                                   vqs_stream_t stream) {
+  VQS_CHECK_ARG(a && v && out && B > 0 && Ca > 0 && Cb > 0 && L > 0, "vqs_concat_channels: bad arguments");
+  const long long n = (long long)B * (Ca + Cb) * L;
+  concat_channels_kernel<<<ew_grid(n), EW_T, 0, (cudaStream_t)stream>>>(a, v, Ca, Cb, L, n, out);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vqs_slice_channels(const float* g, int B, int C, int Ca, int L, float* out, vqs_stream_t stream) {
+  VQS_CHECK_ARG(g && out && B > 0 && C > 0 && Ca > 0 && Ca <= C && L > 0, "vqs_slice_channels: bad arguments");
+  const long long n = (long long)B * Ca * L;
+  slice_channels_kernel<<<ew_grid(n), EW_T, 0, (cudaStream_t)stream>>>(g, C, Ca, L, n, out);
   VQS_LAUNCH_CHECK();
   return 0;
 }

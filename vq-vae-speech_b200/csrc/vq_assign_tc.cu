@@ -358,10 +358,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_assign_tc_kernel(const AssignT
       out[K + i] = a;
     }
   } else if (warp == MMA_WARP) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole converged warp, MMAs guarded by elect_one(): see gemm_tc.cu::issue_mmas) ==========
+    {
       const uint32_t idesc = make_idesc_tf32(Kpad);
-      const uint32_t cbh_a = smem_u32(cbh), cbl_a = smem_u32(cbl);
+      const bool elected = elect_one();
+      const uint64_t cbh_d = make_desc_sw128(smem_u32(cbh)), cbl_d = make_desc_sw128(smem_u32(cbl));
+      const uint64_t xs_d = make_desc_sw128(smem_u32(xs));
       for (int it = 0; it < my_tiles; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -370,22 +372,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) vq_assign_tc_kernel(const AssignT
         mbar_wait(&sh->full[s], ph);
         mbar_wait(&sh->tmem_empty[a], aph ^ 1u);
         tc_fence_after();
-        const uint32_t xh_a = smem_u32(xs + s * stage_bytes), xl_a = xh_a + (uint32_t)x_tile;
+        const uint64_t xh_d = xs_d + (uint64_t)((s * stage_bytes) >> 4), xl_d = xh_d + (uint64_t)(x_tile >> 4);
         const uint32_t dst = tmem_base + (uint32_t)(a * Kpad);
-        uint32_t acc = 0u;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const uint64_t ah = make_desc_sw128(xh_a + kb * XT_BYTES), al = make_desc_sw128(xl_a + kb * XT_BYTES);
-          const uint64_t bh = make_desc_sw128(cbh_a + kb * Kpad * 128), bl = make_desc_sw128(cbl_a + kb * Kpad * 128);
+        if (elected) {
+          uint32_t acc = 0u;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint64_t ao = (uint64_t)((kb * XT_BYTES) >> 4), bo = (uint64_t)((kb * Kpad * 128) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adv = (uint64_t)((k * 32) >> 4);
-            umma_tf32(dst, al + adv, bh + adv, idesc, acc);
-            umma_tf32(dst, ah + adv, bl + adv, idesc, 1u);
-            umma_tf32(dst, ah + adv, bh + adv, idesc, 1u);
-            acc = 1u;
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);
+              umma_tf32(dst, xl_d + ao + adv, cbh_d + bo + adv, idesc, acc);
+              umma_tf32(dst, xh_d + ao + adv, cbl_d + bo + adv, idesc, 1u);
+              umma_tf32(dst, xh_d + ao + adv, cbh_d + bo + adv, idesc, 1u);
+              acc = 1u;
+            }
           }
+          umma_commit(&sh->tmem_full[a]);
         }
-        umma_commit(&sh->tmem_full[a]);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -527,15 +531,16 @@ int launch_assign_tc(const float* z, int layout, int B, int D, int T, const floa
   p.divD = FastDiv((uint32_t)D);
   p.G = stats_groups(K, D);
   {
+    p.debug = 0;
+#ifdef VQS_DEBUG   /* profiling builds only (-DVQS_DEBUG): these bits switch phases off and give WRONG results */
     const char* dbg = getenv("VQS_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
+#endif
   }
   const size_t smem = assign_tc_smem_bytes(K, D);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static DevCache configured;
+  if (dev_needs(configured, smem))
     VQS_CUDA(cudaFuncSetAttribute(vq_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   int grid = num_sms();
   if (grid > p.ntiles) grid = p.ntiles;
   if (grid > max_grid) grid = max_grid;
@@ -808,33 +813,51 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
       }
     }
   } else if (warp == L_MMA_WARP) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(CHUNK);
-      const uint32_t xh_a = smem_u32(xa), xl_a = xh_a + (uint32_t)a_copy;
+    // ================= MMA issuer: the whole converged warp runs the loop, the MMAs are guarded by elect_one() (bare
+    // UTCHMMA instead of an ELECT / BRA.U.ANY loop per MMA, see gemm_tc.cu::issue_mmas), the chunk ring (BSTAGES = TBUF = 2)
+    // is unrolled so that every descriptor is base + constant =================
+    {
+      static_assert(BSTAGES == 2 && TBUF == 2, "the issue loop is unrolled over a ring of two");
+      constexpr uint32_t idesc = make_idesc_tf32(CHUNK);
+      const bool elected = elect_one();
+      const uint64_t xh_d = make_desc_sw128(smem_u32(xa));
+      const uint64_t xl_d = xh_d + (uint64_t)(a_copy >> 4);
+      const uint64_t ring_d = make_desc_sw128(smem_u32(bring));
       mbar_wait(&sh->a_full, 0);
-      for (int c = 0; c < p.nchunks; ++c) {
-        const int s = c % BSTAGES, a = c % TBUF;
-        mbar_wait(&sh->b_full[s], (uint32_t)(c / BSTAGES) & 1u);
-        mbar_wait(&sh->tmem_empty[a], ((uint32_t)(c / TBUF) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t bh_a = smem_u32(bring) + (uint32_t)(s * b_stage), bl_a = bh_a + (uint32_t)b_copy;
-        const uint32_t dst = tmem_base + (uint32_t)(a * CHUNK);
-        uint32_t acc = 0u;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const uint64_t ah = make_desc_sw128(xh_a + kb * XT_BYTES), al = make_desc_sw128(xl_a + kb * XT_BYTES);
-          const uint64_t bh = make_desc_sw128(bh_a + kb * CHUNK * 128), bl = make_desc_sw128(bl_a + kb * CHUNK * 128);
+      uint32_t par = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.nchunks; c0 += 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adv = (uint64_t)((k * 32) >> 4);
-            umma_tf32(dst, al + adv, bh + adv, idesc, acc);
-            umma_tf32(dst, ah + adv, bl + adv, idesc, 1u);
-            umma_tf32(dst, ah + adv, bh + adv, idesc, 1u);
-            acc = 1u;
+        for (int s = 0; s < 2; ++s) {
+          if (c0 + s < p.nchunks) {
+            mbar_wait(&sh->b_full[s], par);
+            mbar_wait(&sh->tmem_empty[s], par ^ 1u);
+            tc_fence_after();
+            const uint64_t bh_d = ring_d + (uint64_t)((s * b_stage) >> 4), bl_d = bh_d + (uint64_t)(b_copy >> 4);
+            const uint32_t dst = tmem_base + (uint32_t)(s * CHUNK);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              if (kb < nkb) {
+                const uint64_t ao = (uint64_t)((kb * XT_BYTES) >> 4), bo = (uint64_t)((kb * CHUNK * 128) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                  if (elected) {
+                    umma_tf32(dst, xl_d + ao + adv, bh_d + bo + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+                    umma_tf32(dst, xh_d + ao + adv, bl_d + bo + adv, idesc, 1u);
+                    umma_tf32(dst, xh_d + ao + adv, bh_d + bo + adv, idesc, 1u);
+                  }
+                }
+              }
+            }
+            if (elected) {
+              umma_commit_multicast(&sh->b_empty[s], (uint16_t)((1u << CLUSTER) - 1));   // stage consumed, tell every CTA
+              umma_commit(&sh->tmem_full[s]);
+            }
+            __syncwarp();
           }
         }
-        umma_commit_multicast(&sh->b_empty[s], (uint16_t)((1u << CLUSTER) - 1));   // stage consumed, tell every CTA
-        umma_commit(&sh->tmem_full[a]);
+        par ^= 1u;
       }
     }
     __syncwarp();
@@ -977,8 +1000,11 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
   p.divD = FastDiv((uint32_t)D);
   p.dbg = se + (size_t)nchunks * CHUNK + 2;
   {
+    p.debug = 0;
+#ifdef VQS_DEBUG   /* profiling builds only (-DVQS_DEBUG): these bits switch phases off and give WRONG results */
     const char* dbg = getenv("VQS_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
+#endif
   }
   VQS_CUDA(cudaMemsetAsync(se + (size_t)nchunks * CHUNK, 0, 8 * sizeof(float), st));
   VQS_CUDA(cudaMemsetAsync(stats, 0, (size_t)K * (D + 1) * sizeof(float), st));
@@ -991,11 +1017,9 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
     set_error("vq_search_large: codebook of %d codes needs %zu bytes of shared memory", K, smem);
     return VQS_ERR_ARG;
   }
-  static size_t configured = 0;
-  if (smem > configured) {
+  static DevCache configured;
+  if (dev_needs(configured, smem))
     VQS_CUDA(cudaFuncSetAttribute(vq_search_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((p.ntiles + CLUSTER - 1) / CLUSTER * CLUSTER));
@@ -1012,6 +1036,7 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
     VQS_CUDA(cudaLaunchKernelEx(&cfg, vq_search_large_kernel, p));
   }
   VQS_LAUNCH_CHECK();
+#ifdef VQS_DEBUG
   {
     const char* dbg = getenv("VQS_TC_DEBUG");
     if (dbg && (atoi(dbg) & 4)) {   // profiling aid: how many rows needed the exact paths (synchronises!)
@@ -1021,6 +1046,7 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
       fprintf(stderr, "[vq_search_large] N=%lld K=%d: top-2 settlements %.0f, full exact scans %.0f\n", p.N, K, h[0], h[1]);
     }
   }
+#endif
   return 0;
 }
 

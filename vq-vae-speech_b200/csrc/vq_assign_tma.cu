@@ -426,28 +426,33 @@ __global__ void __launch_bounds__(BDT ? NT_BDT : NT, 1) vq_assign_tma_kernel(con
     __syncwarp();
   } else if (warp == MMA_WARP) {
     // ================= MMA issuer: 8 single-pass tf32 MMAs per tile on the raw fp32 words =================
-    if (lane == 0) {
+    // (the whole converged warp runs the loop and the MMAs are guarded by elect_one(): bare UTCHMMA instructions instead of
+    // an ELECT / BRA.U.ANY loop per MMA under `if (lane == 0)`, see gemm_tc.cu::issue_mmas)
+    {
       const uint32_t idesc = make_idesc_tf32(Kpad);
-      const uint32_t cb_a = smem_u32(cbs);
+      const bool elected = elect_one();
+      const uint64_t cb_d = make_desc_sw128(smem_u32(cbs));
+      const uint64_t x_d0 = make_desc_sw128(smem_u32(xs));
+      const uint64_t cb_kb = (uint64_t)((Kpad * 128) >> 4);
       for (int it = 0; it < my_tiles; ++it) {
         const int s = it % NSTAGE, a = it % NGROUP;
         mbar_wait_sleep(&sh->full[s], (uint32_t)(it / NSTAGE) & 1u);
         mbar_wait_sleep(&sh->tmem_empty[a], ((uint32_t)(it / NGROUP) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t x_a = smem_u32(xs + s * TILE_BYTES);
+        const uint64_t x_d = x_d0 + (uint64_t)((s * TILE_BYTES) >> 4);
         const uint32_t dst = tmem_base + (uint32_t)(a * Kpad);
-        uint32_t acc = 0u;
+        if (elected) {
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t ad = make_desc_sw128(x_a + kb * XT), bd = make_desc_sw128(cb_a + kb * Kpad * 128);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t ad = x_d + (uint64_t)((kb * XT) >> 4), bd = cb_d + (uint64_t)kb * cb_kb;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_tf32(dst, ad + (uint64_t)((k * 32) >> 4), bd + (uint64_t)((k * 32) >> 4), idesc, acc);
-            acc = 1u;
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(dst, ad + (uint64_t)((k * 32) >> 4), bd + (uint64_t)((k * 32) >> 4), idesc, (kb | k) ? 1u : 0u);
           }
+          umma_commit(&sh->tmem_full[a]);
+          umma_commit(&sh->empty[s]);
         }
-        umma_commit(&sh->tmem_full[a]);
-        umma_commit(&sh->empty[s]);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -789,8 +794,11 @@ int launch_assign_tma(const float* z, int layout, int B, int T, const float* cb,
   p.Kpad = (K + 15) / 16 * 16;
   p.z = z; p.T = T; p.Q = B / 64; p.TT = 0; p.GB = 0; p.tt_shift = 0;
   {
+    p.debug = 0;
+#ifdef VQS_DEBUG   /* profiling builds only (-DVQS_DEBUG): these bits switch phases off and give WRONG results */
     const char* dbg = getenv("VQS_TMA_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
+#endif
   }
   {
     const char* lg = getenv("VQS_TMA_LAG");
@@ -830,13 +838,12 @@ int launch_assign_tma(const float* z, int layout, int B, int T, const float* cb,
     p.ntiles = (int)((N + TR - 1) / TR);
   }
   const size_t smem = smem_bytes_tma(K, p.Kpad);
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[bdt]) {
+  static DevCache configured[2];
+  if (dev_needs(configured[bdt ? 1 : 0], smem)) {
     if (bdt)
       VQS_CUDA(cudaFuncSetAttribute(vq_assign_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
       VQS_CUDA(cudaFuncSetAttribute(vq_assign_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[bdt] = smem;
   }
   int grid = num_sms();
   if (grid > p.ntiles) grid = p.ntiles;

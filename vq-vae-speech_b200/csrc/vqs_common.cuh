@@ -17,6 +17,22 @@ void count_launch(int n = 1);
 void count_engine(int engine);
 int num_sms();
 
+// Per-DEVICE memo of the dynamic-shared-memory attribute of a kernel (cudaFuncSetAttribute is per device; a process that
+// drives several GPUs must configure each one).  dev_needs(c, bytes): true when the current device has not been configured
+// for at least `bytes` yet (and records it); devices beyond the table are configured on every call.
+struct DevCache {
+  size_t v[16] = {0};
+};
+inline bool dev_needs(DevCache& c, size_t bytes) {
+  int d = -1;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 16) return true;
+  if (bytes > c.v[d]) {
+    c.v[d] = bytes;
+    return true;
+  }
+  return false;
+}
+
 #define VQS_CHECK_ARG(cond, ...)            \
   do {                                      \
     if (!(cond)) {                          \

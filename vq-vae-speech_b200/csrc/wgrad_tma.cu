@@ -340,11 +340,9 @@ int launch_wgrad_tma(const WgradParams& p, float* workspace, cudaStream_t st) {
   q.x_relu = d.x_relu;
   q.M = d.M;
   q.Cred = d.Cred;
-  static bool configured = false;
-  if (!configured) {
+  static DevCache configured;
+  if (dev_needs(configured, WT_SMEM))
     VQS_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
-    configured = true;
-  }
   const int tiles_n = d.ksz * q.cpt, tiles_m = d.M / 128;
   dim3 grid(tiles_n, tiles_m, p.splits);
   VQS_CUDA(launch_pdl(wgrad_tma_kernel, grid, dim3(WT_THREADS), WT_SMEM, st, mapA, mapB, q));

@@ -380,6 +380,25 @@ def blc_to_ncl(x, out=None):
     return out
 
 
+def concat_channels(a, v, out=None):
+    """(B, Ca, L) ++ (B, Cb) repeated over L -> (B, Ca + Cb, L)   (speaker conditioning, deconvolutional_decoder.py:108-111)."""
+    B, Ca, L = a.shape
+    Cb = v.shape[1]
+    if out is None:
+        out = torch.empty(B, Ca + Cb, L, dtype=torch.float32, device=a.device)
+    _call('vqs_concat_channels', (_p(a), _p(v), B, Ca, Cb, L, _p(out)))
+    return out
+
+
+def slice_channels(g, Ca, out=None):
+    """First Ca channels of a (B, C, L) tensor as a contiguous (B, Ca, L) tensor."""
+    B, C, L = g.shape
+    if out is None:
+        out = torch.empty(B, Ca, L, dtype=torch.float32, device=g.device)
+    _call('vqs_slice_channels', (_p(g), B, C, Ca, L, _p(out)))
+    return out
+
+
 def mse_workspace(device):
     return torch.empty(148 * 8 * 8 * 2, dtype=torch.uint8, device=device)
 

@@ -10,8 +10,29 @@ the contract implemented here is SURVEY.md 8e:
 
 Nothing here touches CUDA directly, so the same class runs under gloo on CPU tensors (tests/test_parallel_cpu.py).
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+# The conv / wgrad GEMMs of the step are planned as ONE wave of 144 CTAs with ~200 KB of shared memory each (one per SM);
+# an NCCL kernel CTA cannot share an SM with them, so every SM NCCL takes beyond the 4 spare ones pushes a GEMM into a
+# second wave (round 1, 8 GPUs: the conv_3 dgrad launched next to a gradient bucket took 0.205 ms instead of 0.111).
+# 144 + 4 = 148: the communicator is capped at 4 CTAs.  65 MB of gradients per 3 ms step need ~25 GB/s -- far below what 4
+# CTAs move over NVLink 5 / NVSwitch (NVLS reduces inside the switch).
+NCCL_MAX_CTAS = 4
+
+
+def init_nccl(device, max_ctas=NCCL_MAX_CTAS):
+    """torch.distributed.init_process_group('nccl') for one process per GPU (RANK / WORLD_SIZE / MASTER_* from the
+    environment, as torch.distributed.run sets them) with the communicator capped at `max_ctas` CTAs (see above; the
+    environment variables NCCL_MAX_CTAS / NCCL_MIN_CTAS, when already set by the user, win)."""
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    if max_ctas:
+        os.environ.setdefault('NCCL_MAX_CTAS', str(int(max_ctas)))
+        os.environ.setdefault('NCCL_MIN_CTAS', '1')
+    dist.init_process_group('nccl', device_id=device)
+    return DataParallelComm()
 
 
 class DataParallelComm(object):
@@ -45,6 +66,10 @@ class DataParallelComm(object):
     def wait_buckets(self):
         for w in self._works:
             w.wait()
+        self._works = []
+
+    def abandon(self):
+        """Drops Work handles that were created inside an aborted CUDA-graph capture (they belong to no real launch)."""
         self._works = []
 
     def shard(self, global_batch):

@@ -35,9 +35,13 @@ class FusedTrainStep(object):
     steps for a fixed (batch_size, T) shape."""
 
     def __init__(self, model, batch_size, num_frames, learning_rate, use_graph=True, process_group=None,
-                 betas=(0.9, 0.999), eps=1e-8, precision='3xtf32'):
+                 betas=(0.9, 0.999), eps=1e-8, precision='3xtf32', separate_target=None):
         """precision: GEMM engine of the conv / wgrad GEMMs -- '3xtf32' (tcgen05, fp32-accurate split; default), 'tf32'
-        (tcgen05 single pass: cuDNN's default numerics for the reference on a GPU) or 'fp32' (exact FMA on CUDA cores)."""
+        (tcgen05 single pass: cuDNN's default numerics for the reference on a GPU) or 'fp32' (exact FMA on CUDA cores).
+        separate_target: the reference trains against data['output_features'] (convolutional_trainer.py:47), which every
+        shipped experiment sets equal to the input features; True = step() takes its own target batch (B, T, F_out), False
+        = the reconstruction target is the input batch (one copy and one layout pass fewer per step).  Default: True only
+        when the model's output and input feature counts differ."""
         self.model = model
         self.precision = precision
         self.B, self.T = int(batch_size), int(num_frames)
@@ -48,9 +52,11 @@ class FusedTrainStep(object):
         if self.dev.type != 'cuda':
             raise RuntimeError('FusedTrainStep needs the model on a CUDA device (no CPU path)')
         enc, dec, vq = model._encoder, model._decoder, model._vq
-        if getattr(dec, '_use_speaker_conditioning', False):
-            raise NotImplementedError('use_speaker_conditioning draws a fresh random embedding on the host every forward '
-                                      '(global_conditioning.py:34): module path only, not the captured step')
+        # use_speaker_conditioning (deconvolutional_decoder.py:108-111): the reference draws a fresh random speaker
+        # embedding on the host RNG every forward (global_conditioning.py:34); step() draws the same one and uploads the
+        # rows of this batch into a static buffer, like the jitter plan -- the captured schedule only reads that buffer
+        self.use_speaker = bool(getattr(dec, '_use_speaker_conditioning', False))
+        self.separate_target = separate_target
         self.is_ema = isinstance(vq, VectorQuantizerEMA)
         self.nl = enc._residual_stack._num_residual_layers
         if self.nl < 1:
@@ -100,6 +106,7 @@ class FusedTrainStep(object):
         self.flat_vmax = torch.zeros(total, dtype=torch.float32, device=dev)
         self.opt_step = torch.zeros(1, dtype=torch.int64, device=dev)
         self.grads, self.param_names = {}, []
+        self.param_offsets = {}          # name -> offset of the parameter in the flat buffers (p, g, m, v, vmax)
         first_decoder = None
         with torch.no_grad():
             for (name, p), off in zip(params, offs):
@@ -108,6 +115,7 @@ class FusedTrainStep(object):
                 p.data = view
                 self.grads[name] = self.flat_g[off:off + p.numel()].view_as(p)
                 self.param_names.append(name)
+                self.param_offsets[name] = off
                 if first_decoder is None and name.startswith('_decoder.'):
                     first_decoder = off
         # weight-normalised convs (use_kaiming_normal): the optimizer owns weight_g / weight_v; the effective
@@ -168,8 +176,12 @@ class FusedTrainStep(object):
         Tq = T // 2 + 1
         L2 = 2 * Tq
         self.dims = dict(B=B, T=T, Fi=Fi, C=C, R_enc=R_enc, R_dec=R_dec, D=D, K=K, Fo=Fo, Tq=Tq, L2=L2)
-        if Fo != Fi:
-            raise NotImplementedError('the fused step trains input == target features (MFCC-39 both sides)')
+        if self.separate_target is None:
+            self.separate_target = Fo != Fi
+        if Fo != Fi and not self.separate_target:
+            raise ValueError('output features (%d) differ from input features (%d): the step needs separate_target=True' % (Fo, Fi))
+        Dd = m._decoder._conv_1.in_channels           # D, + 40 speaker features when use_speaker_conditioning
+        self.dims['Dd'] = Dd
         if L2 + 3 < T:
             raise RuntimeError('decoder output shorter than the input')
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
@@ -177,6 +189,12 @@ class FusedTrainStep(object):
         b = self.buf = {}
         b['x_in'] = f(B, T, Fi)                  # the (B, T, F) feature batch as the loader delivers it
         b['x'] = f(B, Fi, T)
+        if self.separate_target:
+            b['t_in'], b['target'] = f(B, T, Fo), f(B, Fo, T)
+        if self.use_speaker:
+            b['spk'] = torch.zeros(B, Dd - D, dtype=torch.float32, device=dev)
+            b['qcat'], b['gqcat'] = f(B, Dd, Tq), f(B, Dd, Tq)
+            self.host_spk = torch.zeros(B, Dd - D, dtype=torch.float32).pin_memory()
         b['a1'], b['h2'], b['m2'] = f(B, C, T), f(B, C, T), u8(B, C, T)
         b['a3'], b['h4'], b['m4'], b['h5'], b['m5'] = f(B, C, Tq), f(B, C, Tq), u8(B, C, Tq), f(B, C, Tq), u8(B, C, Tq)
         for i in range(self.nl):
@@ -225,7 +243,7 @@ class FusedTrainStep(object):
                 self.wperm[(name, role)] = (f(numel) if mode is not None else None, tap, mode)
         ws_bytes = 16
         for (M, Cr, k, La) in [(C, Fi, 3, T), (C, C, 3, T), (C, C, 4, Tq), (C, C, 3, Tq), (R_enc, C, 3, Tq),
-                               (C, R_enc, 1, Tq), (D, C, 3, Tq), (C, D, 3, Tq), (R_dec, C, 3, L2), (C, R_dec, 1, L2),
+                               (C, R_enc, 1, Tq), (D, C, 3, Tq), (C, Dd, 3, Tq), (R_dec, C, 3, L2), (C, R_dec, 1, L2),
                                (C, C, 3, L2), (C, C, 3, L2), (C, Fo, 2, L2 + 2)]:
             ws_bytes = max(ws_bytes, ops.wgrad_workspace_bytes(M, Cr, k, B, La))
         self.ws_wgrad = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -287,6 +305,8 @@ class FusedTrainStep(object):
 
         # ---- 1. encoder forward (convolutional_encoder.py:118-146) ----
         ops.blc_to_ncl(b['x_in'], b['x'])                                            # vq_vae.py:118
+        if self.separate_target:
+            ops.blc_to_ncl(b['t_in'], b['target'])                                   # trainer.py:47
         cfwd(b['x'], E + '_conv_1.weight', P(E + '_conv_1.bias'), 1, 1, out=b['a1'], relu=True)
         cfwd(b['a1'], E + '_conv_2.weight', P(E + '_conv_2.bias'), 1, 1, out=b['h2'], relu=True,
                          mask_out=b['m2'], add_post=b['a1'])
@@ -327,6 +347,9 @@ class FusedTrainStep(object):
         if self.use_jitter:
             ops.jitter_fwd(b['q'], b['jitter_src'], b['qj'])
             dec_in = b['qj']
+        if self.use_speaker:                                                         # decoder.py:108-111
+            ops.concat_channels(dec_in, b['spk'], out=b['qcat'])
+            dec_in = b['qcat']
         cfwd(dec_in, DEC + '_conv_1.weight', P(DEC + '_conv_1.bias'), 1, 1, out=b['d1'])
         ops.upsample2_fwd(b['d1'], b['u'])
         xd = [b['u']] + [b['d_x%d' % i] for i in range(1, nl)]
@@ -343,7 +366,8 @@ class FusedTrainStep(object):
                           out=b['recon'], splitk_ws=ws)                                          # trimmed to T (vq_vae.py:133-137)
 
         # ---- 4. loss (trainer.py:54-56): MSE against the input features, gradient in the same pass ----
-        ops.mse_fwd_bwd(b['recon'], b['x'], (Fi * T, T, 1), 1.0, b['recon_loss'], b['g_recon'], self.ws_mse)
+        ops.mse_fwd_bwd(b['recon'], b['target'] if self.separate_target else b['x'], (Fo * T, T, 1), 1.0, b['recon_loss'],
+                        b['g_recon'], self.ws_mse)
 
         # ---- 5. decoder backward ----
         gq2 = self._view('gA2', C, Lt2)
@@ -377,11 +401,14 @@ class FusedTrainStep(object):
         F.conv1d_wgrad(gd1, dec_in, G[DEC + '_conv_1.weight'], 1, 1, ws)
         ops.bias_grad(gd1, G[DEC + '_conv_1.bias'])
         gq = b['gq']
-        if self.use_jitter:
-            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=b['gqj'], splitk_ws=ws)
-            ops.jitter_bwd(b['gqj'], b['jitter_src'], gq)
+        g_dec_in = b['gqj'] if self.use_jitter else gq
+        if self.use_speaker:       # gradient of the concatenation: its first D channels (the speaker features are constants)
+            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=b['gqcat'], splitk_ws=ws)
+            ops.slice_channels(b['gqcat'], D, out=g_dec_in)
         else:
-            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=gq, splitk_ws=ws)
+            cdgrad(gd1, DEC + '_conv_1.weight', Tq, 1, 1, out=g_dec_in, splitk_ws=ws)
+        if self.use_jitter:
+            ops.jitter_bwd(b['gqj'], b['jitter_src'], gq)
         self._emit_wn_fold(*self.buckets['dec_rest'])
         if self.world > 1:       # decoder gradients are complete: allreduce the rest of them under the encoder's backward
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_rest']))
@@ -464,17 +491,40 @@ class FusedTrainStep(object):
     def _run_schedule(self):
         ops.replay(self.schedule)
 
-    def load_batch(self, x_btf, non_blocking=True):
-        """Stages one (B, T, F) feature batch (host pinned or device tensor) into the static input buffer."""
+    def load_batch(self, x_btf, target_btf=None, non_blocking=True):
+        """Stages one (B, T, F) feature batch (host pinned or device tensor) into the static input buffer, and the
+        reconstruction target (B, T, F_out) when the step was built with separate_target."""
         self.buf['x_in'].copy_(x_btf, non_blocking=non_blocking)
+        if self.separate_target:
+            if target_btf is None:
+                raise ValueError('this step was built with separate_target: pass the target batch (trainer.py:47)')
+            self.buf['t_in'].copy_(target_btf, non_blocking=non_blocking)
+        elif target_btf is not None:
+            raise ValueError('this step reconstructs its input; build it with separate_target=True to pass a target')
+
+    def set_speaker_features(self, speaker_dic, speaker_id):
+        """Draws the reference's per-forward random speaker embedding on the host RNG -- the same nn.Embedding constructor
+        + normal_(0, 0.1) sequence as global_conditioning.py:34,62-65, so the same torch seed gives the same features --
+        and uploads the rows of this batch's speakers."""
+        emb = torch.nn.Embedding(len(speaker_dic), self.dims['Dd'] - self.dims['D'], padding_idx=None)
+        emb.weight.data.normal_(0, 0.1)
+        rows = emb.weight.data[torch.as_tensor(speaker_id).view(self.B, -1)[:, 0].long().cpu()]
+        self.host_spk.copy_(rows)
+        self.buf['spk'].copy_(self.host_spk, non_blocking=True)
 
     def set_jitter_plan(self, src):
         self.buf['jitter_src'].copy_(torch.as_tensor(np.asarray(src, dtype=np.int32)), non_blocking=True)
 
-    def step(self, x_btf=None):
-        """One training step on the batch currently staged (or on x_btf).  Returns nothing; `losses()` reads results."""
+    def step(self, x_btf=None, target_btf=None, speaker_dic=None, speaker_id=None):
+        """One training step (convolutional_trainer.py:44-74) on the batch currently staged (or on x_btf; target_btf =
+        data['output_features'] when built with separate_target; speaker_dic / speaker_id as ConvolutionalVQVAE.forward
+        takes them, used only with use_speaker_conditioning).  Returns nothing; `losses()` reads results."""
         if x_btf is not None:
-            self.load_batch(x_btf)
+            self.load_batch(x_btf, target_btf)
+        if self.use_speaker:
+            if speaker_dic is None or speaker_id is None:
+                raise ValueError('use_speaker_conditioning: step() needs speaker_dic and speaker_id')
+            self.set_speaker_features(speaker_dic, speaker_id)
         if self.use_jitter:
             self.last_plan = jitter_plan(self.dims['Tq'], self.model._decoder._jitter._probability)
             self.set_jitter_plan(self.last_plan)
@@ -489,12 +539,31 @@ class FusedTrainStep(object):
                     warnings.warn('CUDA-graph capture of the training step failed (%s); replaying launch by launch' % exc)
                     self.use_graph = False
                     self.graph = None
-                    torch.cuda.synchronize()
+                    torch.cuda.synchronize()            # the aborted capture has ended; nothing of it ran
+                    self.comm.abandon()                 # Work handles created while capturing belong to no real launch
                     self._run_schedule()
                     self.steps_done += 1
                     return
             self.graph.replay()
         self.steps_done += 1
+
+    def set_hyper_parameters(self, lr=None, betas=None, eps=None):
+        """Changes the optimizer's hyper-parameters.  They are arguments of the recorded vqs_amsgrad_step launch, so the
+        schedule entry is rewritten and a captured graph is dropped (re-captured on the next step)."""
+        if lr is not None:
+            self.lr = float(lr)
+        if betas is not None:
+            self.betas = (float(betas[0]), float(betas[1]))
+        if eps is not None:
+            self.eps = float(eps)
+        for i, (fn, args, keep) in enumerate(self.schedule):
+            if fn is not None and fn.__name__ == 'vqs_amsgrad_step':
+                a = list(args)
+                a[8:12] = [self.lr, self.betas[0], self.betas[1], self.eps]
+                self.schedule[i] = (fn, tuple(a), keep)
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph = None
 
     def _capture(self):
         """Captures the recorded schedule into one CUDA graph.  The schedule is pure (no host sync, no allocation), and
@@ -528,30 +597,36 @@ class FusedTrainStep(object):
 # ------------------------------------------------------------------------------------------------
 # checkpoint wire format of the reference (convolutional_trainer.py:76-86, pipeline_factory.py:108-126)
 # ------------------------------------------------------------------------------------------------
-def optimizer_state_dict(step):
-    """torch.optim.Adam(amsgrad=True)-compatible state_dict of a FusedTrainStep: the flat AMSGrad buffers are sliced back
-    into per-parameter exp_avg / exp_avg_sq / max_exp_avg_sq, indexed in model.parameters() order like torch does, so
-    `torch.optim.Adam(model.parameters(), lr, amsgrad=True).load_state_dict(...)` accepts it (the reference resumes
-    exactly that way, pipeline_factory.py:118-120).  Parameters Adam never stepped (EMA codebook) have no state."""
-    order = []
-    seen = set()
+def _param_order(step):
+    order, seen = [], set()
     for name, p in step.model.named_parameters():
         if id(p) not in seen:
             seen.add(id(p))
             order.append(name)
+    return order
+
+
+def optimizer_state_dict(step):
+    """torch.optim.Adam(amsgrad=True)-compatible state_dict of a FusedTrainStep: the flat AMSGrad buffers are sliced back
+    into per-parameter exp_avg / exp_avg_sq / max_exp_avg_sq, indexed in model.parameters() order like torch does, so
+    `torch.optim.Adam(model.parameters(), lr, amsgrad=True).load_state_dict(...)` accepts it (the reference resumes
+    exactly that way, pipeline_factory.py:118-120).  Parameters Adam never stepped (EMA codebook) have no state.  Only the
+    named parameters the optimizer owns are listed (step.param_names: for weight-normalised convs weight_g / weight_v, not
+    the effective-weight scratch buffers), at their offsets in the flat buffers."""
+    order = _param_order(step)
+    params = dict(step.model.named_parameters())
     state = {}
     nstep = int(step.opt_step.item())
-    for name, g in step.grads.items():
-        off = g.storage_offset()
-        n = g.numel()
-        if nstep == 0:
-            continue
-        state[order.index(name)] = {
-            'step': torch.tensor(float(nstep)),
-            'exp_avg': step.flat_m[off:off + n].view_as(g).clone(),
-            'exp_avg_sq': step.flat_v[off:off + n].view_as(g).clone(),
-            'max_exp_avg_sq': step.flat_vmax[off:off + n].view_as(g).clone(),
-        }
+    if nstep > 0:
+        for name in step.param_names:
+            off, p = step.param_offsets[name], params[name]
+            n = p.numel()
+            state[order.index(name)] = {
+                'step': torch.tensor(float(nstep)),
+                'exp_avg': step.flat_m[off:off + n].view_as(p).clone(),
+                'exp_avg_sq': step.flat_v[off:off + n].view_as(p).clone(),
+                'max_exp_avg_sq': step.flat_vmax[off:off + n].view_as(p).clone(),
+            }
     group = dict(lr=step.lr, betas=tuple(step.betas), eps=step.eps, weight_decay=0, amsgrad=True, maximize=False,
                  foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False,
                  params=list(range(len(order))))
@@ -559,25 +634,29 @@ def optimizer_state_dict(step):
 
 
 def load_optimizer_state_dict(step, sd):
-    """Inverse of optimizer_state_dict: accepts a torch Adam(amsgrad=True) state_dict (e.g. from a reference checkpoint)."""
-    order = []
-    seen = set()
-    for name, p in step.model.named_parameters():
-        if id(p) not in seen:
-            seen.add(id(p))
-            order.append(name)
+    """Inverse of optimizer_state_dict: accepts a torch Adam(amsgrad=True) state_dict (e.g. from a reference checkpoint),
+    including its hyper-parameters -- optimizer.load_state_dict restores lr / betas / eps of the checkpoint
+    (pipeline_factory.py:118-120), so does this."""
+    order = _param_order(step)
     nstep = 0
     for idx, st in sd['state'].items():
         name = order[int(idx)]
-        if name not in step.grads:
+        if name not in step.param_offsets:
             continue
-        g = step.grads[name]
-        off, n = g.storage_offset(), g.numel()
+        off, n = step.param_offsets[name], st['exp_avg'].numel()
         step.flat_m[off:off + n].copy_(st['exp_avg'].reshape(-1))
         step.flat_v[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
         step.flat_vmax[off:off + n].copy_(st['max_exp_avg_sq'].reshape(-1))
         nstep = max(nstep, int(float(st['step'])))
     step.opt_step.fill_(nstep)
+    groups = sd.get('param_groups') or []
+    if groups:
+        g0 = groups[0]
+        if not g0.get('amsgrad', True):
+            import warnings
+            warnings.warn('checkpoint optimizer has amsgrad=False; the fused step always runs Adam(amsgrad=True) '
+                          '(convolutional_trainer.py:41-42)')
+        step.set_hyper_parameters(lr=g0.get('lr'), betas=g0.get('betas'), eps=g0.get('eps'))
 
 
 def save_checkpoint(step, path, experiment_name, epoch, train_res_recon_error=-1, train_res_perplexity=-1):
