@@ -469,8 +469,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += t1[j];
           tmem_ld32(ta, t1);
+          // main term: undo the expected truncation loss of its (4 nkb / 3) MMAs per accumulator, then the correction terms
+          // (a stride-2 dgrad, l_div = 2, reads a zero operand for every other tap: half of its MMAs add nothing)
+          int n_mma = (4 * nkb + 2) / 3;
+          if constexpr (MODE == 0) n_mma /= prm.p.d.l_div;
+          const float comp = tf32x3_comp(n_mma);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += t1[j];
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], comp, t1[j]);
         } else {
           tmem_ld32(ta, v);
         }

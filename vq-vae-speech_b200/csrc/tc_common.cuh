@@ -115,6 +115,17 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
 __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
   return (uint32_t)(r * 128 + ((((k >> 2) ^ (r & 7)) << 4) | ((k & 3) << 2)));
 }
+// Truncation-loss compensation of a 3xTF32 accumulation.  tcgen05.mma adds into its fp32 TMEM accumulator with TRUNCATION
+// (the smaller addend loses its low bits toward zero), so every sum comes out slightly too small: measured against fp64 on
+// sign-uncorrelated (normal) operands the signed relative bias of a main-term accumulator that received n MMAs is
+// -(3.0e-7 + 1.607e-8 n), linear in n to three digits from n = 1 to n = 384 (profiles/r02m_tc_bias_before.txt; K = 2304:
+// -1.84e-6).  One GEMM is inside the 1e-5 bar either way, but the loss is systematic, so it compounds LINEARLY over the
+// ~17 GEMMs of the backward chain (4e-5 on the encoder gradients of the 768-wide model).  The epilogues multiply the sum of
+// the main-term accumulators by 1 + that expected loss; the residual bias is then a few 1e-8 (r02m_tc_bias_after.txt).
+// Operands whose products all share one sign lose more (slope 5.9e-8 per MMA): those stay under-corrected, never over.
+__device__ __forceinline__ float tf32x3_comp(int n_mmas_per_accumulator) {
+  return 1.0f + (3.0e-7f + 1.607e-8f * (float)n_mmas_per_accumulator);
+}
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 

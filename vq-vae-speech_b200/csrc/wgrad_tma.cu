@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tma_kernel(const __grid_c
       mbar_wait_sleep(&sh->tmem_full, 0);
       tc_fence_after();
     }
+    const float comp = tf32x3_comp((4 * nkb + 2) / 3);
 #pragma unroll 1
     for (int cb = 0; cb < 64; cb += 16) {
       float r[16];
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tma_kernel(const __grid_c
         wt_tmem_ld16(ta, t3);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = ((r[e] + t1[e]) + t2[e]) + t3[e];
+        for (int e = 0; e < 16; ++e) r[e] = fmaf((r[e] + t1[e]) + t2[e], comp, t3[e]);   // tc_common.cuh::tf32x3_comp
       } else {
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = 0.f;
