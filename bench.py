@@ -254,6 +254,7 @@ def workload_config(args, world, batch_override=None):
             'per_gpu_batch': b, 'global_batch': b * world, 'frames': args.frames, 'decay': args.decay,
             'use_jitter': bool(getattr(args, 'jitter', False)),
             'parallelism': 'dp%d' % world, 'gemm_engine': getattr(args, 'precision', None),
+            'dp_exchange': getattr(args, 'dp_exchange', None),
             'l2': 'no explicit flush: every step streams weights + optimizer state + activations >> 126 MB L2'}
 
 
@@ -352,6 +353,10 @@ def run_b200(args):
     model = ConvolutionalVQVAE(cfg, dev).to(dev).train()
     B, T = args.batch, args.frames
     eng = FusedTrainStep(model, B, T, cfg['learning_rate'], precision=args.precision)
+    args.dp_exchange = None if world == 1 else (
+        'own kernels over NVLS multicast / peer memory (csrc/dp_nvls.cu): statistics summed through peer pointers, gradient '
+        'allreduce folded into a sharded AMSGrad kernel (multimem.ld_reduce / multimem.st)' if eng.nvls is not None else
+        'NCCL allreduces captured into the CUDA graph (4 gradient buckets + statistics)')
     gen = torch.Generator().manual_seed(1234 + rank)        # each rank trains on its own shard of the global batch
     host = [torch.randn(B, T, 39, generator=gen).pin_memory() for _ in range(8)]
     devb = [h.to(dev) for h in host]
@@ -504,17 +509,21 @@ def dp_parity_check(eng, devb, world):
       * the replicated state -- flat parameters, AMSGrad moments, codebook, EMA state -- is BIT-identical on all ranks after
         the timed steps (DataParallelComm.assert_replicated: MIN- and MAX-allreduce agree);
       * one more step from the same state gives bit-identical parameters whether it is replayed from the captured CUDA graph
-        (NCCL allreduces inside the graph) or issued launch by launch with eager NCCL calls -- the eager path is the one the
-        2-rank oracle test pins to the per-shard contract (tests/test_parallel_gpu.py, SURVEY 8e);
+        (the exchange kernels / NCCL allreduces inside the graph) or issued launch by launch -- the launch-by-launch path is
+        the one the 2-rank oracle tests pin to the per-shard contract (tests/test_parallel_gpu.py, SURVEY 8e);
       * every rank's losses are finite and the EMA statistics of the step sum to world x rows (global counts).
     Raises on failure; returns the summary that goes into the JSON line."""
     import torch
     import torch.distributed as dist
     comm, vq = eng.comm, eng.model._vq
-    state = [eng.flat_p, eng.flat_m, eng.flat_v, eng.flat_vmax, eng.opt_step]
+    replicated = [eng.flat_p, eng.opt_step]
     if eng.is_ema:
-        state += [vq._embedding.weight.data, vq._ema_w.data, vq._ema_cluster_size]
-    for i, t in enumerate(state):
+        replicated += [vq._embedding.weight.data, vq._ema_w.data, vq._ema_cluster_size]
+    moments = [eng.flat_m, eng.flat_v, eng.flat_vmax]
+    if getattr(eng, 'nvls', None) is None:
+        replicated += moments                     # (with the NVLS exchange the AMSGrad moments are sharded over the ranks)
+    state = replicated + (moments if getattr(eng, 'nvls', None) is not None else [])
+    for i, t in enumerate(replicated):
         comm.assert_replicated(t.float() if t.dtype != torch.float32 else t, 'replicated state %d' % i)
     saved = [t.clone() for t in state]
     eng.load_batch(devb[0])
@@ -539,8 +548,9 @@ def dp_parity_check(eng, devb, world):
            'rank0_losses_graph': la, 'rank0_losses_eager': lb}
     if not (ok_same and ok_finite and counts == rows):
         raise RuntimeError('data-parallel parity check failed: %r' % (out,))
-    for i, t in enumerate(state):
+    for i, t in enumerate(replicated):
         comm.assert_replicated(t.float() if t.dtype != torch.float32 else t, 'replicated state %d after the check' % i)
+    out['exchange'] = 'nvls' if getattr(eng, 'nvls', None) is not None else 'nccl'
     return out
 
 

@@ -58,6 +58,41 @@ long long vqs_launch_count(void);
 long long vqs_engine_count(int engine);
 
 /* ------------------------------------------------------------------------------------------------ */
+/* data-parallel exchange over NVLink / NVSwitch peer memory (csrc/dp_nvls.cu)                        */
+/* ------------------------------------------------------------------------------------------------ */
+/* The reference has no working multi-GPU path (its nn.DataParallel wrap is dead code, pipeline_factory.py:56-61); these
+ * entry points implement the data-parallel contract of SURVEY.md 8e -- EMA statistics summed over shards, gradients
+ * averaged, replicas bit-identical -- with this library's own kernels on symmetric buffers (every rank allocates the same
+ * buffer; rank r's copy is mapped into every process, and the whole set additionally behind one NVLS multicast address).
+ * The caller (parallel.py, through torch.distributed._symmetric_memory) owns the mappings.  One process per GPU, at most
+ * VQS_DP_MAX_WORLD GPUs of one NVSwitch domain. */
+#define VQS_DP_MAX_WORLD 8
+#define VQS_DP_CHANNELS 4        /* independent barrier sequences */
+#define VQS_DP_PAD_WORD0 256     /* first 32-bit word of the signal pad this library uses (VQS_DP_CHANNELS * VQS_DP_MAX_WORLD words) */
+typedef struct {
+  int rank, world;
+  void* peer_pads[VQS_DP_MAX_WORLD];   /* peer_pads[r]: rank r's signal pad as mapped into THIS process (r == rank: own pad) */
+  unsigned int* epochs;                /* >= VQS_DP_CHANNELS counters in local device memory, zero-initialised once */
+} vqs_dp_ctx;
+typedef struct {
+  const void* p[VQS_DP_MAX_WORLD];     /* p[r]: rank r's copy of a symmetric buffer as mapped into this process */
+} vqs_dp_ptrs;
+/* Cross-GPU barrier on `stream`: returns (on the device) once every rank's stream has reached its matching call. */
+int vqs_dp_barrier(const vqs_dp_ctx* ctx, int channel, vqs_stream_t stream);
+/* dst[i] = sum over ranks, in rank order, of rank r's src vector (n floats) -- bit-identical on every rank.  Starts with a
+ * barrier on `channel` (all vectors complete).  dst is local memory.  Used for the packed [counts | dw] EMA statistics. */
+int vqs_dp_allreduce_small(const vqs_dp_ctx* ctx, const vqs_dp_ptrs* src, float* dst, long long n, int channel,
+                           vqs_stream_t stream);
+/* Adam(amsgrad=True) step (convolutional_trainer.py:41-42,68) fused with the gradient allreduce: barrier(ch_before); rank r
+ * updates elements [r n/W, (r+1) n/W) of the flat buffers with g = multimem.ld_reduce(mc_g) / W (the NVSwitch adds the W
+ * gradient copies) and writes the new parameters to every GPU through mc_p (multimem.st); barrier(ch_after).  mc_p / mc_g:
+ * NVLS multicast addresses of the symmetric parameter / gradient buffers; p_local: this rank's copy of the parameters;
+ * m, v, vmax: LOCAL optimizer state (only this rank's slice is ever touched: the state is sharded over the ranks). */
+int vqs_dp_amsgrad_step(const vqs_dp_ctx* ctx, float* mc_p, const float* p_local, const float* mc_g, float* m, float* v,
+                        float* vmax, long long n, long long* step, int inc_step, double lr, double beta1, double beta2,
+                        double eps, int ch_before, int ch_after, vqs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* VQ bottleneck                                                                                    */
 /* ------------------------------------------------------------------------------------------------ */
 /* Row layouts.  FLAT_ND: z is a contiguous (N, D) matrix, N = B*T.

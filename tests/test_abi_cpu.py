@@ -41,10 +41,11 @@ def test_struct_layout_matches_c():
 #include <stddef.h>
 #include "vqs_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(vqs_conv_gemm_desc), offsetof(vqs_conv_gemm_desc, x_sb),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(vqs_conv_gemm_desc), offsetof(vqs_conv_gemm_desc, x_sb),
          offsetof(vqs_conv_gemm_desc, out), offsetof(vqs_conv_gemm_desc, precision),
          sizeof(vqs_wgrad_desc), offsetof(vqs_wgrad_desc, dW), offsetof(vqs_conv_gemm_desc, splitk_ws),
-         offsetof(vqs_conv_gemm_desc, splitk_ws_bytes), sizeof(vqs_permute_item));
+         offsetof(vqs_conv_gemm_desc, splitk_ws_bytes), sizeof(vqs_permute_item),
+         sizeof(vqs_dp_ctx), offsetof(vqs_dp_ctx, peer_pads), offsetof(vqs_dp_ctx, epochs), sizeof(vqs_dp_ptrs));
   return 0;
 }'''
     import tempfile
@@ -56,7 +57,10 @@ int main(void) {
         vals = [int(v) for v in subprocess.check_output([exe]).split()]
     C, W = _lib.ConvGemmDesc, _lib.WgradDesc
     assert vals == [ctypes.sizeof(C), C.x_sb.offset, C.out.offset, C.precision.offset, ctypes.sizeof(W), W.dW.offset,
-                    C.splitk_ws.offset, C.splitk_ws_bytes.offset, ctypes.sizeof(_lib.PermuteItem)]
+                    C.splitk_ws.offset, C.splitk_ws_bytes.offset, ctypes.sizeof(_lib.PermuteItem),
+                    ctypes.sizeof(_lib.DpCtx), _lib.DpCtx.peer_pads.offset, _lib.DpCtx.epochs.offset,
+                    ctypes.sizeof(_lib.DpPtrs)]
+    assert (_lib.DP_MAX_WORLD, _lib.DP_CHANNELS, _lib.DP_PAD_WORD0) == (8, 4, 256)      # VQS_DP_* of the header
 
 
 def test_argument_validation_without_gpu():

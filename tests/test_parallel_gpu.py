@@ -111,10 +111,18 @@ def _nccl_worker(rank, world, port, ret):
                 grads0 = {k: (v * eng.comm.grad_scale).cpu().numpy() for k, v in eng.gradients().items()}
         assert eng.graph is not None
         vq = model._vq
-        for t, what in ((eng.flat_p, 'parameters'), (eng.flat_m, 'exp_avg'), (eng.flat_vmax, 'max_exp_avg_sq'),
-                        (vq._embedding.weight.data, 'codebook'), (vq._ema_cluster_size, 'cluster sizes')):
+        checks = [(eng.flat_p, 'parameters'), (vq._embedding.weight.data, 'codebook'), (vq._ema_cluster_size, 'cluster sizes')]
+        if eng.nvls is None:                               # (the NVLS exchange shards the AMSGrad moments over the ranks)
+            checks += [(eng.flat_m, 'exp_avg'), (eng.flat_vmax, 'max_exp_avg_sq')]
+        for t, what in checks:
             comm.assert_replicated(t, what)
-        ret[rank] = dict(steps=res, grads0=grads0, cs=vq._ema_cluster_size.cpu().numpy(),
+        # the optimizer state a checkpoint would hold is complete and identical on both ranks either way (collective)
+        from vq_vae_speech_b200.trainer import optimizer_state_dict
+        sd = optimizer_state_dict(eng)
+        flat = torch.cat([st['exp_avg_sq'].reshape(-1) for _, st in sorted(sd['state'].items())])
+        comm.assert_replicated(flat, 'gathered exp_avg_sq')
+        assert float(flat.abs().sum()) > 0
+        ret[rank] = dict(steps=res, grads0=grads0, cs=vq._ema_cluster_size.cpu().numpy(), nvls=eng.nvls is not None,
                          W=vq._embedding.weight.detach().cpu().numpy())
         dist.barrier()
         torch.cuda.synchronize()

@@ -51,6 +51,18 @@ class PermuteItem(Structure):
 
 PERMUTE_MAX_ITEMS = 32
 
+DP_MAX_WORLD, DP_CHANNELS, DP_PAD_WORD0 = 8, 4, 256
+
+
+class DpCtx(Structure):
+    """struct vqs_dp_ctx (include/vqs_b200.h)."""
+    _fields_ = [('rank', c_int), ('world', c_int), ('peer_pads', c_void_p * DP_MAX_WORLD), ('epochs', c_void_p)]
+
+
+class DpPtrs(Structure):
+    """struct vqs_dp_ptrs (include/vqs_b200.h)."""
+    _fields_ = [('p', c_void_p * DP_MAX_WORLD)]
+
 # name -> (restype, argtypes); every symbol include/vqs_b200.h declares
 PROTOTYPES = {
     'vqs_version': (c_int, []),
@@ -91,6 +103,10 @@ PROTOTYPES = {
     'vqs_weight_norm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'vqs_weight_norm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'vqs_normalize_features': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    'vqs_dp_barrier': (c_int, [c_void_p, c_int, c_void_p]),
+    'vqs_dp_allreduce_small': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    'vqs_dp_amsgrad_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                    c_void_p, c_int, c_double, c_double, c_double, c_double, c_int, c_int, c_void_p]),
     'vqs_amsgrad_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int,
                                  c_double, c_double, c_double, c_double, c_double, c_void_p]),
 }

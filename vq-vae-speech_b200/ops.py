@@ -418,6 +418,25 @@ def amsgrad_step(p, g, m, v, vmax, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, g
                                             float(g_scale)))
 
 
+def dp_barrier(ctx, channel):
+    """Cross-GPU barrier on the current stream (csrc/dp_nvls.cu).  ctx: parallel.NvlsExchange.ctx (kept alive by the caller)."""
+    _call('vqs_dp_barrier', (ctypes.byref(ctx), int(channel)), ctx)
+
+
+def dp_allreduce_small(ctx, src_ptrs, dst, channel):
+    """dst (local) = sum over ranks, in rank order, of the symmetric vector behind src_ptrs (a _lib.DpPtrs)."""
+    _call('vqs_dp_allreduce_small', (ctypes.byref(ctx), ctypes.byref(src_ptrs), _p(dst), dst.numel(), int(channel)),
+          (ctx, src_ptrs))
+
+
+def dp_amsgrad_step(ctx, mc_p, p_local, mc_g, m, v, vmax, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, inc_step=True,
+                    ch_before=1, ch_after=2):
+    """Adam(amsgrad=True) fused with the gradient allreduce over the NVLS multicast mappings mc_p / mc_g (addresses)."""
+    _call('vqs_dp_amsgrad_step', (ctypes.byref(ctx), ctypes.c_void_p(int(mc_p)), _p(p_local), ctypes.c_void_p(int(mc_g)),
+                                  _p(m), _p(v), _p(vmax), p_local.numel(), _p(step, torch.int64), int(inc_step), float(lr),
+                                  float(beta1), float(beta2), float(eps), int(ch_before), int(ch_after)), ctx)
+
+
 def normalize_features(x64, mean64, std64, out=None):
     """(x - mean) / std in float64 on the device, stored as float32 (the reference normalises in numpy float64 and casts
     with .float()): x64 (..., F) float64, mean64 / std64 (F,) float64."""

@@ -35,6 +35,105 @@ def init_nccl(device, max_ctas=NCCL_MAX_CTAS):
     return DataParallelComm()
 
 
+class NvlsExchange(object):
+    """Symmetric buffers + signal pads for the library's own data-parallel kernels (csrc/dp_nvls.cu): every rank allocates
+    the same buffers through torch.distributed._symmetric_memory (CUDA VMM + fabric handles; torch is used for the memory
+    plumbing only), which maps each rank's copy into every process and the whole set behind one NVLS multicast address.
+    Needs the NCCL backend, one process per GPU, <= 8 GPUs of one NVSwitch domain, multicast support."""
+
+    def __init__(self, process_group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._symm = symm_mem
+        self.pg = process_group if process_group is not None else dist.group.WORLD
+        self.group_name = self.pg.group_name
+        self.world, self.rank = dist.get_world_size(self.pg), dist.get_rank(self.pg)
+        if self.world > _lib.DP_MAX_WORLD:
+            raise RuntimeError('NvlsExchange supports at most %d ranks' % _lib.DP_MAX_WORLD)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self._handles = []
+        # a small buffer first: its handle carries the signal pads (one per rank, mapped everywhere)
+        probe, hdl = self._alloc(64)
+        if not hdl.multicast_ptr:
+            raise RuntimeError('symmetric memory has no NVLS multicast mapping on this system')
+        need = (_lib.DP_PAD_WORD0 + _lib.DP_CHANNELS * _lib.DP_MAX_WORLD) * 4
+        if hdl.signal_pad_size < need:
+            raise RuntimeError('signal pad of %d bytes < %d' % (hdl.signal_pad_size, need))
+        # zero this library's words of the own pad, then a torch-side barrier: no kernel of ours has signalled yet
+        pad = hdl.get_signal_pad(self.rank, (hdl.signal_pad_size // 4,), dtype=torch.int32)
+        pad[_lib.DP_PAD_WORD0:_lib.DP_PAD_WORD0 + _lib.DP_CHANNELS * _lib.DP_MAX_WORLD].zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.pg)
+        self.epochs = torch.zeros(_lib.DP_CHANNELS, dtype=torch.int32, device=self.device)
+        self.ctx = _lib.DpCtx()
+        self.ctx.rank, self.ctx.world = self.rank, self.world
+        for r in range(self.world):
+            self.ctx.peer_pads[r] = int(hdl.signal_pad_ptrs[r])
+        self.ctx.epochs = self.epochs.data_ptr()
+        self._ctypes = ctypes
+
+    def _alloc(self, numel):
+        t = self._symm.empty(int(numel), dtype=torch.float32, device=self.device)
+        hdl = self._symm.rendezvous(t, self.group_name)
+        self._handles.append((t, hdl))
+        return t, hdl
+
+    def symmetric_zeros(self, numel):
+        """(tensor, multicast address, _lib.DpPtrs of the peers' copies) of a zeroed symmetric fp32 buffer of `numel`
+        elements.  Collective: every rank must call it in the same order with the same size."""
+        from . import _lib
+        t, hdl = self._alloc(numel)
+        t.zero_()
+        ptrs = _lib.DpPtrs()
+        for r in range(self.world):
+            ptrs.p[r] = int(hdl.buffer_ptrs[r])
+        torch.cuda.synchronize()
+        dist.barrier(group=self.pg)
+        return t, int(hdl.multicast_ptr), ptrs
+
+    def slice_bounds(self, numel):
+        """[lo, hi) of the flat buffers (in elements) that this rank's optimizer shard owns -- the split vqs_dp_amsgrad_step
+        uses: float4 granules, ceil(n / 4 / W) per rank."""
+        n4 = numel // 4
+        per = (n4 + self.world - 1) // self.world
+        lo4 = per * self.rank
+        hi4 = min(lo4 + per, n4)
+        return 4 * lo4, 4 * max(hi4, lo4)
+
+    def gather_sharded(self, flat):
+        """Full copy of a rank-sharded flat buffer (AMSGrad moments): every rank contributes its own slice (collective)."""
+        lo, hi = self.slice_bounds(flat.numel())
+        out = torch.zeros_like(flat)
+        out[lo:hi].copy_(flat[lo:hi])
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.pg)
+        return out
+
+    def peer_view(self, tensor, rank, numel=None):
+        """Rank `rank`'s copy of a symmetric tensor of this exchange as a tensor of this process (P2P mapping)."""
+        for t, hdl in self._handles:
+            if t.data_ptr() == tensor.data_ptr():
+                return hdl.get_buffer(rank, (numel if numel is not None else tensor.numel(),), torch.float32)
+        raise KeyError('not a symmetric tensor of this exchange')
+
+
+def nvls_available(process_group=None):
+    """True when the library's own NVLS exchange can be used: NCCL process group with > 1 rank on CUDA, torch symmetric
+    memory importable, not switched off by VQS_DP_NVLS=0 (the NCCL-allreduce path of round 1 stays as the fallback)."""
+    if os.environ.get('VQS_DP_NVLS', '1') == '0':
+        return False
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(process_group) < 2:
+        return False
+    if dist.get_backend(process_group) != 'nccl' or not torch.cuda.is_available():
+        return False
+    try:
+        import importlib
+        importlib.import_module('torch.distributed._symmetric_memory')
+    except Exception:
+        return False
+    return True
+
+
 class DataParallelComm(object):
     def __init__(self, process_group=None):
         self.pg = process_group
@@ -42,6 +141,19 @@ class DataParallelComm(object):
         self.world = dist.get_world_size(process_group) if self.enabled else 1
         self.rank = dist.get_rank(process_group) if self.enabled else 0
         self._works = []
+        self.nvls = None
+        if nvls_available(process_group):
+            try:
+                self.nvls = NvlsExchange(process_group)
+            except Exception as exc:            # no multicast on this system: NCCL allreduces instead
+                import warnings
+                warnings.warn('NVLS exchange unavailable (%s); using NCCL allreduces' % (exc,))
+                self.nvls = None
+            # every rank must take the same path
+            flag = torch.tensor([1 if self.nvls is not None else 0], device='cuda')
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=process_group)
+            if int(flag.item()) == 0:
+                self.nvls = None
 
     @property
     def grad_scale(self):

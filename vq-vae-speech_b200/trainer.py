@@ -99,8 +99,15 @@ class FusedTrainStep(object):
             offs.append(total)
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         dev = self.dev
-        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.nvls = self.comm.nvls if self.world > 1 else None
+        if self.nvls is not None:
+            # symmetric buffers: the optimizer kernel reads the gradient SUM of all GPUs through the NVLS multicast mapping of
+            # flat_g and broadcasts the new parameters through the one of flat_p (csrc/dp_nvls.cu)
+            self.flat_p, self.mc_p, _ = self.nvls.symmetric_zeros(total)
+            self.flat_g, self.mc_g, _ = self.nvls.symmetric_zeros(total)
+        else:
+            self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_vmax = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -204,7 +211,14 @@ class FusedTrainStep(object):
         b['enc_out'], b['m_e'] = f(B, C, Tq), u8(B, C, Tq)
         b['z'], b['q'], b['qj'] = f(B, D, Tq), f(B, D, Tq), f(B, D, Tq)
         b['idx'] = torch.empty(B * Tq, dtype=torch.int64, device=dev)
-        b['stats'] = f(K * (D + 1))
+        if self.nvls is not None and self.is_ema:
+            # the local statistics live in a symmetric buffer (the peers read them), their sum over ranks in a local one
+            b['stats_local'], _, self.stats_ptrs = self.nvls.symmetric_zeros((K * (D + 1) + 63) // 64 * 64)
+            b['stats_local'] = b['stats_local'][:K * (D + 1)]
+            b['stats'] = f(K * (D + 1))
+        else:
+            b['stats'] = f(K * (D + 1))
+            b['stats_local'] = b['stats']
         b['vq_scalars'] = torch.zeros(8, dtype=torch.float32, device=dev)
         b['jitter_src'] = torch.arange(Tq, dtype=torch.int32, device=dev)
         b['d1'], b['u'] = f(B, C, Tq), f(B, C, L2)
@@ -331,11 +345,14 @@ class FusedTrainStep(object):
         # ---- 2. VQ bottleneck ----
         vq = m._vq
         cb = vq._embedding.weight.data
-        ops.vq_assign(b['z'], cb, LAYOUT_BDT_AS_DTB, self.ws_vq, idx=b['idx'], stats=b['stats'])
+        ops.vq_assign(b['z'], cb, LAYOUT_BDT_AS_DTB, self.ws_vq, idx=b['idx'], stats=b['stats_local'])
         n_rows_total = B * Tq
         if self.is_ema:
             if self.world > 1:
-                ops.record_callable(self._allreduce_stats)
+                if self.nvls is not None:     # barrier + rank-ordered sum of the peers' vectors: one small kernel of ours
+                    ops.dp_allreduce_small(self.nvls.ctx, self.stats_ptrs, b['stats'], channel=0)
+                else:
+                    ops.record_callable(self._allreduce_stats)
                 n_rows_total = self.comm.total_rows(B * Tq)
             ops.vq_ema_update(vq._ema_cluster_size, vq._ema_w.data, cb, b['stats'], vq._decay, vq._epsilon)
         beta = float(vq._commitment_cost)
@@ -384,7 +401,7 @@ class FusedTrainStep(object):
         ops.bias_grad(gq1, G[DEC + '_conv_trans_1.bias'])
         tdgrad(gq1, DEC + '_conv_trans_1.weight', L2, 1, out=g, mask=b['s'], mask_kind=MASK_FLOAT)
         self._emit_wn_fold(*self.buckets['dec_convT'])
-        if self.world > 1:       # the three transposed convs are done: their gradients start travelling now
+        if self.world > 1 and self.nvls is None:       # the three transposed convs are done: their gradients start travelling now
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_convT']))
         other = self._view('gB2', C, L2)
         R_dec = d['R_dec']
@@ -410,7 +427,7 @@ class FusedTrainStep(object):
         if self.use_jitter:
             ops.jitter_bwd(b['gqj'], b['jitter_src'], gq)
         self._emit_wn_fold(*self.buckets['dec_rest'])
-        if self.world > 1:       # decoder gradients are complete: allreduce the rest of them under the encoder's backward
+        if self.world > 1 and self.nvls is None:       # decoder gradients are complete: allreduce the rest of them under the encoder's backward
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_rest']))
 
         # ---- 6. VQ backward (autograd of ema.py:165-169 / vector_quantizer.py:136-141), upstream d(loss)/d(vq_loss) = 1
@@ -455,21 +472,21 @@ class FusedTrainStep(object):
         cdgrad(gp4, E + '_conv_4.weight', Tq, 1, 1, out=gp3, add_pre=gh4, mask=b['a3'],
                        mask_kind=MASK_FLOAT)
         self._emit_wn_fold(*self.buckets['enc_hi'])
-        if self.world > 1:       # conv_4 .. pre_vq (and the codebook gradient) are final
+        if self.world > 1 and self.nvls is None:       # conv_4 .. pre_vq (and the codebook gradient) are final
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_hi']))
         # conv_3 (k4 s2 p2): a3 = relu(conv3(h2))
         F.conv1d_wgrad(gp3, b['h2'], G[E + '_conv_3.weight'], 2, 2, ws)
         ops.bias_grad(gp3, G[E + '_conv_3.bias'])
         gh2, gp2 = b['gT_a'], b['gT_b']
         self._emit_wn_fold(*self.buckets['enc_c3'])
-        if self.world > 1:
+        if self.world > 1 and self.nvls is None:
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_c3']))
         cdgrad(gp3, E + '_conv_3.weight', T, 2, 2, out=gh2, out2=gp2, mask2=b['m2'], mask2_kind=MASK_U8)
         # conv_2: h2 = relu(p2) + a1 ; a1 = relu(p1)
         F.conv1d_wgrad(gp2, b['a1'], G[E + '_conv_2.weight'], 1, 1, ws)
         ops.bias_grad(gp2, G[E + '_conv_2.bias'])
         self._emit_wn_fold(*self.buckets['enc_c2'])
-        if self.world > 1:
+        if self.world > 1 and self.nvls is None:
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_c2']))
         gp1 = self._view('gA2', C, T)
         cdgrad(gp2, E + '_conv_2.weight', T, 1, 1, out=gp1, add_pre=gh2, mask=b['a1'],
@@ -480,6 +497,13 @@ class FusedTrainStep(object):
         # ---- 8. gradient allreduce (average) + fused AMSGrad over the flat buffers (trainer.py:41-42,68) ----
         g_scale = 1.0
         self._emit_wn_fold(*self.buckets['enc_c1'])
+        if self.nvls is not None:
+            # the gradient allreduce is folded into the optimizer: barrier, Adam on this rank's slice with
+            # g = multimem.ld_reduce(gradients of all GPUs) / W, parameters broadcast by multimem.st, barrier.  Nothing ran
+            # beside the backward pass; the optimizer state is sharded over the ranks.
+            ops.dp_amsgrad_step(self.nvls.ctx, self.mc_p, self.flat_p, self.mc_g, self.flat_m, self.flat_v, self.flat_vmax,
+                                self.opt_step, self.lr, self.betas[0], self.betas[1], self.eps, ch_before=1, ch_after=2)
+            return
         if self.world > 1:
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_c1']))
             ops.record_callable(self._wait_buckets)
@@ -561,6 +585,10 @@ class FusedTrainStep(object):
                 a = list(args)
                 a[8:12] = [self.lr, self.betas[0], self.betas[1], self.eps]
                 self.schedule[i] = (fn, tuple(a), keep)
+            if fn is not None and fn.__name__ == 'vqs_dp_amsgrad_step':
+                a = list(args)
+                a[10:14] = [self.lr, self.betas[0], self.betas[1], self.eps]
+                self.schedule[i] = (fn, tuple(a), keep)
         if self.graph is not None:
             torch.cuda.synchronize()
             self.graph = None
@@ -590,8 +618,22 @@ class FusedTrainStep(object):
         return self.buf['idx'].view(-1, 1)
 
     def gradients(self):
-        """name -> gradient view (valid after a step; world>1: already summed over ranks, not yet divided)."""
-        return dict(self.grads)
+        """name -> gradient (valid after a step; world > 1: summed over ranks, not yet divided).  With the NVLS exchange the
+        flat buffer holds this rank's LOCAL gradient (the sum only ever exists inside the optimizer kernel), so the sum is
+        formed here with a collective: every rank must call it (debugging / tests only)."""
+        if self.nvls is None:
+            return dict(self.grads)
+        import torch.distributed as dist
+        tot = self.flat_g.clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.comm.pg)
+        out = {}
+        for name, g in self.grads.items():
+            if name in self.param_offsets:
+                off = self.param_offsets[name]
+                out[name] = tot[off:off + g.numel()].view_as(g)
+            else:
+                out[name] = g
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -617,15 +659,18 @@ def optimizer_state_dict(step):
     params = dict(step.model.named_parameters())
     state = {}
     nstep = int(step.opt_step.item())
+    fm, fv, fx = step.flat_m, step.flat_v, step.flat_vmax
+    if getattr(step, 'nvls', None) is not None:     # moments are sharded over the ranks: collect them (collective call)
+        fm, fv, fx = (step.nvls.gather_sharded(t) for t in (fm, fv, fx))
     if nstep > 0:
         for name in step.param_names:
             off, p = step.param_offsets[name], params[name]
             n = p.numel()
             state[order.index(name)] = {
                 'step': torch.tensor(float(nstep)),
-                'exp_avg': step.flat_m[off:off + n].view_as(p).clone(),
-                'exp_avg_sq': step.flat_v[off:off + n].view_as(p).clone(),
-                'max_exp_avg_sq': step.flat_vmax[off:off + n].view_as(p).clone(),
+                'exp_avg': fm[off:off + n].view_as(p).clone(),
+                'exp_avg_sq': fv[off:off + n].view_as(p).clone(),
+                'max_exp_avg_sq': fx[off:off + n].view_as(p).clone(),
             }
     group = dict(lr=step.lr, betas=tuple(step.betas), eps=step.eps, weight_decay=0, amsgrad=True, maximize=False,
                  foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False,
