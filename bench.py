@@ -298,10 +298,13 @@ def vq_bench(dev, pk, rows, K=44, D=64, iters=20):
                 f()
                 e1.record()
                 evs.append((name, e0, e1))
+            # the bottleneck as the captured training step runs it: search + statistics, EMA update, gather-only forward
+            # (q = W_new[idx], z not read again), backward with the forward's losses formed in the same sweep over z
             br('assign', lambda: ops.vq_assign(z, W, layout, ws, idx=idx, stats=stats))
             br('ema_update', lambda: ops.vq_ema_update(cs, ew, W, stats, 0.99, 1e-5))
-            br('quantize', lambda: ops.vq_quantize(z, idx, W, layout, ws, stats[:K], N, 0.25, out=q, scalars=sc))
-            br('backward', lambda: ops.vq_backward(g, one, 2 * 0.25 / (N * D), z, idx, W, layout, out=gz))
+            br('quantize', lambda: ops.vq_gather(idx, W, layout, shape, out=q))
+            br('backward', lambda: ops.vq_backward_loss(g, one, 2 * 0.25 / (N * D), z, idx, W, layout, ws, stats[:K], N, 0.25,
+                                                        out=gz, scalars=sc))
         for _ in range(3):
             once(None)
         torch.cuda.synchronize()
@@ -325,6 +328,8 @@ def vq_bench(dev, pk, rows, K=44, D=64, iters=20):
     out['peak_source'] = pk['src']
     out['bytes_per_row'] = 20 * D + 16
     out['K'], out['D'] = K, D
+    out['passes'] = ('assign (reads z, writes idx + statistics) | ema_update | quantize = gather-only forward (reads idx, '
+                     'writes q) | backward (reads g, z, idx; writes grad_z; forms the losses): z is read twice in total')
     out['search_engine'] = ('auto: streaming engine (row tiles as raw tf32 tcgen05 operands + exact fp32 settlement, '
                             'identical indices): flat rows arrive by TMA, (B,D,T) rows (B % 64 == 0) by a cp.async gather '
                             'into the same swizzled layout; element-wise kernels tiled with indices staged in smem')

@@ -151,6 +151,17 @@ int vqs_vq_quantize(const float* z, int layout, int B, int D, int T, const int64
 int vqs_vq_backward(const float* g_out, const float* g_loss, float coef, const float* z, int layout, int B, int D, int T,
                     const int64_t* idx, const float* codebook, int K, float* grad_z, vqs_stream_t stream);
 
+/* vqs_vq_backward that ALSO forms the losses of the forward pass in the same sweep (it reads z, idx and the codebook
+ * anyway): scalars as vqs_vq_quantize writes them (SSE, e_latent = mean((q - x)^2), perplexity, vq_loss of either class).
+ * Together with vqs_vq_quantize(z = NULL): the gather-only forward -- out = codebook[idx] exactly, z not read -- the fused
+ * forward + backward moves 20 D + 16 bytes per row instead of 24 D + 16: z is read once.  The value of the
+ * gather-only `quantized` is q itself where the reference's is fl(x + fl(q - x)) (vector_quantizer_ema.py:169): equal
+ * within an ulp of max(|x|, |q|).  The drop-in modules keep the exact forward; the captured training step uses this pair. */
+int vqs_vq_backward_loss(const float* g_out, const float* g_loss, float coef, const float* z, int layout, int B, int D, int T,
+                         const int64_t* idx, const float* codebook, int K, float* grad_z, const float* counts,
+                         double n_rows_total, float beta, float* scalars, void* workspace, size_t workspace_bytes,
+                         vqs_stream_t stream);
+
 /* Codebook gradient of the non-EMA VectorQuantizer (autograd of vector_quantizer.py:136-139):
  *   grad_E[k] (+)= g_loss[0] * coef * (counts[k] * E[k] - dw[k]),  coef = 2/(N*D). */
 int vqs_vq_grad_codebook(const float* stats, const float* codebook, const float* g_loss, float coef, int K, int D,

@@ -516,3 +516,47 @@ def test_pairwise_l2_large_matches_oracle():
     assert rel_err(ops.pairwise_l2(zd, LAYOUT_BDT_AS_DTB, D).cpu().numpy(), enc.reshape(-1)) < TOL
     assert rel_err(ops.pairwise_l2(Wd, LAYOUT_FLAT_ND, D).cpu().numpy(), emb) < TOL
     assert rel_err(ops.pairwise_l2(zd, LAYOUT_BDT_AS_DTB, D, Wd).cpu().numpy(), fve.reshape(-1)) < TOL
+
+
+@pytest.mark.parametrize('layout_name,shape', [('flat', (8192, 64)), ('flat', (300, 64)), ('bdt', (256, 64, 32)),
+                                               ('bdt', (3, 64, 17)), ('bdt', (5, 2, 24))])
+def test_gather_forward_and_backward_with_losses_equal_the_exact_pair(layout_name, shape):
+    """The captured training step runs the bottleneck as vq_gather (q = W[idx], z not read) + vq_backward_loss (grad_z and the
+    forward's losses in one sweep over z).  Against the exact pair vq_quantize + vq_backward on the same inputs: the gathered
+    value is bit-equal to W[idx] and within an ulp of max(|x|, |q|) of the straight-through value fl(x + fl(q - x)); grad_z is
+    bit-identical; SSE / e_latent / perplexity / vq_loss agree to 1e-6 (a different summation order of the same terms)."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from vq_vae_speech_b200 import ops, LAYOUT_BDT_AS_DTB, LAYOUT_FLAT_ND
+    dev = torch.device('cuda:0')
+    layout = LAYOUT_FLAT_ND if layout_name == 'flat' else LAYOUT_BDT_AS_DTB
+    D = shape[1]
+    K = 44 if D == 64 else 10
+    g = torch.Generator(device=dev).manual_seed(sum(shape))
+    z = torch.randn(*shape, device=dev, generator=g)
+    W = torch.randn(K, D, device=dev, generator=g)
+    gq = torch.randn(*shape, device=dev, generator=g)
+    one = torch.ones(1, device=dev)
+    ws = ops.vq_workspace(K, D, dev)
+    idx, stats = ops.vq_assign(z, W, layout, ws)
+    N = idx.numel()
+    beta, coef = 0.25, 2 * 0.25 / (N * D)
+    q_exact, sc_exact = ops.vq_quantize(z, idx, W, layout, ws, stats[:K], N, beta)
+    gz_exact = ops.vq_backward(gq, one, coef, z, idx, W, layout)
+    sc_exact = sc_exact.clone()
+    q = ops.vq_gather(idx, W, layout, shape)
+    gz, sc = ops.vq_backward_loss(gq, one, coef, z, idx, W, layout, ws, stats[:K], N, beta)
+    # the gathered value is W[idx] exactly, in z's layout
+    rows = W[idx]                                                       # (N, D) in the reference's row order
+    if layout_name == 'flat':
+        want = rows
+    else:
+        B, _, T = shape
+        want = rows.reshape(D, T, B).permute(2, 0, 1).contiguous()     # inverse of permute(1, 2, 0).view(-1, D)
+    assert torch.equal(q, want)
+    tol = 2.4e-7 * torch.maximum(z.abs(), q.abs()) + 1e-30
+    assert bool(((q - q_exact).abs() <= tol).all())
+    assert torch.equal(gz, gz_exact)
+    for i in range(5):
+        a, b = float(sc[i]), float(sc_exact[i])
+        assert abs(a - b) <= 1e-6 * abs(b) + 1e-12, (i, a, b)

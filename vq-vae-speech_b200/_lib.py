@@ -80,6 +80,8 @@ PROTOTYPES = {
                                 c_void_p, c_double, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     'vqs_vq_backward': (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_int, c_void_p, c_void_p]),
+    'vqs_vq_backward_loss': (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_int, c_void_p, c_void_p, c_double, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     'vqs_vq_grad_codebook': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_int, c_void_p]),
     'vqs_conv_gemm': (c_int, [POINTER(ConvGemmDesc), c_void_p]),
     'vqs_wgrad_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

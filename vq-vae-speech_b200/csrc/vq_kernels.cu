@@ -454,6 +454,7 @@ struct EwParams {
   float coef;
   long long total;  // N*D
   int layout, B, D, T, K;
+  int gather;       // forward only: out = codebook[idx] exactly, z is not read (no straight-through arithmetic, no SSE)
   FastDiv divD, divT;
   // blocked (B, D, T) order (BLK): a warp = 16 batch items x 2 groups of 4 frames of one channel
   FastDiv divNTP;   // NTP = ceil(T / 8) frame pairs
@@ -552,7 +553,11 @@ __global__ void __launch_bounds__(256) vq_elementwise_kernel(const EwParams p) {
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       if (BWD) {
-        r[e] = fmaf(c, __fsub_rn(x[e], q[e]), g[e]);
+        const float df = __fsub_rn(x[e], q[e]);
+        r[e] = fmaf(c, df, g[e]);
+        sse = fmaf(df, df, sse);     // (x - q)^2: the commitment / codebook loss, when the caller asked for it here
+      } else if (p.gather) {
+        r[e] = q[e];
       } else {
         float df = __fsub_rn(q[e], x[e]);
         r[e] = __fadd_rn(x[e], df);  // inputs + (quantized - inputs).detach()  (ema.py:169)
@@ -563,6 +568,11 @@ __global__ void __launch_bounds__(256) vq_elementwise_kernel(const EwParams p) {
     else p.out[o] = r[0];
   };
   auto load = [&](const long long o, float (&x)[VEC], float (&g)[VEC]) {
+    if (!BWD && p.gather) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) x[e] = 0.f;
+      return;
+    }
     if (VEC == 4) {
       float4 xv = ldg_stream4(p.z + o);
       x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
@@ -590,7 +600,7 @@ __global__ void __launch_bounds__(256) vq_elementwise_kernel(const EwParams p) {
     for (int u = 0; u < UNR; ++u)
       if (off[u] >= 0) process(off[u], x[u], g[u]);
   }
-  if (!BWD) {
+  if (p.sse_partials != nullptr) {
     double s = warp_sum((double)sse);
     if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -641,7 +651,7 @@ __global__ void __launch_bounds__(256) vq_elementwise_bdt_tile_kernel(const EwPa
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const size_t o = o0 + (size_t)(32 * h * D + dd) * T;
-          xv[dd][h] = ldg_stream4(p.z + o);
+          xv[dd][h] = (BWD || !p.gather) ? ldg_stream4(p.z + o) : make_float4(0.f, 0.f, 0.f, 0.f);
           if (BWD) gv[dd][h] = ldg_stream4(p.g + o);
         }
     }
@@ -660,7 +670,14 @@ __global__ void __launch_bounds__(256) vq_elementwise_bdt_tile_kernel(const EwPa
           if (BWD) {
             const float g[4] = {gv[dd][h].x, gv[dd][h].y, gv[dd][h].z, gv[dd][h].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) r[e] = fmaf(c, __fsub_rn(x[e], q[e]), g[e]);
+            for (int e = 0; e < 4; ++e) {
+              const float df = __fsub_rn(x[e], q[e]);
+              r[e] = fmaf(c, df, g[e]);
+              sse = fmaf(df, df, sse);
+            }
+          } else if (p.gather) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = q[e];
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -674,7 +691,7 @@ __global__ void __launch_bounds__(256) vq_elementwise_bdt_tile_kernel(const EwPa
       }
     }
   }
-  if (!BWD) {
+  if (p.sse_partials != nullptr) {
     double sd = warp_sum((double)sse);
     if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = sd;
     __syncthreads();
@@ -710,7 +727,7 @@ __global__ void __launch_bounds__(256) vq_elementwise_flat_tile_kernel(const EwP
     for (int i = 0; i < RPT; ++i) {
       const long long r = r0 + rq + 16 * i;
       if (r < N) {
-        xv[i] = ldg_stream4(p.z + r * D + c4 * 4);
+        xv[i] = (BWD || !p.gather) ? ldg_stream4(p.z + r * D + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (BWD) gv[i] = ldg_stream4(p.g + r * D + c4 * 4);
       }
     }
@@ -727,7 +744,14 @@ __global__ void __launch_bounds__(256) vq_elementwise_flat_tile_kernel(const EwP
         if (BWD) {
           const float g[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = fmaf(c, __fsub_rn(x[e], q[e]), g[e]);
+          for (int e = 0; e < 4; ++e) {
+            const float df = __fsub_rn(x[e], q[e]);
+            o[e] = fmaf(c, df, g[e]);
+            sse = fmaf(df, df, sse);
+          }
+        } else if (p.gather) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = q[e];
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -740,7 +764,7 @@ __global__ void __launch_bounds__(256) vq_elementwise_flat_tile_kernel(const EwP
       }
     }
   }
-  if (!BWD) {
+  if (p.sse_partials != nullptr) {
     double sd = warp_sum((double)sse);
     if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = sd;
     __syncthreads();
@@ -1108,6 +1132,27 @@ extern "C" int vqs_vq_quantize(const float* z, int layout, int B, int D, int T, 
                                vqs_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (int e = check_vq_shape(layout, B, D, T, K)) return e;
+  if (z == nullptr) {
+    // gather only: out = codebook[idx] in z's layout, exactly; z is not read, no loss is formed here (the training step
+    // takes the loss from vqs_vq_backward_loss, which reads z anyway: 264 instead of 520 bytes per row in this pass)
+    VQS_CHECK_ARG(idx && codebook && out, "vqs_vq_quantize: NULL pointer");
+    EwParams g;
+    g.z = nullptr; g.g = nullptr; g.gl = nullptr; g.idx = idx; g.cb = codebook; g.out = out; g.sse_partials = nullptr;
+    g.coef = 0.f; g.gather = 1;
+    g.total = (long long)B * D * T;
+    g.layout = layout; g.B = B; g.D = D; g.T = T; g.K = K;
+    g.divD = FastDiv((uint32_t)D);
+    g.divT = FastDiv((uint32_t)T);
+    int grid = 0;
+    if (int e = launch_elementwise(false, g, (size_t)K * D * 4, grid, st)) return e;
+    if (q_rows != nullptr) {
+      long long N = (long long)B * T;
+      long long blocks = (N * D + 255) / 256;
+      gather_rows_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(idx, codebook, N, D, q_rows);
+      VQS_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   VQS_CHECK_ARG(z && idx && codebook && out && scalars && workspace, "vqs_vq_quantize: NULL pointer");
   if (workspace_bytes < vqs_vq_workspace_bytes(K, D)) {
     set_error("vqs_vq_quantize: workspace too small");
@@ -1121,7 +1166,7 @@ extern "C" int vqs_vq_quantize(const float* z, int layout, int B, int D, int T, 
   double* sse_part = (double*)((char*)workspace + front);
   EwParams p;
   p.z = z; p.g = nullptr; p.gl = nullptr; p.idx = idx; p.cb = codebook; p.out = out; p.sse_partials = sse_part;
-  p.coef = 0.f;
+  p.coef = 0.f; p.gather = 0;
   p.total = (long long)B * D * T;
   p.layout = layout; p.B = B; p.D = D; p.T = T; p.K = K;
   p.divD = FastDiv((uint32_t)D);
@@ -1146,13 +1191,45 @@ extern "C" int vqs_vq_backward(const float* g_out, const float* g_loss, float co
   VQS_CHECK_ARG(g_out && g_loss && z && idx && codebook && grad_z, "vqs_vq_backward: NULL pointer");
   EwParams p;
   p.z = z; p.g = g_out; p.gl = g_loss; p.idx = idx; p.cb = codebook; p.out = grad_z; p.sse_partials = nullptr;
-  p.coef = coef;
+  p.coef = coef; p.gather = 0;
   p.total = (long long)B * D * T;
   p.layout = layout; p.B = B; p.D = D; p.T = T; p.K = K;
   p.divD = FastDiv((uint32_t)D);
   p.divT = FastDiv((uint32_t)T);
   int grid = 0;
   return launch_elementwise(true, p, (size_t)K * D * 4, grid, (cudaStream_t)stream);
+}
+
+extern "C" int vqs_vq_backward_loss(const float* g_out, const float* g_loss, float coef, const float* z, int layout, int B,
+                                    int D, int T, const int64_t* idx, const float* codebook, int K, float* grad_z,
+                                    const float* counts, double n_rows_total, float beta, float* scalars, void* workspace,
+                                    size_t workspace_bytes, vqs_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = check_vq_shape(layout, B, D, T, K)) return e;
+  VQS_CHECK_ARG(g_out && g_loss && z && idx && codebook && grad_z && scalars && workspace,
+                "vqs_vq_backward_loss: NULL pointer");
+  if (workspace_bytes < vqs_vq_workspace_bytes(K, D)) {
+    set_error("vqs_vq_backward_loss: workspace too small");
+    return VQS_ERR_WORKSPACE;
+  }
+  size_t front = partials_bytes(K, D);
+  if (search_large_supported(K, D)) {
+    size_t l = align_up(search_large_workspace_bytes(K, D), 256);
+    if (l > front) front = l;
+  }
+  double* sse_part = (double*)((char*)workspace + front);
+  EwParams p;
+  p.z = z; p.g = g_out; p.gl = g_loss; p.idx = idx; p.cb = codebook; p.out = grad_z; p.sse_partials = sse_part;
+  p.coef = coef; p.gather = 0;
+  p.total = (long long)B * D * T;
+  p.layout = layout; p.B = B; p.D = D; p.T = T; p.K = K;
+  p.divD = FastDiv((uint32_t)D);
+  p.divT = FastDiv((uint32_t)T);
+  int grid = 0;
+  if (int e = launch_elementwise(true, p, (size_t)K * D * 4, grid, st)) return e;
+  vq_finalize_kernel<<<1, 256, 0, st>>>(sse_part, grid, counts, K, n_rows_total, (double)p.total, beta, scalars);
+  VQS_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int vqs_vq_grad_codebook(const float* stats, const float* codebook, const float* g_loss, float coef, int K,

@@ -186,6 +186,32 @@ def vq_backward(g_out, g_loss, coef, z, idx, codebook, layout, out=None):
     return out
 
 
+def vq_gather(idx, codebook, layout, shape, out=None):
+    """Gather-only forward: out (shape = z's shape, z's layout) = codebook[idx] exactly; z is not read (vqs_vq_quantize with
+    z = NULL).  The losses then come from vq_backward_loss."""
+    K, D = codebook.shape
+    if out is None:
+        out = torch.empty(*shape, dtype=torch.float32, device=codebook.device)
+    B, _, T = vq_shape(out, layout, D)
+    _call('vqs_vq_quantize', (None, layout, B, D, T, _p(idx, torch.int64), _p(codebook), K, _p(out), None, None, 0.0, 0.0,
+                              None, None, 0))
+    return out
+
+
+def vq_backward_loss(g_out, g_loss, coef, z, idx, codebook, layout, ws, counts, n_rows_total, beta, out=None, scalars=None):
+    """grad_z and, in the same sweep over z, the forward's losses (scalars as vq_quantize fills them)."""
+    K, D = codebook.shape
+    B, _, T = vq_shape(z, layout, D)
+    if out is None:
+        out = torch.empty_like(z)
+    if scalars is None:
+        scalars = torch.empty(8, dtype=torch.float32, device=z.device)
+    _call('vqs_vq_backward_loss', (_p(g_out), _p(g_loss), float(coef), _p(z), layout, B, D, T, _p(idx, torch.int64),
+                                   _p(codebook), K, _p(out), _p(counts), float(n_rows_total), float(beta), _p(scalars),
+                                   _pany(ws), ws.numel()))
+    return out, scalars
+
+
 def vq_grad_codebook(stats, codebook, g_loss, coef, out=None, accumulate=False):
     K, D = codebook.shape
     if out is None:

@@ -356,8 +356,10 @@ class FusedTrainStep(object):
                 n_rows_total = self.comm.total_rows(B * Tq)
             ops.vq_ema_update(vq._ema_cluster_size, vq._ema_w.data, cb, b['stats'], vq._decay, vq._epsilon)
         beta = float(vq._commitment_cost)
-        ops.vq_quantize(b['z'], b['idx'], cb, LAYOUT_BDT_AS_DTB, self.ws_vq, b['stats'][:K], n_rows_total, beta,
-                        out=b['q'], scalars=b['vq_scalars'])
+        # forward value of the bottleneck: q = W_new[idx] as a pure gather-write (z is not read again); the losses are formed by
+        # the VQ backward kernel, which reads z, idx and the codebook anyway (vqs_b200.h: vqs_vq_backward_loss)
+        ops.vq_gather(b['idx'], cb, LAYOUT_BDT_AS_DTB, (B, D, Tq), out=b['q'])
+        self._vq_loss_args = (b['stats'][:K], n_rows_total, beta)
 
         # ---- 3. decoder forward (deconvolutional_decoder.py:100-137) ----
         dec_in = b['q']
@@ -432,7 +434,9 @@ class FusedTrainStep(object):
 
         # ---- 6. VQ backward (autograd of ema.py:165-169 / vector_quantizer.py:136-141), upstream d(loss)/d(vq_loss) = 1
         n_local = B * Tq
-        ops.vq_backward(gq, b['one'], 2.0 * beta / (n_local * D), b['z'], b['idx'], cb, LAYOUT_BDT_AS_DTB, out=b['gz'])
+        counts, n_rows_total, _ = self._vq_loss_args
+        ops.vq_backward_loss(gq, b['one'], 2.0 * beta / (n_local * D), b['z'], b['idx'], cb, LAYOUT_BDT_AS_DTB, self.ws_vq,
+                             counts, n_rows_total, beta, out=b['gz'], scalars=b['vq_scalars'])
         if not self.is_ema:
             ops.vq_grad_codebook(b['stats'], cb, b['one'], 2.0 / (n_local * D), out=G['_vq._embedding.weight'])
 
