@@ -43,14 +43,21 @@ constexpr int N_PROD_WARPS = 16;
 constexpr int N_PROD = N_PROD_WARPS * 32;
 constexpr int TC_THREADS = N_PROD + 64;   // + warp 16 (TMEM allocator, MMA issuer) + warp 17 (second MMA issuer, 3xTF32)
 
-template <int BN, int PASSES>
+// PAIR = 1: the CTA is one half of a cta_group::2 pair (cluster of two CTAs along grid.y = two neighbouring 128-row tiles of
+// M sharing one BN-column tile): it stages its own 128 x 32 block of A and only BNL = BN / 2 rows of B (rows
+// [rank * BNL, rank * BNL + BNL) of the tile); the MMAs (M = 256) are issued by the leader CTA and read both halves.
+#ifndef VQS_PAIR_STAGES
+#define VQS_PAIR_STAGES 4
+#endif
+template <int BN, int PASSES, int PAIR = 0>
 struct TcCfg {
   static constexpr int NOPS = (PASSES == 3) ? 2 : 1;                // hi (+ lo) copies per operand
-  static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+  static constexpr int BNL = PAIR ? BN / 2 : BN;                    // B rows staged by this CTA
+  static constexpr int A_BYTES = BM * 128, B_BYTES = BNL * 128;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
   // (3-pass, BN = 64: a ring of 3 x 48 KB measured faster than 4 -- 584 vs 743 cycles per k-block in the protocol
   // microbenchmark profiles/mma_pipe.cu)
-  static constexpr int STAGES_MAX = (PASSES == 3) ? 3 : 4;
+  static constexpr int STAGES_MAX = PAIR ? VQS_PAIR_STAGES : ((PASSES == 3) ? 3 : 4);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > STAGES_MAX ? STAGES_MAX : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int NACC = (PASSES == 3) ? 4 : 1;                // TMEM accumulators of BN columns each
@@ -225,10 +232,21 @@ __device__ __forceinline__ bool tc_mask_on(const void* m, int kind, size_t i) {
 // accumulator); role 1: main term of the 3xTF32 split; role 2: its correction terms.  The stage ring is unrolled: k-block i0 + j lives in stage j, so all descriptors are base + constant
 // and the round-robin accumulator of a k-step is a compile-time constant.
 // ---------------------------------------------------------------------------------------------------
-template <int BN, int PASSES, int ROLE>
+template <int PAIR>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR) umma_tf32_pair(tmem_d, a, b, idesc, acc);
+  else umma_tf32(tmem_d, a, b, idesc, acc);
+}
+template <int PAIR>
+__device__ __forceinline__ void umma_done(uint64_t* bar) {
+  if (PAIR) umma_commit_pair(bar);
+  else umma_commit(bar);
+}
+
+template <int BN, int PASSES, int ROLE, int PAIR>
 __device__ __forceinline__ void issue_mmas(TcShared* sh, uint32_t smem_base, uint32_t tmem_base, int nkb) {
-  using Cfg = TcCfg<BN, PASSES>;
-  constexpr uint32_t idesc = make_idesc_tf32(BN);
+  using Cfg = TcCfg<BN, PASSES, PAIR>;
+  constexpr uint32_t idesc = make_idesc_tf32(BN, PAIR ? 256 : 128);
   constexpr int S = Cfg::STAGES;
   const uint64_t d0 = make_desc_sw128(smem_base);
   const bool elected = elect_one();
@@ -236,6 +254,8 @@ __device__ __forceinline__ void issue_mmas(TcShared* sh, uint32_t smem_base, uin
 #pragma unroll 1
   for (int i0 = 0; i0 < nkb; i0 += S) {
     const uint32_t nz = i0 > 0 ? 1u : 0u;      // accumulate flag of the first MMA into each accumulator
+    // k-step t of the CTA goes to main accumulator 1 + t % 3 whatever the ring depth (S * 4 need not be a multiple of 3)
+    const uint32_t rot = (uint32_t)(i0 * (BKF / 8)) % 3u;
 #pragma unroll
     for (int j = 0; j < S; ++j) {
       if (i0 + j < nkb) {
@@ -254,36 +274,42 @@ __device__ __forceinline__ void issue_mmas(TcShared* sh, uint32_t smem_base, uin
             if (ROLE == 1) {
               // main term: accumulators 1..3 round-robin (the tensor core truncates when it accumulates: one accumulator
               // drifts 1.8e-5 relative over 864 MMAs, see the file header)
-              umma_tf32(tmem_base + (uint32_t)((1 + g % 3) * BN), a_hi + adv, b_hi + adv, idesc, g < 3 ? nz : 1u);
+              uint32_t acc = (uint32_t)(g % 3) + rot;
+              acc = acc >= 3u ? acc - 3u : acc;
+              umma_issue<PAIR>(tmem_base + (1u + acc) * (uint32_t)BN, a_hi + adv, b_hi + adv, idesc, g < 3 ? nz : 1u);
             } else {
-              umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, g == 0 ? nz : 1u);
-              umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_issue<PAIR>(tmem_base, a_lo + adv, b_hi + adv, idesc, g == 0 ? nz : 1u);
+              umma_issue<PAIR>(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
             }
           } else {
-            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, g == 0 ? nz : 1u);
+            umma_issue<PAIR>(tmem_base, a_hi + adv, b_hi + adv, idesc, g == 0 ? nz : 1u);
           }
         }
-        if (elected) umma_commit(&sh->empty[j]);  // frees the smem slot once this thread's MMAs have read it
+        if (elected) umma_done<PAIR>(&sh->empty[j]);  // frees the smem slot (of both CTAs of a pair) once this thread's MMAs have read it
         __syncwarp();
       }
     }
     par ^= 1u;
   }
-  if (elected) umma_commit(&sh->tmem_full);       // this thread's share of the accumulators is complete
+  if (elected) umma_done<PAIR>(&sh->tmem_full);   // this thread's share of the accumulators is complete
   __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int MODE, int BN, int PASSES, int KSZ>
+template <int MODE, int BN, int PASSES, int KSZ, int PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<MODE> prm) {
-  using Cfg = TcCfg<BN, PASSES>;
+  using Cfg = TcCfg<BN, PASSES, PAIR>;
+  constexpr int BNL = Cfg::BNL;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs), 1 = peer
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   TcShared* sh = reinterpret_cast<TcShared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // pairs are the CTAs (2i, 2i + 1) of grid.x (cta_group::2 wants the pair adjacent in x): grid = (M tiles, N tiles, splits)
+  const int tile_m = PAIR ? blockIdx.x : blockIdx.y, tile_n = PAIR ? blockIdx.y : blockIdx.x;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
 
   bool a_image = false;
   if constexpr (MODE == 0) a_image = prm.p.d.a_tap_major == 2;
@@ -305,15 +331,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&sh->full[s], N_PROD_WARPS + (a_image ? 1 : 0));
+      // (pair: the leader's full[] also waits for one arrival of the peer's relay warp = "the peer's half is staged")
+      mbar_init(&sh->full[s], N_PROD_WARPS + (a_image ? 1 : 0) + ((PAIR && rank == 0) ? 1 : 0));
       mbar_init(&sh->empty[s], Cfg::N_ISSUERS);
     }
     mbar_init(&sh->tmem_full, Cfg::N_ISSUERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == N_PROD_WARPS) tmem_alloc(&sh->tmem_base, Cfg::TMEM_COLS);
+  if (warp == N_PROD_WARPS) {
+    if (PAIR) tmem_alloc_pair(&sh->tmem_base, Cfg::TMEM_COLS);
+    else tmem_alloc(&sh->tmem_base, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
   pdl_prologue_done();
@@ -326,23 +357,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
     const float* xb = nullptr;
     int lbase = 0, brow = 0, bk0 = 0;
     if constexpr (MODE == 0) {
-      constexpr int TPR = N_PROD / BN;
+      constexpr int TPR = N_PROD / BNL;
       brow = ptid / TPR;
       bk0 = (ptid % TPR) * (8 / TPR);
-      const int n = n0 + brow;
+      const int n = n0 + (int)rank * BNL + brow;
       n_ok = n < prm.p.Ntot;
       uint32_t bb = 0, ll = 0;
       if (n_ok) prm.p.divL.divmod((uint32_t)n, bb, ll);
       xb = prm.p.d.X + (long long)bb * prm.p.d.x_sb;
       lbase = (int)ll * prm.p.d.l_mul + prm.p.d.off;
     }
-    using Regs = typename std::conditional<MODE == 0, ConvRegs<BN>, WgradRegs<BN>>::type;
-    WgradRows<BN> rows;
+    using Regs = typename std::conditional<MODE == 0, ConvRegs<BNL>, WgradRegs<BNL>>::type;
+    WgradRows<BNL> rows;
     if constexpr (MODE == 1) {
       const vqs_wgrad_desc& d = prm.p.d;
 #pragma unroll
-      for (int i = 0; i < WgradRegs<BN>::RB; ++i) {
-        const int n = n0 + warp + i * N_PROD_WARPS;
+      for (int i = 0; i < WgradRegs<BNL>::RB; ++i) {
+        const int n = n0 + (int)rank * BNL + warp + i * N_PROD_WARPS;
         const int c = n / KSZ, j = n - c * KSZ;
         rows.xoff[i] = c * d.Lx;
         rows.pj[i] = (n < prm.p.Nw) ? j * d.j_mul + d.off : -(1 << 29);
@@ -351,24 +382,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
       rows.na = na < 0 ? 0 : na;
     }
     auto load = [&](int kb, Regs& rg) {
-      if constexpr (MODE == 0) load_conv<BN>(prm.p, kb, rg, m0, ptid, n_ok, xb, lbase, bk0);
-      else load_wgrad<BN>(prm.p, kb, rg, rows, m0, warp, lane);
+      if constexpr (MODE == 0) load_conv<BNL>(prm.p, kb, rg, m0, ptid, n_ok, xb, lbase, bk0);
+      else load_wgrad<BNL>(prm.p, kb, rg, rows, m0, warp, lane);
     };
     // Register ring of depth 3: while k-block i is stored, the loads of i+1 and i+2 are in flight.  With ~1.2k cycles of
     // loaded-L2 latency and 32 KB of operands per k-block, one block in flight caps the SM at ~27 B/clk (measured: 2.8k
     // cycles per k-block); two blocks in flight cover the 768-cycle MMA time of a 3xTF32 k-block.
     const uint32_t smem_base = smem_u32(smem);
     uint32_t offA = 0, off0 = 0;
-    uint32_t offB[ConvRegs<BN>::CH];
+    uint32_t offB[ConvRegs<BNL>::CH];
     if constexpr (MODE == 0) {
       const int r0a = ptid >> 3, ca = ptid & 7;
       offA = (uint32_t)(r0a * 128 + ((ca ^ (r0a & 7)) << 4));
 #pragma unroll
-      for (int ci = 0; ci < ConvRegs<BN>::CH; ++ci) offB[ci] = (uint32_t)(brow * 128 + (((bk0 + ci) ^ (brow & 7)) << 4));
+      for (int ci = 0; ci < ConvRegs<BNL>::CH; ++ci) offB[ci] = (uint32_t)(brow * 128 + (((bk0 + ci) ^ (brow & 7)) << 4));
     } else {
       off0 = sw128_off(warp, lane);
 #pragma unroll
-      for (int ci = 0; ci < ConvRegs<BN>::CH; ++ci) offB[ci] = 0;
+      for (int ci = 0; ci < ConvRegs<BNL>::CH; ++ci) offB[ci] = 0;
     }
     auto stage = [&](int i, const Regs& rg) {
       const int s = i % Cfg::STAGES;
@@ -383,7 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
           // A operand: one bulk copy per copy (hi, lo) of the pre-built 128 x 32 image block of this k-block; the copy
           // engine signals full[s] with complete_tx (async proxy: no fence needed), this thread adds the extra arrival
           const int nkb_all = prm.p.Ktot / BKF;
-          const float* blk = prm.p.d.A + ((size_t)blockIdx.y * nkb_all + (kb_begin + i)) * 8192;
+          const float* blk = prm.p.d.A + ((size_t)tile_m * nkb_all + (kb_begin + i)) * 8192;
           const uint32_t bar = smem_u32(&sh->full[s]);
           constexpr uint32_t bytes = (PASSES == 3) ? 2u * Cfg::A_BYTES : (uint32_t)Cfg::A_BYTES;
           asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
@@ -399,9 +430,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
                          "l"(blk + 4096), "r"((uint32_t)Cfg::A_BYTES), "r"(bar)
                          : "memory");
         }
-        store_conv<BN, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, offA, offB);
+        store_conv<BNL, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, offA, offB);
       } else {
-        store_wgrad<BN, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, off0);
+        store_wgrad<BNL, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, off0);
       }
       fence_proxy_async();  // this thread's generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -431,11 +462,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
     // DISJOINT accumulators (warp 16: main term Ah*Bh into accumulators 1..3 round-robin; warp 17: correction terms
     // Al*Bh + Ah*Bl into accumulator 0), so the order of additions into every accumulator stays fixed (deterministic) while
     // the issue rate doubles.  Both commit to empty[s] / tmem_full (barrier count = 2).
-    if (PASSES == 3) {
-      if (warp == N_PROD_WARPS) issue_mmas<BN, PASSES, 1>(sh, smem_u32(smem), tmem_base, nkb);
-      else issue_mmas<BN, PASSES, 2>(sh, smem_u32(smem), tmem_base, nkb);
+    if (PAIR && rank != 0) {
+      // peer CTA of a pair: no MMAs; warp 16 relays "stage s of this CTA is full" to the leader's full[s]
+      if (warp == N_PROD_WARPS) {
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % Cfg::STAGES;
+          mbar_wait(&sh->full[s], (uint32_t)(i / Cfg::STAGES) & 1u);
+          if (lane == 0) mbar_arrive_cluster(&sh->full[s], 0);
+          __syncwarp();
+        }
+      }
+    } else if (PASSES == 3) {
+      if (warp == N_PROD_WARPS) issue_mmas<BN, PASSES, 1, PAIR>(sh, smem_u32(smem), tmem_base, nkb);
+      else issue_mmas<BN, PASSES, 2, PAIR>(sh, smem_u32(smem), tmem_base, nkb);
     } else if (warp == N_PROD_WARPS) {
-      issue_mmas<BN, PASSES, 0>(sh, smem_u32(smem), tmem_base, nkb);
+      issue_mmas<BN, PASSES, 0, PAIR>(sh, smem_u32(smem), tmem_base, nkb);
     }
   }
 
@@ -556,44 +597,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // neither CTA leaves (or frees its half of the pair's TMEM) while the other still works
   if (warp == N_PROD_WARPS) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int MODE, int BN, int PASSES, int KSZ>
+template <int MODE, int BN, int PASSES, int KSZ, int PAIR>
 int launch_tc_t(const TcParams<MODE>& prm, dim3 grid, cudaStream_t st) {
-  using Cfg = TcCfg<BN, PASSES>;
-  auto kern = gemm_tc_kernel<MODE, BN, PASSES, KSZ>;
+  using Cfg = TcCfg<BN, PASSES, PAIR>;
+  auto kern = gemm_tc_kernel<MODE, BN, PASSES, KSZ, PAIR>;
   static DevCache configured;  // per instantiation and device
   if (dev_needs(configured, Cfg::SMEM_BYTES))
     VQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  VQS_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, prm));
+  if (PAIR) {
+    cudaError_t e = launch_pdl_cluster(kern, dim3(grid.y, grid.x, grid.z), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, 2, 1, prm);
+    if (e != cudaSuccess) {
+      cudaFuncAttributes fa = {};
+      cudaFuncGetAttributes(&fa, kern);
+      set_error("pair GEMM launch failed: %s (grid %u x %u x %u, %d threads, %d B dynamic + %zu B static smem, %d registers, "
+                "max dynamic smem %d)", cudaGetErrorString(e), grid.x, grid.y, grid.z, TC_THREADS, Cfg::SMEM_BYTES,
+                fa.sharedSizeBytes, fa.numRegs, fa.maxDynamicSharedSizeBytes);
+      return (int)e;
+    }
+  } else {
+    VQS_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, prm));
+  }
   VQS_LAUNCH_CHECK();
   return 0;
 }
 
-template <int MODE, int BN, int PASSES>
+template <int MODE, int BN, int PASSES, int PAIR>
 int launch_tc_k(const TcParams<MODE>& prm, int ksz, dim3 grid, cudaStream_t st) {
+  // (wgrad rows are (c, j) pairs: the kernel divides by KSZ; the conv-like GEMM does not use it)
+  if (MODE == 0) return launch_tc_t<MODE, BN, PASSES, 1, PAIR>(prm, grid, st);
   switch (ksz) {
-    case 1: return launch_tc_t<MODE, BN, PASSES, 1>(prm, grid, st);
-    case 2: return launch_tc_t<MODE, BN, PASSES, 2>(prm, grid, st);
-    case 3: return launch_tc_t<MODE, BN, PASSES, 3>(prm, grid, st);
-    case 4: return launch_tc_t<MODE, BN, PASSES, 4>(prm, grid, st);
+    case 1: return launch_tc_t<MODE, BN, PASSES, 1, PAIR>(prm, grid, st);
+    case 2: return launch_tc_t<MODE, BN, PASSES, 2, PAIR>(prm, grid, st);
+    case 3: return launch_tc_t<MODE, BN, PASSES, 3, PAIR>(prm, grid, st);
+    case 4: return launch_tc_t<MODE, BN, PASSES, 4, PAIR>(prm, grid, st);
   }
   set_error("tcgen05 GEMM: kernel size %d not supported (1..4)", ksz);
   return VQS_ERR_ARG;
 }
 
+// CTA pairs (VQS_GEMM_PAIR=0 disables; read once): 128-column tiles whose grid has an even number of 128-row tiles
+bool pair_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("VQS_GEMM_PAIR");
+    cached = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  return cached == 1;
+}
+
 template <int MODE>
 int launch_tc(const TcParams<MODE>& prm, int ksz, int bn, int precision, dim3 grid, cudaStream_t st) {
+  const bool pair = bn == 128 && grid.y % 2 == 0 && pair_enabled();
   if (precision == 2) {
-    if (bn == 128) return launch_tc_k<MODE, 128, 3>(prm, ksz, grid, st);
-    return launch_tc_k<MODE, 64, 3>(prm, ksz, grid, st);
+    if (pair) return launch_tc_k<MODE, 128, 3, 1>(prm, ksz, grid, st);
+    if (bn == 128) return launch_tc_k<MODE, 128, 3, 0>(prm, ksz, grid, st);
+    return launch_tc_k<MODE, 64, 3, 0>(prm, ksz, grid, st);
   }
-  if (bn == 128) return launch_tc_k<MODE, 128, 1>(prm, ksz, grid, st);
-  return launch_tc_k<MODE, 64, 1>(prm, ksz, grid, st);
+  if (pair) return launch_tc_k<MODE, 128, 1, 1>(prm, ksz, grid, st);
+  if (bn == 128) return launch_tc_k<MODE, 128, 1, 0>(prm, ksz, grid, st);
+  return launch_tc_k<MODE, 64, 1, 0>(prm, ksz, grid, st);
 }
 
 }  // namespace

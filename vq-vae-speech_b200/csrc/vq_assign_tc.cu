@@ -592,14 +592,7 @@ constexpr int TBUF = 2;       // TMEM accumulators (CHUNK columns each)
 #endif
 constexpr int CLUSTER = VQS_LARGE_CLUSTER;   // CTAs that share every codebook chunk through a multicast bulk copy (L2 reads / CLUSTER)
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+// (cluster_ctarank / cluster_sync_all: tc_common.cuh)
 // tcgen05.commit that arrives on the barrier at the same shared-memory offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(

@@ -24,8 +24,10 @@ def convT_out_len(Lin, k, pad):
 # The tensor-core engines take the pre-split, pre-swizzled operand IMAGE (vqs_permute_weight modes 3 / 4; needs
 # Cred % 32 == 0); everything else runs the canonical arrangement on the exact-fp32 CUDA-core engine.
 import collections
+import os
 
 GemmW = collections.namedtuple('GemmW', 'A tap M Cred ksz')   # tap: 0 canonical, 1 tap-major matrix, 2 operand image
+_NO_IMAGE = os.environ.get('VQS_NO_IMAGE', '0') == '1'    # A/B probe: tap-major matrices instead of operand images
 _ROLES = {'conv_fwd': (3, None), 'conv_dgrad': (4, 0), 'convT_fwd': (4, 0), 'convT_dgrad': (3, None)}
 
 
@@ -39,6 +41,8 @@ def gemm_weight_layout(w_shape, role, precision=None):
     prec = ops.get_precision() if precision is None else precision
     M, Cred, k = _role_dims(w_shape, role)
     if prec != 'fp32' and Cred % 32 == 0:
+        if _NO_IMAGE:     # plain tap-major fp32 matrix [M][ksz][Cred]: the GEMM's producer warps load and split it themselves
+            return 1, {3: 1, 4: 2}[_ROLES[role][0]], M * Cred * k
         return 2, _ROLES[role][0], ((M + 127) // 128) * (k * Cred // 32) * 8192
     return 0, _ROLES[role][1], M * Cred * k
 
