@@ -46,9 +46,6 @@ constexpr int TC_THREADS = N_PROD + 64;   // + warp 16 (TMEM allocator, MMA issu
 // PAIR = 1: the CTA is one half of a cta_group::2 pair (cluster of two CTAs along grid.y = two neighbouring 128-row tiles of
 // M sharing one BN-column tile): it stages its own 128 x 32 block of A and only BNL = BN / 2 rows of B (rows
 // [rank * BNL, rank * BNL + BNL) of the tile); the MMAs (M = 256) are issued by the leader CTA and read both halves.
-#ifndef VQS_PAIR_STAGES
-#define VQS_PAIR_STAGES 4
-#endif
 template <int BN, int PASSES, int PAIR = 0>
 struct TcCfg {
   static constexpr int NOPS = (PASSES == 3) ? 2 : 1;                // hi (+ lo) copies per operand
@@ -57,7 +54,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
   // (3-pass, BN = 64: a ring of 3 x 48 KB measured faster than 4 -- 584 vs 743 cycles per k-block in the protocol
   // microbenchmark profiles/mma_pipe.cu)
-  static constexpr int STAGES_MAX = PAIR ? VQS_PAIR_STAGES : ((PASSES == 3) ? 3 : 4);
+  static constexpr int STAGES_MAX = PAIR ? 4 : ((PASSES == 3) ? 3 : 4);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > STAGES_MAX ? STAGES_MAX : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int NACC = (PASSES == 3) ? 4 : 1;                // TMEM accumulators of BN columns each
@@ -65,6 +62,46 @@ struct TcCfg {
   static constexpr int N_ISSUERS = (PASSES == 3) ? 2 : 1;           // threads that issue tcgen05.mma (see issue_mmas)
   static_assert(STAGES >= 2, "need at least a double buffer");
 };
+
+// Profiling builds only (-DVQS_GEMM_TIMING): CTA (0, 0, 0) leaves clock64() stamps of its phases in g_tc_timing, read back by
+// vqs_debug_gemm_timing (profiles/probe_gemm_phases.py).  0: prologue done, 1: first stage full (issuer), 2: last MMA issued,
+// 3: accumulators complete (epilogue warp 0), 4: epilogue done, 5: kernel entry, 6 / 7: globaltimer at entry / end.
+#ifdef VQS_GEMM_TIMING
+__device__ long long g_tc_timing[48];
+#define TC_STAMP(i)                                                                        \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_timing[i] = clock64(); \
+  } while (0)
+__device__ __forceinline__ long long tc_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP_PEER(i)                                                                   \
+  do {                                                                                     \
+    if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_timing[i] = clock64(); \
+  } while (0)
+#define TC_STAMP_NS(i)                                                                           \
+  do {                                                                                           \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_timing[i] = tc_globaltimer(); \
+  } while (0)
+#else
+#define TC_STAMP(i) do {} while (0)
+#define TC_STAMP_PEER(i) do {} while (0)
+#define TC_STAMP_NS(i) do {} while (0)
+#endif
+#ifdef VQS_GEMM_TIMING
+#define TC_ACC_BEGIN() const long long _t0 = clock64()
+#define TC_ACC_END(v) v += clock64() - _t0
+#define TC_ACC_PUT(i, v)                                                                 \
+  do {                                                                                   \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_timing[i] = (v);     \
+  } while (0)
+#else
+#define TC_ACC_BEGIN() do {} while (0)
+#define TC_ACC_END(v) do {} while (0)
+#define TC_ACC_PUT(i, v) do {} while (0)
+#endif
 
 struct TcShared {
   uint64_t full[4], empty[4], tmem_full;
@@ -251,6 +288,7 @@ __device__ __forceinline__ void issue_mmas(TcShared* sh, uint32_t smem_base, uin
   const uint64_t d0 = make_desc_sw128(smem_base);
   const bool elected = elect_one();
   uint32_t par = 0;
+  [[maybe_unused]] long long acc_full = 0;
 #pragma unroll 1
   for (int i0 = 0; i0 < nkb; i0 += S) {
     const uint32_t nz = i0 > 0 ? 1u : 0u;      // accumulate flag of the first MMA into each accumulator
@@ -259,8 +297,15 @@ __device__ __forceinline__ void issue_mmas(TcShared* sh, uint32_t smem_base, uin
 #pragma unroll
     for (int j = 0; j < S; ++j) {
       if (i0 + j < nkb) {
-        mbar_wait(&sh->full[j], par);
+        {
+          TC_ACC_BEGIN();
+          mbar_wait(&sh->full[j], par);
+          TC_ACC_END(acc_full);
+        }
         tc_fence_after();
+        if (ROLE != 2 && i0 == 0 && j == 0 && elected) TC_STAMP(1);
+        if (elected && i0 + j == 40) TC_STAMP(ROLE == 2 ? 25 : 23);
+        if (elected && i0 + j == 41) TC_STAMP(ROLE == 2 ? 28 : 27);
         const uint64_t a_hi = d0 + (uint64_t)((j * Cfg::STAGE_BYTES) >> 4);
         const uint64_t b_hi = a_hi + (uint64_t)(Cfg::A_BYTES >> 4);
         const uint64_t a_lo = a_hi + (uint64_t)((Cfg::A_BYTES + Cfg::B_BYTES) >> 4);
@@ -286,11 +331,14 @@ __device__ __forceinline__ void issue_mmas(TcShared* sh, uint32_t smem_base, uin
           }
         }
         if (elected) umma_done<PAIR>(&sh->empty[j]);  // frees the smem slot (of both CTAs of a pair) once this thread's MMAs have read it
+        if (elected && i0 + j == 40) TC_STAMP(ROLE == 2 ? 26 : 24);
         __syncwarp();
       }
     }
     par ^= 1u;
   }
+  if (ROLE != 2 && elected) TC_STAMP(2);
+  if (elected) TC_ACC_PUT(ROLE == 2 ? 15 : 14, acc_full);
   if (elected) umma_done<PAIR>(&sh->tmem_full);   // this thread's share of the accumulators is complete
   __syncwarp();
 }
@@ -307,6 +355,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   TcShared* sh = reinterpret_cast<TcShared*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    TC_STAMP(5);
+    TC_STAMP_NS(6);
+  }
   // pairs are the CTAs (2i, 2i + 1) of grid.x (cta_group::2 wants the pair adjacent in x): grid = (M tiles, N tiles, splits)
   const int tile_m = PAIR ? blockIdx.x : blockIdx.y, tile_n = PAIR ? blockIdx.y : blockIdx.x;
   const int m0 = tile_m * BM, n0 = tile_n * BN;
@@ -332,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
       // (pair: the leader's full[] also waits for one arrival of the peer's relay warp = "the peer's half is staged")
-      mbar_init(&sh->full[s], N_PROD_WARPS + (a_image ? 1 : 0) + ((PAIR && rank == 0) ? 1 : 0));
+      mbar_init(&sh->full[s], ((PAIR && MODE == 0) ? N_PROD_WARPS / Cfg::STAGES : N_PROD_WARPS) + (a_image ? 1 : 0) + ((PAIR && rank == 0) ? 1 : 0));
       mbar_init(&sh->empty[s], Cfg::N_ISSUERS);
     }
     mbar_init(&sh->tmem_full, Cfg::N_ISSUERS);
@@ -348,7 +400,146 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
   pdl_prologue_done();
+  if (tid == 0) TC_STAMP(0);
 
+  constexpr bool GROUPS = PAIR && MODE == 0;   // one group of producer warps per ring stage (conv-like GEMM of a CTA pair)
+  if constexpr (GROUPS) {
+  if (warp < N_PROD_WARPS) {
+    // ================= producers of a CTA pair: one group of warps per ring stage =================
+    // A thread that fills EVERY stage spends ~1000 cycles per k-block on serially dependent work (index arithmetic, waiting
+    // for an empty slot, stores, fence.proxy.async, arrive: measured with -DVQS_GEMM_TIMING) against 768 cycles of MMA
+    // work -- the producers' critical path, not their throughput, paced the ring.  Here group g = warp / 4 owns stage g and
+    // handles k-blocks g, g + 4, ...: four times the data per visit, a quarter of the visits, so the fixed costs are paid once
+    // per four k-blocks and the loads of the group's next k-block have ~3 k-block periods to land (one register buffer).
+    // Conv: a thread owns one B row (n) and 16 of the 32 channels: a warp's load covers 32 consecutive positions of one
+    // channel (whole 128-byte lines), its 16-byte stores hit each bank group from exactly four lanes (the minimum).
+    constexpr int S = Cfg::STAGES;
+    constexpr int GW = N_PROD_WARPS / S, GT = GW * 32;
+    static_assert(!PAIR || (N_PROD_WARPS % S == 0 && GW == 4), "one group of four producer warps per stage");
+    const int g = warp / GW, gt = tid - g * GT;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t sA_hi = smem_base + (uint32_t)(g * Cfg::STAGE_BYTES);
+    const uint32_t sB_hi = sA_hi + Cfg::A_BYTES;
+    const uint32_t sA_lo = sA_hi + Cfg::A_BYTES + Cfg::B_BYTES;
+    const uint32_t sB_lo = sA_lo + Cfg::A_BYTES;
+    [[maybe_unused]] long long acc_empty = 0, acc_store = 0, acc_fence = 0;
+    auto wait_empty = [&](int i) {
+      TC_ACC_BEGIN();
+      mbar_wait(&sh->empty[g], ((uint32_t)(i / S) & 1u) ^ 1u);
+      TC_ACC_END(acc_empty);
+    };
+    auto publish = [&]() {
+      TC_ACC_BEGIN();
+      fence_proxy_async();  // this thread's generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->full[g]);          // one arrival per warp of the group
+      TC_ACC_END(acc_fence);
+    };
+    if constexpr (MODE == 0) {
+      constexpr int PARTS = GT / BNL;          // threads per B row: 2
+      constexpr int CPT = BKF / PARTS;         // channels per thread: 16
+      static_assert(GT % BNL == 0 && BKF % PARTS == 0 && CPT % 4 == 0, "B row split");
+      const vqs_conv_gemm_desc& d = prm.p.d;
+      const int brow = gt % BNL, part = gt / BNL;
+      const int n = n0 + (int)rank * BNL + brow;
+      const bool n_ok = n < prm.p.Ntot;
+      uint32_t bb = 0, ll = 0;
+      if (n_ok) prm.p.divL.divmod((uint32_t)n, bb, ll);
+      const float* xb = d.X + (long long)bb * d.x_sb + (long long)(part * CPT) * d.x_sc;
+      const int lbase = (int)ll * d.l_mul + d.off;
+      uint32_t offB[CPT / 4];
+#pragma unroll
+      for (int ci = 0; ci < CPT / 4; ++ci) offB[ci] = (uint32_t)(brow * 128 + (((part * (CPT / 4) + ci) ^ (brow & 7)) << 4));
+      const int nkb_all = prm.p.Ktot / BKF;
+      const float* ablk = d.A + ((size_t)tile_m * nkb_all + kb_begin) * 8192;
+      // without an image (a_tap_major = 1: plain fp32 matrix [M][ksz][Cred]) the group loads and splits the 128 x 32 block of A
+      // itself: half the L2 -> SM bytes of the image (hi and lo copies), and with both operands at 43 KB per k-block and
+      // CTA the image-fed pair sat on the L2 slices' output limit (~42 B/clk per SM with every SM asking)
+      constexpr int AI = BM * 8 / GT;            // 16-byte chunks of A per thread: 8
+      const int arow0 = gt >> 3, acol = gt & 7;  // 8 consecutive threads read one 128-byte row segment
+      const uint32_t offA = (uint32_t)(arow0 * 128 + ((acol ^ (arow0 & 7)) << 4));   // rows step by 16: (r & 7) fixed
+      const float* arow = d.A + (size_t)(m0 + arow0) * prm.p.Ktot + (size_t)kb_begin * BKF + acol * 4;
+      const bool rl = d.x_relu != 0;
+      float v[CPT];
+      float4 va[AI];
+      auto load = [&](int i) {
+        if (!a_image) {
+#pragma unroll
+          for (int r = 0; r < AI; ++r)
+            va[r] = (m0 + arow0 + r * (GT / 8) < d.M)
+                        ? __ldg(reinterpret_cast<const float4*>(arow + (size_t)r * (GT / 8) * prm.p.Ktot + (size_t)i * BKF))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int kb = kb_begin + i;
+        const uint32_t j = prm.p.divCpb.div((uint32_t)kb);     // tap-major K: k-block = tap j, channels [c0, c0 + 32)
+        const int c0 = (kb - (int)j * prm.p.cpb) * BKF;
+        int pn = lbase + (int)j * d.j_mul;
+        bool ok = n_ok && pn >= 0;
+        if (d.l_div == 2) {
+          ok = ok && ((pn & 1) == 0);
+          pn >>= 1;
+        }
+        ok = ok && pn < d.Lin;
+        const float* ptr = xb + (long long)pn * d.x_sl + (long long)c0 * d.x_sc;
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) v[e] = ok ? __ldg(ptr + (long long)e * d.x_sc) : 0.f;
+      };
+      if (g < nkb) load(g);
+      for (int i = g; i < nkb; i += S) {
+        wait_empty(i);
+        if (gt == 0 && i == 40) TC_STAMP(20);
+        if (lane == 0 && i == 40) TC_STAMP(36 + (warp & 3));
+        if (gt == 0 && i == 40) TC_STAMP_PEER(29);
+        if (gt == 0 && i == 44) TC_STAMP(22);
+        TC_ACC_BEGIN();
+        if (!a_image) {
+#pragma unroll
+          for (int r = 0; r < AI; ++r) {
+            const uint32_t o = offA + (uint32_t)(r * (GT / 8) * 128);
+            st_vec4<PASSES>(sA_hi + o, sA_lo + o, va[r]);
+          }
+        } else if (gt == 0) {
+          // A operand: one bulk copy per copy (hi, lo) of the pre-built 128 x 32 image block of this k-block; the copy
+          // engine signals full[g] with complete_tx (async proxy: no fence needed), this thread adds the extra arrival
+          const float* blk = ablk + (size_t)i * 8192;
+          const uint32_t bar = smem_u32(&sh->full[g]);
+          constexpr uint32_t bytes = (PASSES == 3) ? 2u * Cfg::A_BYTES : (uint32_t)Cfg::A_BYTES;
+          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
+                       "r"(bytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           sA_hi),
+                       "l"(blk), "r"((uint32_t)Cfg::A_BYTES), "r"(bar)
+                       : "memory");
+          if (PASSES == 3)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             sA_lo),
+                         "l"(blk + 4096), "r"((uint32_t)Cfg::A_BYTES), "r"(bar)
+                         : "memory");
+        }
+#pragma unroll
+        for (int ci = 0; ci < CPT / 4; ++ci) {
+          float4 q = make_float4(v[ci * 4 + 0], v[ci * 4 + 1], v[ci * 4 + 2], v[ci * 4 + 3]);
+          if (rl) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
+          st_vec4<PASSES>(sB_hi + offB[ci], sB_lo + offB[ci], q);
+        }
+        TC_ACC_END(acc_store);
+        if (lane == 0 && i == 40) TC_STAMP(40 + (warp & 3));
+        publish();
+        if (gt == 0 && i == 40) TC_STAMP(21);
+        if (lane == 0 && i == 40) TC_STAMP(32 + (warp & 3));
+        if (gt == 0 && i == 40) TC_STAMP_PEER(30);
+        if (i + S < nkb) load(i + S);
+      }
+    }
+    if (tid == 0) {
+      TC_ACC_PUT(16, acc_empty);
+      TC_ACC_PUT(17, acc_store);
+      TC_ACC_PUT(18, acc_fence);
+      TC_STAMP(19);
+    }
+  }
+  } else {
   if (warp < N_PROD_WARPS) {
     // ================= producers =================
     const int ptid = tid;
@@ -401,10 +592,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
 #pragma unroll
       for (int ci = 0; ci < ConvRegs<BNL>::CH; ++ci) offB[ci] = 0;
     }
+    [[maybe_unused]] long long acc_empty = 0, acc_store = 0, acc_fence = 0;
     auto stage = [&](int i, const Regs& rg) {
       const int s = i % Cfg::STAGES;
       const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
-      mbar_wait(&sh->empty[s], ph ^ 1u);
+      {
+        TC_ACC_BEGIN();
+        mbar_wait(&sh->empty[s], ph ^ 1u);
+        TC_ACC_END(acc_empty);
+      }
+      TC_ACC_BEGIN();
       const uint32_t sA_hi = smem_base + (uint32_t)(s * Cfg::STAGE_BYTES);
       const uint32_t sB_hi = sA_hi + Cfg::A_BYTES;
       const uint32_t sA_lo = sA_hi + Cfg::A_BYTES + Cfg::B_BYTES;
@@ -434,9 +631,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
       } else {
         store_wgrad<BNL, PASSES>(prm.p, rg, sA_hi, sA_lo, sB_hi, sB_lo, off0);
       }
-      fence_proxy_async();  // this thread's generic-proxy smem writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->full[s]);          // one arrival per producer warp
+      TC_ACC_END(acc_store);
+      {
+        TC_ACC_BEGIN();
+        fence_proxy_async();  // this thread's generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->full[s]);          // one arrival per producer warp
+        TC_ACC_END(acc_fence);
+      }
     };
     Regs r0, r1, r2;
     if (nkb > 0) load(kb_begin, r0);
@@ -451,7 +653,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
       if (i + 4 < nkb) load(kb_begin + i + 4, r1);
       stage(i + 2, r2);
     }
-  } else {
+    if (tid == 0) {
+      TC_ACC_PUT(16, acc_empty);
+      TC_ACC_PUT(17, acc_store);
+      TC_ACC_PUT(18, acc_fence);
+      TC_STAMP(19);
+    }
+  }
+  }
+  if (warp >= N_PROD_WARPS) {
     // ================= MMA issuers =================
     // Measured with profiles/mma_rate.cu: the tensor core retires a 128 x 128 x 8 TF32 MMA every 64 cycles, but the round-1
     // issue loop (under `if (lane == 0)`: an ELECT / BRA.U.ANY loop per MMA, descriptors and the accumulator rotation
@@ -468,6 +678,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
         for (int i = 0; i < nkb; ++i) {
           const int s = i % Cfg::STAGES;
           mbar_wait(&sh->full[s], (uint32_t)(i / Cfg::STAGES) & 1u);
+          if (lane == 0 && i == 40) TC_STAMP_PEER(31);
           if (lane == 0) mbar_arrive_cluster(&sh->full[s], 0);
           __syncwarp();
         }
@@ -487,10 +698,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   if (warp < N_PROD_WARPS && (warp >> 2) < BN / 32) {
     const int q = warp & 3;                 // TMEM lane quarter -> rows m0 + 32 q .. + 31
     float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 33);  // stage buffers are idle by now
+    // lane r keeps the bias of row m0 + 32 q + r (fetched before the accumulators are waited for; the rows take it by
+    // shuffle: a load per row inside the store loop cost one exposed L2 latency per ROW -- 19 k of the kernel's 115 k cycles)
+    float bias_r = 0.f;
+    if constexpr (MODE == 0) {
+      const int mr = m0 + q * 32 + lane;
+      if (prm.p.d.bias != nullptr && prm.p.partial == nullptr && mr < prm.p.d.M) bias_r = __ldg(prm.p.d.bias + mr);
+    }
     if (nkb > 0) {
       mbar_wait(&sh->tmem_full, 0);
       tc_fence_after();
     }
+    if (tid == 0) TC_STAMP(3);
     int Ncols;
     if constexpr (MODE == 0) Ncols = prm.p.Ntot;
     else Ncols = prm.p.Nw;
@@ -524,9 +743,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
+      if (tid == 0) TC_STAMP(8);
 #pragma unroll
       for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
       __syncwarp();
+      if (tid == 0) TC_STAMP(9);
       const int n = n0 + blk * 32 + lane;
       const bool n_ok = n < Ncols;
       if constexpr (MODE == 0) {
@@ -544,56 +765,124 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
         uint32_t b = 0, l = 0;
         if (n_ok) prm.p.divL.divmod((uint32_t)n, b, l);
         const size_t col = (size_t)b * d.M * d.Lout + l;
-        // 8 rows at a time: all global reads of the batch are issued before the first use (the serial version paid one
-        // load latency per row: +50 us per 768x768x3 layer, profiles/r01c)
-        const float bias_on = d.bias ? 1.f : 0.f;
-#pragma unroll 1
-        for (int rb = 0; rb < 32; rb += 8) {
-          const int mb = m0 + q * 32 + rb;
-          if (mb >= d.M) break;
-          float x[8], pre[8], post[8];
-          bool k1[8], k2[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const bool live = n_ok && (mb + q < d.M);
-            const size_t o = col + (size_t)(mb + q) * d.Lout;
-            x[q] = stg[(rb + q) * 33 + lane];
-            pre[q] = (live && d.add_pre) ? d.add_pre[o] : 0.f;
-            post[q] = (live && d.add_post) ? d.add_post[o] : 0.f;
-            k1[q] = (live && d.mask_kind) ? tc_mask_on(d.mask, d.mask_kind, o) : true;
-            k2[q] = (live && d.out2 && d.mask2_kind) ? tc_mask_on(d.mask2, d.mask2_kind, o) : true;
+        // Every tensor of the epilogue is addressed as (per-lane base) + (row offset, 32 bits); the optional operands are
+        // warp-uniform branches around whole batches of 8 rows, so that a layer pays only for what it uses (the first version
+        // evaluated all of them as predicated-off code with 64-bit index arithmetic per row and tensor: ~800 instructions
+        // per batch, 16 k cycles per tile = a fifth of the kernel; measured with -DVQS_GEMM_TIMING).
+        const int mrow0 = m0 + q * 32;
+        const int rows_here = d.M - mrow0 < 32 ? d.M - mrow0 : 32;      // rows of this warp inside the matrix (<= 0: none)
+        float* const outp = d.out + col;
+        const bool has_pre = d.add_pre != nullptr, has_post = d.add_post != nullptr, has_mask = d.mask_kind != 0;
+        const bool has_out2 = d.out2 != nullptr, has_mask2 = has_out2 && d.mask2_kind != 0, pre_relu = d.add_pre_relu != 0;
+        const bool relu = d.relu != 0, has_mask_out = d.mask_out != nullptr;
+        const uint32_t Lo = (uint32_t)d.Lout;
+        if (!(has_pre || has_post || has_mask || has_out2)) {
+          // bias (+ ReLU, + mask_out): one shared-memory read, one shuffle and one store per row
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const float bias_m = __shfl_sync(0xffffffffu, bias_r, r);
+            float v1 = stg[r * 33 + lane] + bias_m;
+            if (relu) v1 = fmaxf(v1, 0.f);
+            if (r < rows_here && n_ok) {
+              const uint32_t ro = (uint32_t)(mrow0 + r) * Lo;
+              if (has_mask_out) d.mask_out[col + ro] = v1 > 0.f ? 1 : 0;
+              outp[ro] = v1;
+            }
           }
+        } else {
+          // 8 rows at a time: all global reads of the batch are issued before the first use (the serial version paid one
+          // load latency per row: +50 us per 768x768x3 layer, profiles/r01c)
+#pragma unroll 1
+          for (int rb = 0; rb < 32; rb += 8) {
+            if (rb >= rows_here) break;
+            float x[8], pre[8], post[8];
+            bool k1[8], k2[8];
+            bool live[8];
+            uint32_t ro[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int m = mb + q;
-            if (!n_ok || m >= d.M) continue;
-            const size_t o = col + (size_t)m * d.Lout;
-            float v1 = x[q];
-            if (bias_on != 0.f) v1 += __ldg(d.bias + m);
-            v1 += d.add_pre_relu ? fmaxf(pre[q], 0.f) : pre[q];
-            if (d.relu) v1 = fmaxf(v1, 0.f);
-            if (d.mask_out) d.mask_out[o] = v1 > 0.f ? 1 : 0;
-            if (!k1[q]) v1 = 0.f;
-            v1 += post[q];
-            d.out[o] = v1;
-            if (d.out2) d.out2[o] = k2[q] ? v1 : 0.f;
+            for (int q = 0; q < 8; ++q) {
+              live[q] = n_ok && (rb + q < rows_here);
+              ro[q] = (uint32_t)(mrow0 + rb + q) * Lo;
+              x[q] = stg[(rb + q) * 33 + lane];
+              pre[q] = 0.f;
+              post[q] = 0.f;
+              k1[q] = true;
+              k2[q] = true;
+            }
+            if (has_pre) {
+              const float* pp = d.add_pre + col;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) if (live[q]) pre[q] = pp[ro[q]];
+            }
+            if (has_post) {
+              const float* pp = d.add_post + col;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) if (live[q]) post[q] = pp[ro[q]];
+            }
+            if (has_mask) {
+              if (d.mask_kind == 1) {
+                const float* pp = reinterpret_cast<const float*>(d.mask) + col;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (live[q]) k1[q] = pp[ro[q]] > 0.f;
+              } else {
+                const unsigned char* pp = reinterpret_cast<const unsigned char*>(d.mask) + col;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (live[q]) k1[q] = pp[ro[q]] != 0;
+              }
+            }
+            if (has_mask2) {
+              if (d.mask2_kind == 1) {
+                const float* pp = reinterpret_cast<const float*>(d.mask2) + col;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (live[q]) k2[q] = pp[ro[q]] > 0.f;
+              } else {
+                const unsigned char* pp = reinterpret_cast<const unsigned char*>(d.mask2) + col;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (live[q]) k2[q] = pp[ro[q]] != 0;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float bias_m = __shfl_sync(0xffffffffu, bias_r, rb + q);   // (all lanes: before the per-lane skip)
+              float v1 = x[q] + bias_m;
+              v1 += pre_relu ? fmaxf(pre[q], 0.f) : pre[q];
+              if (relu) v1 = fmaxf(v1, 0.f);
+              const bool pos = v1 > 0.f;
+              if (!k1[q]) v1 = 0.f;
+              v1 += post[q];
+              if (live[q]) {
+                if (has_mask_out) d.mask_out[col + ro[q]] = pos ? 1 : 0;
+                outp[ro[q]] = v1;
+                if (has_out2) d.out2[col + ro[q]] = k2[q] ? v1 : 0.f;
+              }
+            }
+            if (tid == 0) TC_STAMP(10 + (rb >> 3));
           }
         }
       } else {
         const vqs_wgrad_desc& d = prm.p.d;
         float* out = prm.p.partial ? prm.p.partial + (size_t)blockIdx.z * d.M * prm.p.Nw : d.dW;
         const bool accum = (prm.p.partial == nullptr) && d.accumulate;
-        for (int r = 0; r < 32; ++r) {
-          const int m = m0 + q * 32 + r;
-          if (m >= d.M) break;
-          if (!n_ok) continue;
-          const size_t o = (size_t)m * prm.p.Nw + n;
-          const float x = stg[r * 33 + lane];
-          out[o] = accum ? out[o] + x : x;
+        const int rows_here = d.M - (m0 + q * 32) < 32 ? d.M - (m0 + q * 32) : 32;
+        float* const op = out + (size_t)(m0 + q * 32) * prm.p.Nw + n;
+        if (n_ok) {
+          if (accum) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+              if (r < rows_here) op[(size_t)r * prm.p.Nw] += stg[r * 33 + lane];
+          } else {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+              if (r < rows_here) op[(size_t)r * prm.p.Nw] = stg[r * 33 + lane];
+          }
         }
       }
       __syncwarp();
     }
+  }
+  if (tid == 0) {
+    TC_STAMP(4);
+    TC_STAMP_NS(7);
   }
   tc_fence_before();
   __syncthreads();
@@ -632,15 +921,18 @@ int launch_tc_t(const TcParams<MODE>& prm, dim3 grid, cudaStream_t st) {
 template <int MODE, int BN, int PASSES, int PAIR>
 int launch_tc_k(const TcParams<MODE>& prm, int ksz, dim3 grid, cudaStream_t st) {
   // (wgrad rows are (c, j) pairs: the kernel divides by KSZ; the conv-like GEMM does not use it)
-  if (MODE == 0) return launch_tc_t<MODE, BN, PASSES, 1, PAIR>(prm, grid, st);
-  switch (ksz) {
-    case 1: return launch_tc_t<MODE, BN, PASSES, 1, PAIR>(prm, grid, st);
-    case 2: return launch_tc_t<MODE, BN, PASSES, 2, PAIR>(prm, grid, st);
-    case 3: return launch_tc_t<MODE, BN, PASSES, 3, PAIR>(prm, grid, st);
-    case 4: return launch_tc_t<MODE, BN, PASSES, 4, PAIR>(prm, grid, st);
+  if constexpr (MODE == 0) {
+    return launch_tc_t<MODE, BN, PASSES, 1, PAIR>(prm, grid, st);
+  } else {
+    switch (ksz) {
+      case 1: return launch_tc_t<MODE, BN, PASSES, 1, PAIR>(prm, grid, st);
+      case 2: return launch_tc_t<MODE, BN, PASSES, 2, PAIR>(prm, grid, st);
+      case 3: return launch_tc_t<MODE, BN, PASSES, 3, PAIR>(prm, grid, st);
+      case 4: return launch_tc_t<MODE, BN, PASSES, 4, PAIR>(prm, grid, st);
+    }
+    set_error("tcgen05 GEMM: kernel size %d not supported (1..4)", ksz);
+    return VQS_ERR_ARG;
   }
-  set_error("tcgen05 GEMM: kernel size %d not supported (1..4)", ksz);
-  return VQS_ERR_ARG;
 }
 
 // CTA pairs (VQS_GEMM_PAIR=0 disables; read once): 128-column tiles whose grid has an even number of 128-row tiles
@@ -655,7 +947,8 @@ bool pair_enabled() {
 
 template <int MODE>
 int launch_tc(const TcParams<MODE>& prm, int ksz, int bn, int precision, dim3 grid, cudaStream_t st) {
-  const bool pair = bn == 128 && grid.y % 2 == 0 && pair_enabled();
+  bool pair = bn == 128 && grid.y % 2 == 0 && pair_enabled();
+  if constexpr (MODE == 0) pair = pair && prm.p.d.a_tap_major != 0;     // an image or the tap-major matrix (conv_tc_supported)
   if (precision == 2) {
     if (pair) return launch_tc_k<MODE, 128, 3, 1>(prm, ksz, grid, st);
     if (bn == 128) return launch_tc_k<MODE, 128, 3, 0>(prm, ksz, grid, st);
@@ -669,6 +962,7 @@ int launch_tc(const TcParams<MODE>& prm, int ksz, int bn, int precision, dim3 gr
 }  // namespace
 
 bool conv_tc_supported(const ConvParams& p) {
+  if ((long long)p.d.M * p.d.Lout >= (1ll << 31)) return false;              // (32-bit row offsets in the epilogue)
   if (p.d.a_tap_major == 2) return p.d.Cred % BKF == 0 && p.d.ksz >= 1;       // pre-built operand image
   return p.a_vec && p.d.a_tap_major == 1 && p.d.Cred % BKF == 0 && p.d.ksz >= 1;
 }
@@ -839,3 +1133,11 @@ int launch_wgrad_tc(const WgradParams& p, int precision, cudaStream_t st) {
 }
 
 }  // namespace vqs
+
+#ifdef VQS_GEMM_TIMING
+extern "C" int vqs_debug_gemm_timing(long long* out8) {
+  VQS_CUDA(cudaDeviceSynchronize());
+  VQS_CUDA(cudaMemcpyFromSymbol(out8, vqs::g_tc_timing, sizeof(long long) * 48));
+  return 0;
+}
+#endif

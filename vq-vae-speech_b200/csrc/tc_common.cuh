@@ -95,7 +95,10 @@ __device__ __forceinline__ void cluster_sync_all() {   // every thread of both C
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   uint32_t ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+  // (default semantics = release at CTA scope.  ".release.cluster" compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive: the
+  // relay warp of the pair GEMM then needed ~2500 cycles per k-block and paced the whole ring.  The data this arrival
+  // announces was published to the async proxy by its writers (fence.proxy.async) before they arrived on the local barrier.)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 // executed by one warp of EACH CTA of the pair
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
