@@ -81,4 +81,6 @@ for (B, C, L, k) in ((64, 768, 47, 3), (64, 768, 48, 3), (64, 768, 24, 3), (64, 
     if k == 3:
         ms = timeit(lambda: F.conv1d_wgrad(y, x, dW, 1, pad, ws))
         t = stamps()
-        print('%-44s %.4f ms | CTA0: issue loop %7d cyc, epilogue %6d, total %7d' % (tag + ' wgrad', ms, t[2] - t[1], t[4] - t[3], t[4] - t[5]), flush=True)
+        print('%-44s %.4f ms | CTA0: to first full %d | issue loop %7d cyc | drain %d | epilogue %6d | total %7d | issuers waiting: main %d corr %d | '
+              'producer thread 0: waiting for an empty stage %d, stores %d, fence + arrive %d' % (
+                  tag + ' wgrad', ms, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[4] - t[0], t[14], t[15], t[16], t[17], t[18]), flush=True)

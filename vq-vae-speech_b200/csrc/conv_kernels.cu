@@ -10,6 +10,8 @@
 #include "vqs_common.cuh"
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "gemm_params.cuh"
 
 namespace vqs {
@@ -355,7 +357,7 @@ struct WgradPlan {
   int bm, bn, splits, kt_per_split;
 };
 // bk = reduction elements per k-tile of the engine (16: CUDA cores, 32: tcgen05); tc tiles are always 128 x 128
-WgradPlan plan_wgrad(int M, int Nw, int Kred, int bk = BK, bool tc = false) {
+WgradPlan plan_wgrad(int M, int Nw, int Kred, int bk = BK, bool tc = false, bool pair = false) {
   WgradPlan pl;
   pl.bm = (tc || M > 64) ? 128 : 64;
   pl.bn = (tc || Nw > 64) ? 128 : 64;
@@ -369,6 +371,10 @@ WgradPlan plan_wgrad(int M, int Nw, int Kred, int bk = BK, bool tc = false) {
     // 1 split of 48 k-blocks = 0.081 ms; 768 x 768 x 3072: 12 splits = 3 rounds of 8 = 0.060 ms) -- plus the reduction pass
     // over the partials.  "3 CTAs per SM" (the first rule) paid a whole extra round on most layers of the step (1.52 ms of
     // wgrad per step; 1.34 ms with the cheapest split).
+    // CTA-pair kernel (gemm_tc.cu, even number of 128-row tiles): 0.55 us per k-block and ~7 us of prologue / first loads /
+    // epilogue per round (-DVQS_GEMM_TIMING stamps: 24.5 k cycles for 24 k-blocks, 12.5 k around them), so fewer, longer
+    // rounds and no reduction pass win more often than with the 1.6 us k-blocks of the single-CTA kernels
+    const double kb_us = pair ? 0.55 : 1.6, round_us = pair ? 7.0 : 4.0;
     const double sms = (double)num_sms();
     double best = 1e30;
     int best_kps = ktiles;
@@ -376,13 +382,19 @@ WgradPlan plan_wgrad(int M, int Nw, int Kred, int bk = BK, bool tc = false) {
       const int kps = (ktiles + s - 1) / s;
       const int se = (ktiles + kps - 1) / kps;
       const double rounds = ceil((double)tiles * se / sms);
-      double cost = rounds * (kps * 1.6 + 4.0);
+      double cost = rounds * (kps * kb_us + round_us);
       if (se > 1) cost += 2.0 + se * ((double)M * Nw * 4.0) / 5.0e6;
       if (cost < best - 1e-9) {
         best = cost;
         best_kps = kps;
       }
     }
+#ifdef VQS_DEBUG
+    if (const char* e = getenv("VQS_WGRAD_SPLITS")) {   // profiling builds: force the split (profiles/probe_wgrad_splits.py)
+      const int s = atoi(e);
+      if (s >= 1 && s <= max_s) best_kps = (ktiles + s - 1) / s;
+    }
+#endif
     pl.kt_per_split = best_kps;
     pl.splits = (ktiles + best_kps - 1) / best_kps;
     return pl;
@@ -578,6 +590,8 @@ extern "C" size_t vqs_wgrad_workspace_bytes(int M, int Cred, int ksz, int B, int
   if (M <= 0 || Cred <= 0 || ksz <= 0 || B <= 0 || La <= 0) return 0;
   WgradPlan pl = plan_wgrad(M, Cred * ksz, B * La);
   WgradPlan pt = plan_wgrad(M, Cred * ksz, B * La, 32, true);
+  WgradPlan pp = plan_wgrad(M, Cred * ksz, B * La, 32, true, true);
+  if (pp.splits > pt.splits) pt = pp;
   int s = pl.splits > pt.splits ? pl.splits : pt.splits;
   size_t need = s > 1 ? (size_t)s * M * Cred * ksz * sizeof(float) : 0;
   if (M % 128 == 0 && Cred % 128 == 0) {   // the TMA-fed kernel always goes through the workspace (tile blocks + reduce)
@@ -612,7 +626,7 @@ extern "C" int vqs_wgrad_gemm(const vqs_wgrad_desc* d, void* workspace, size_t w
     return launch_wgrad_tma(p, (float*)workspace, st);
   }
   const bool tc = d->precision != VQS_PREC_FP32 && wgrad_tc_supported(p);
-  WgradPlan pl = tc ? plan_wgrad(d->M, p.Nw, p.Kred, 32, true) : plan_wgrad(d->M, p.Nw, p.Kred);
+  WgradPlan pl = tc ? plan_wgrad(d->M, p.Nw, p.Kred, 32, true, wgrad_tc_pairs(p)) : plan_wgrad(d->M, p.Nw, p.Kred);
   p.splits = pl.splits;
   p.kt_per_split = pl.kt_per_split;
   p.divLa = FastDiv((uint32_t)d->La);

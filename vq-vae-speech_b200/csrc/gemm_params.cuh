@@ -29,6 +29,7 @@ int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st);
 int launch_wgrad_tc(const WgradParams& p, int precision, cudaStream_t st);
 bool conv_tc_supported(const ConvParams& p);
 bool wgrad_tc_supported(const WgradParams& p);
+bool wgrad_tc_pairs(const WgradParams& p);   // the tensor-core wgrad of this shape runs as CTA pairs (plan its split accordingly)
 // TMA-fed wgrad (wgrad_tma.cu): k-blocks are 32 positions of one utterance; plan the split over wgrad_tma_kblocks(p)
 bool wgrad_tma_supported(const WgradParams& p);
 int wgrad_tma_kblocks(const WgradParams& p);

@@ -56,7 +56,7 @@ struct TcCfg {
   // microbenchmark profiles/mma_pipe.cu)
   static constexpr int STAGES_MAX = PAIR ? 4 : ((PASSES == 3) ? 3 : 4);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > STAGES_MAX ? STAGES_MAX : (200 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, row table*/;
   static constexpr int NACC = (PASSES == 3) ? 4 : 1;                // TMEM accumulators of BN columns each
   static constexpr int TMEM_COLS = NACC * BN;
   static constexpr int N_ISSUERS = (PASSES == 3) ? 2 : 1;           // threads that issue tcgen05.mma (see issue_mmas)
@@ -106,6 +106,7 @@ __device__ __forceinline__ long long tc_globaltimer() {
 struct TcShared {
   uint64_t full[4], empty[4], tmem_full;
   uint32_t tmem_base;
+  int2 btab[64];   // wgrad pair kernel: per B row of this CTA (c * Lx, j * j_mul + off), or a very negative shift for rows beyond Nw
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
       // (pair: the leader's full[] also waits for one arrival of the peer's relay warp = "the peer's half is staged")
-      mbar_init(&sh->full[s], ((PAIR && MODE == 0) ? N_PROD_WARPS / Cfg::STAGES : N_PROD_WARPS) + (a_image ? 1 : 0) + ((PAIR && rank == 0) ? 1 : 0));
+      mbar_init(&sh->full[s], (PAIR ? N_PROD_WARPS / Cfg::STAGES : N_PROD_WARPS) + (a_image ? 1 : 0) + ((PAIR && rank == 0) ? 1 : 0));
       mbar_init(&sh->empty[s], Cfg::N_ISSUERS);
     }
     mbar_init(&sh->tmem_full, Cfg::N_ISSUERS);
@@ -394,6 +395,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
     if (PAIR) tmem_alloc_pair(&sh->tmem_base, Cfg::TMEM_COLS);
     else tmem_alloc(&sh->tmem_base, Cfg::TMEM_COLS);
   }
+  if constexpr (PAIR && MODE == 1) {
+    if (tid < BNL) {
+      const int nrow = n0 + (int)rank * BNL + tid;
+      const int c = nrow / KSZ, j = nrow - c * KSZ;
+      sh->btab[tid] = make_int2(c * prm.p.d.Lx, nrow < prm.p.Nw ? j * prm.p.d.j_mul + prm.p.d.off : -(1 << 29));
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();     // the peer's barriers exist before anything arrives on them
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   pdl_prologue_done();
   if (tid == 0) TC_STAMP(0);
 
-  constexpr bool GROUPS = PAIR && MODE == 0;   // one group of producer warps per ring stage (conv-like GEMM of a CTA pair)
+  constexpr bool GROUPS = PAIR != 0;           // one group of producer warps per ring stage (CTA pairs)
   if constexpr (GROUPS) {
   if (warp < N_PROD_WARPS) {
     // ================= producers of a CTA pair: one group of warps per ring stage =================
@@ -529,6 +537,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
         if (gt == 0 && i == 40) TC_STAMP(21);
         if (lane == 0 && i == 40) TC_STAMP(32 + (warp & 3));
         if (gt == 0 && i == 40) TC_STAMP_PEER(30);
+        if (i + S < nkb) load(i + S);
+      }
+    } else {
+      // wgrad: lane = position inside the k-block (global reads run along l: whole lines), warp wg of the group owns rows
+      // wg, wg + 4, ... of both tiles.  Per element: one address, one load, the split, two stores with immediate offsets.
+      constexpr int RA = BM / GW, RB = BNL / GW;     // 32 rows of A, 16 of B per thread
+      const vqs_wgrad_desc& d = prm.p.d;
+      const int wg = warp - g * GW;
+      // rows step by 4: (row & 7) alternates between two values, two rows further on the offset grows by 1024 B
+      const uint32_t off_e = sw128_off(wg, lane), off_o = sw128_off(wg + 4, lane);
+      const int na = (d.M - m0 - wg + GW - 1) / GW;  // A rows of this warp inside the matrix (<= 0: none)
+      const uint32_t btab = smem_u32(&sh->btab[wg]);
+      const uint32_t astep = (uint32_t)(GW * d.La);
+      const uint32_t Lx = (uint32_t)d.Lx;
+      const bool rl = d.x_relu != 0;
+      float va[RA], vb[RB];
+      auto load = [&](int i) {
+        const int kk = (kb_begin + i) * BKF + lane;
+        const bool k_ok = kk < prm.p.Kred;
+        uint32_t b = 0, l = 0;
+        if (k_ok) prm.p.divLa.divmod((uint32_t)kk, b, l);
+        const float* ab = d.Aact + ((size_t)b * d.M + m0 + wg) * d.La + l;
+        const float* xb = d.X + ((size_t)b * d.Cred) * d.Lx;
+        const int lp = k_ok ? (int)l * d.l_mul : -(1 << 29);   // (an invalid k never passes the bounds test below)
+#pragma unroll
+        for (int r = 0; r < RA; ++r) va[r] = (k_ok && r < na) ? __ldg(ab + r * astep) : 0.f;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          int xoff, pj;
+          asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(xoff), "=r"(pj) : "r"(btab + (uint32_t)(r * GW * 8)));
+          const int pn = lp + pj;
+          vb[r] = ((uint32_t)pn < Lx) ? __ldg(xb + (uint32_t)(xoff + pn)) : 0.f;
+        }
+      };
+      if (g < nkb) load(g);
+      for (int i = g; i < nkb; i += S) {
+        wait_empty(i);
+        TC_ACC_BEGIN();
+#pragma unroll
+        for (int r = 0; r < RA; ++r) {
+          const uint32_t o = ((r & 1) ? off_o : off_e) + (uint32_t)((r >> 1) * 1024);
+          st_elem<PASSES>(sA_hi + o, sA_lo + o, va[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const uint32_t o = ((r & 1) ? off_o : off_e) + (uint32_t)((r >> 1) * 1024);
+          st_elem<PASSES>(sB_hi + o, sB_lo + o, rl ? fmaxf(vb[r], 0.f) : vb[r]);
+        }
+        TC_ACC_END(acc_store);
+        publish();
         if (i + S < nkb) load(i + S);
       }
     }
@@ -894,6 +952,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
   }
 }
 
+// CTA pairs (VQS_GEMM_PAIR=0 disables; read once): 128-column tiles whose grid has an even number of 128-row tiles
+bool pair_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("VQS_GEMM_PAIR");
+    cached = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  return cached == 1;
+}
+
 template <int MODE, int BN, int PASSES, int KSZ, int PAIR>
 int launch_tc_t(const TcParams<MODE>& prm, dim3 grid, cudaStream_t st) {
   using Cfg = TcCfg<BN, PASSES, PAIR>;
@@ -935,16 +1003,6 @@ int launch_tc_k(const TcParams<MODE>& prm, int ksz, dim3 grid, cudaStream_t st) 
   }
 }
 
-// CTA pairs (VQS_GEMM_PAIR=0 disables; read once): 128-column tiles whose grid has an even number of 128-row tiles
-bool pair_enabled() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("VQS_GEMM_PAIR");
-    cached = (e != nullptr && atoi(e) == 0) ? 0 : 1;
-  }
-  return cached == 1;
-}
-
 template <int MODE>
 int launch_tc(const TcParams<MODE>& prm, int ksz, int bn, int precision, dim3 grid, cudaStream_t st) {
   bool pair = bn == 128 && grid.y % 2 == 0 && pair_enabled();
@@ -967,6 +1025,7 @@ bool conv_tc_supported(const ConvParams& p) {
   return p.a_vec && p.d.a_tap_major == 1 && p.d.Cred % BKF == 0 && p.d.ksz >= 1;
 }
 bool wgrad_tc_supported(const WgradParams& p) { return p.d.ksz >= 1 && p.d.ksz <= 4 && p.Kred >= 32; }
+bool wgrad_tc_pairs(const WgradParams& p) { return pair_enabled() && ((p.d.M + BM - 1) / BM) % 2 == 0; }
 
 // Folds the split-K partials partial[z][m][n = b * Lout + l] in a fixed order and applies the descriptor's fused epilogue
 // (vqs_b200.h: bias, add_pre (+relu), relu, mask_out, mask, add_post, out, out2 / mask2), coalesced along l.
