@@ -610,13 +610,32 @@ struct LShared {
 // ([hi | lo] x [k-block] x [128 rows x 128 B, SWIZZLE_128B]), so that a chunk is ONE contiguous block in global memory
 // and a single thread can stream it with cp.async.bulk (TMA bulk copy, completion on an mbarrier) -- 4096 16-byte
 // cp.async per chunk gave 10 B/clk/SM.  Also |e_k|^2 (fp32, sequential order = the exact path's) and +inf padding.
+// The |e_k|^2 term of the score rides in the GEMM as ONE EXTRA k-step (round 2): the row tile gets a constant column 1, the chunk a
+// column g_k = -(1 - EPS_SCORE) |e_k|^2 / 2 (split hi + lo like every operand), so the accumulator holds
+// v = x.e_k + g_k and the lower-bound score is just -2 v: the scan warps compare raw accumulator words (2 instructions per score
+// instead of a shared-memory load, two FMAs, a compare and a branch -- the scan, not the tensor pipe, bounded the kernel at 4850
+// cycles per chunk against 1536 of MMA work).  The extra operands are [128 rows x 8 floats] tiles in the un-swizzled K-major
+// canonical layout (8-row x 16-byte core matrices: LBO = 128 B between the two k-halves, SBO = 256 B between row groups).
+constexpr int AUG_FLOATS = CHUNK * 8;                 // one copy (hi or lo) of the extra k-step of a chunk
+__host__ __device__ __forceinline__ int aug_off(int row, int k) {   // float index inside such a tile
+  return (row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
+}
+__device__ __forceinline__ uint64_t make_desc_kmajor_plain(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;              // leading byte offset: next 16-byte k-chunk
+  d |= (uint64_t)(256 >> 4) << 32;              // stride byte offset: next group of 8 rows
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+
 __global__ void cb_prep_kernel(const float* __restrict__ cb, int K, int D, int Kpad, float* __restrict__ img,
                                float* __restrict__ se) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
   const int nkb = D / 32;
   const int copy_floats = nkb * CHUNK * 32;            // floats per copy of one chunk
-  float* chunk = img + (size_t)(k / CHUNK) * 2 * copy_floats;
+  float* chunk = img + (size_t)(k / CHUNK) * (2 * copy_floats + 2 * AUG_FLOATS);
   const int row = k % CHUNK;
   float s = 0.f;
   for (int j = 0; j < D; ++j) {
@@ -628,6 +647,14 @@ __global__ void cb_prep_kernel(const float* __restrict__ cb, int K, int D, int K
     s = fmaf(v, v, s);
   }
   se[k] = (k < K) ? s : INFINITY;
+  // extra k-step: column 0 = g_k (padding codes: a huge negative value, never among the best), columns 1..7 = 0
+  const float g = (k < K) ? -0.5f * (s * (1.f - EPS_SCORE)) : -1e30f;
+  const float gh = tf32_hi(g);
+  float* aug = chunk + 2 * copy_floats;
+  for (int j = 0; j < 8; ++j) {
+    aug[aug_off(row, j)] = j == 0 ? gh : 0.f;
+    aug[AUG_FLOATS + aug_off(row, j)] = j == 0 ? g - gh : 0.f;
+  }
 }
 
 struct Top3 {
@@ -647,6 +674,18 @@ __device__ __forceinline__ void top3_push(Top3& a, float sc, int k) {
   }
 }
 
+// the same for the three LARGEST values (the scan runs on v = x.e + g: largest v = smallest score)
+__device__ __forceinline__ void top3_push_max(Top3& a, float v, int k) {
+  if (v > a.t) {
+    const bool lb = v > a.b, ls = v > a.s;
+    a.t = ls ? a.s : v;
+    a.s = lb ? a.b : (ls ? v : a.s);
+    a.ks = lb ? a.kb : (ls ? k : a.ks);
+    a.b = lb ? v : a.b;
+    a.kb = lb ? k : a.kb;
+  }
+}
+
 __device__ __forceinline__ float exact_dist(const uint8_t* xh, const uint8_t* xl, int R, const float* __restrict__ e,
                                             float sx, float sek, int D) {
   float dot = 0.f;
@@ -661,11 +700,11 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
   const int D = p.D, K = p.K, nkb = p.nkb;
   const int a_copy = nkb * XT_BYTES;                 // one copy (hi or lo) of the row tile / of a code chunk
   uint8_t* xa = smem;                                 // [hi | lo]
-  uint8_t* bring = smem + 2 * a_copy;                 // BSTAGES x [hi | lo] chunk images
+  uint8_t* aaug = smem + 2 * a_copy;                  // the row tile's extra k-step: column 0 = 1 (4 KB, un-swizzled)
+  uint8_t* bring = aaug + AUG_FLOATS * 4;             // BSTAGES x [hi | lo | extra k-step hi | lo] chunk images
   const int b_copy = nkb * CHUNK * 128;
-  const int b_stage = 2 * b_copy;
-  float* se_s = reinterpret_cast<float*>(bring + BSTAGES * b_stage);   // [nchunks*CHUNK]
-  float* mrg = se_s + p.nchunks * CHUNK;                          // [128][6] merge buffer of the upper column half
+  const int b_stage = 2 * b_copy + 2 * AUG_FLOATS * 4;
+  float* mrg = reinterpret_cast<float*>(bring + BSTAGES * b_stage);   // [128][6] merge buffer of the upper column half
   int* sidx = reinterpret_cast<int*>(mrg + TROWS * 6);           // [128]
   LShared* sh = reinterpret_cast<LShared*>(sidx + TROWS);
 
@@ -682,7 +721,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == L_MMA_WARP) tmem_alloc(&sh->tmem_base, TBUF * CHUNK);
-  for (int i = tid; i < p.nchunks * CHUNK; i += L_THREADS) se_s[i] = __ldg(p.se + i);
+  const float* se_s = p.se;      // |e|^2 (only the settlement of near-ties reads it now: global memory)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // remote CTAs multicast into this CTA's ring and arrive on its barriers: all must be initialised
@@ -700,6 +739,11 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
     const int ptid = tid - L_SCAN_WARPS * 32;
     const uint32_t xh_a = smem_u32(xa), xl_a = xh_a + (uint32_t)a_copy;
     // ---- the row tile (once) ----
+    if (ptid < TROWS) {                                                  // extra k-step: (1, 0, ..., 0) per row
+      const uint32_t o = smem_u32(aaug) + (uint32_t)((ptid >> 3) * 256 + (ptid & 7) * 16);
+      sts_v4(o, make_float4(1.f, 0.f, 0.f, 0.f));
+      sts_v4(o + 128, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
     for (int e = ptid; e < (TROWS - rows) * D; e += L_PROD_THREADS) {   // zero tail rows
       uint32_t r, j;
       p.divD.divmod((uint32_t)e, r, j);
@@ -816,6 +860,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
       const uint64_t xh_d = make_desc_sw128(smem_u32(xa));
       const uint64_t xl_d = xh_d + (uint64_t)(a_copy >> 4);
       const uint64_t ring_d = make_desc_sw128(smem_u32(bring));
+      const uint64_t aug_a = make_desc_kmajor_plain(smem_u32(aaug));
+      const uint64_t aug_b0 = make_desc_kmajor_plain(smem_u32(bring) + (uint32_t)(2 * b_copy));
       mbar_wait(&sh->a_full, 0);
       uint32_t par = 0;
 #pragma unroll 1
@@ -844,6 +890,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
               }
             }
             if (elected) {
+              // the |e|^2 term: (1, 0, ...) x (g_hi, 0, ...) and (1, 0, ...) x (g_lo, 0, ...)
+              const uint64_t ab = aug_b0 + (uint64_t)((s * b_stage) >> 4);
+              umma_tf32(dst, aug_a, ab, idesc, 1u);
+              umma_tf32(dst, aug_a, ab + (uint64_t)((AUG_FLOATS * 4) >> 4), idesc, 1u);
+            }
+            if (elected) {
               umma_commit_multicast(&sh->b_empty[s], (uint16_t)((1u << CLUSTER) - 1));   // stage consumed, tell every CTA
               umma_commit(&sh->tmem_full[s]);
             }
@@ -859,7 +911,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
     const int q = warp & 3, half = warp >> 2;
     const int r = q * 32 + lane;
     Top3 top;
-    top.b = top.s = top.t = INFINITY;
+    top.b = top.s = top.t = -INFINITY;     // the three largest accumulator words v = x.e - (1 - EPS) |e|^2 / 2
     top.kb = top.ks = 0;
     for (int c = 0; c < p.nchunks; ++c) {
       const int a = c % TBUF;
@@ -879,9 +931,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
       if (lane == 0) mbar_arrive(&sh->tmem_empty[a]);      // scores are in registers: the accumulator is free again
       const int kbase = c * CHUNK + half * (CHUNK / 2);
 #pragma unroll
-      for (int j = 0; j < CHUNK / 2; ++j)
-        top3_push(top, fmaf(-2.f, v[j], se_s[kbase + j] * (1.f - EPS_SCORE)), kbase + j);
+      for (int j = 0; j < CHUNK / 2; ++j) top3_push_max(top, v[j], kbase + j);
     }
+    // back to lower-bound scores (smaller = better): s = (1 - EPS) |e|^2 - 2 x.e = -2 v
+    top.b *= -2.f;
+    top.s *= -2.f;
+    top.t *= -2.f;
     // ---- merge the two column halves (ties need no care here: equal scores are re-checked exactly) ----
     if (half == 1) {
       float* m = mrg + r * 6;
@@ -975,7 +1030,7 @@ bool search_large_supported(int K, int D) { return (D == 32 || D == 64) && K >= 
 
 size_t search_large_workspace_bytes(int K, int D) {
   const int nchunks = (K + CHUNK - 1) / CHUNK;
-  return ((size_t)nchunks * 2 * CHUNK * D + (size_t)nchunks * CHUNK + 8) * sizeof(float);
+  return ((size_t)nchunks * (2 * CHUNK * D + 2 * AUG_FLOATS) + (size_t)nchunks * CHUNK + 8) * sizeof(float);
 }
 
 int launch_search_large(const float* z, int layout, int B, int D, int T, const float* cb, int K, int64_t* idx,
@@ -983,7 +1038,7 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
   SearchLargeParams p;
   const int nchunks = (K + CHUNK - 1) / CHUNK;
   float* img = (float*)workspace;
-  float* se = img + (size_t)nchunks * 2 * CHUNK * D;
+  float* se = img + (size_t)nchunks * (2 * CHUNK * D + 2 * AUG_FLOATS);
   p.z = z; p.cb = cb; p.img = img; p.se = se; p.idx = idx; p.stats = stats;
   p.N = (long long)B * T;
   p.layout = layout; p.B = B; p.D = D; p.T = T; p.K = K;
@@ -1004,8 +1059,8 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
   cb_prep_kernel<<<(nchunks * CHUNK + 127) / 128, 128, 0, st>>>(cb, K, D, nchunks * CHUNK, img, se);
   VQS_LAUNCH_CHECK();
   const int a_copy = p.nkb * XT_BYTES;
-  const size_t smem = (size_t)2 * a_copy + (size_t)BSTAGES * 2 * p.nkb * CHUNK * 128 +
-                      ((size_t)nchunks * CHUNK + TROWS * 6 + TROWS) * 4 + sizeof(LShared) + 1024 + 64;
+  const size_t smem = (size_t)2 * a_copy + AUG_FLOATS * 4 + (size_t)BSTAGES * (2 * p.nkb * CHUNK * 128 + 2 * AUG_FLOATS * 4) +
+                      ((size_t)TROWS * 6 + TROWS) * 4 + sizeof(LShared) + 1024 + 64;
   if (smem > 226 * 1024) {
     set_error("vq_search_large: codebook of %d codes needs %zu bytes of shared memory", K, smem);
     return VQS_ERR_ARG;
