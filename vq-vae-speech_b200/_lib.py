@@ -121,8 +121,10 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    from . import build as _build
-    path = _build.build()
+    path = os.environ.get('VQS_LIB_PATH')      # profiling builds (profiles/build_variant.py); default: the in-tree library
+    if not path:
+        from . import build as _build
+        path = _build.build()
     if not os.path.exists(path):
         raise RuntimeError('libvqs_b200.so is missing (%s); run `python vq-vae-speech_b200/build.py`' % path)
     lib = ctypes.CDLL(path)

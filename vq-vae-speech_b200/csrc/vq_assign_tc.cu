@@ -554,12 +554,21 @@ int launch_assign_tc(const float* z, int layout, int B, int D, int T, const floa
 
 // =====================================================================================================================
 // Large codebooks (K > what fits shared memory, e.g. the 512 / 4096-code sweep): the distance search is a real GEMM
-// N x 64 . 64 x K.  One CTA = one 128-row tile that stays resident in shared memory (hi/lo split) while the codebook is
-// streamed past it in 128-code chunks (pre-split hi/lo copies in global memory, cp.async into a 2-stage ring), 24 tf32
-// MMAs per chunk into one of two TMEM accumulators; 8 scan warps keep a running top-3 of the scores per row.  Rows whose
-// best and second-best scores are closer than 2*tol are settled exactly in fp32 (top-2 when the third is far, a full
-// scan otherwise), so indices equal the fp32 search.  Statistics go straight to global memory with atomics (contention
-// is low at large K), as in the CUDA-core kernel.
+// N x 64 . 64 x K.  PERSISTENT kernel, one CTA per SM walking over 128-row tiles: a tile stays in shared memory (hi/lo split)
+// while the codebook is streamed past it in 128-code chunks (pre-built shared-memory images in global memory, one
+// cp.async.bulk per chunk into a 2-stage ring), 24 + 2 tf32 MMAs per chunk into one of two TMEM accumulators; 8 scan warps keep
+// a running top-3 of the scores per row.  Rows whose best and second-best scores are closer than 2*tol are settled exactly
+// in fp32, so indices equal the fp32 search.
+//
+// Why persistent (round 2, profiles/r04b_k4096_phases.txt): one CTA per tile spent 18.7 us per tile with NOTHING to do (launch,
+// barrier / TMEM set-up, the row tile's HBM round trip before the first MMA, merge + settlement + 8192 statistics atomics after the
+// last one) against 27.8 us of MMA work per tile at K = 4096, and a 220 KB CTA cannot share its SM with a second one.  Now the next
+// tile's rows are prefetched into registers while the MMAs of the current tile run and stored the moment the last MMA has read
+// the tile (a_empty: tcgen05.commit), the chunk ring and the two accumulators run on across tile boundaries, and the
+// statistics of tile i (global atomics, low contention at large K) are issued by the otherwise idle producer warps from
+// the L2-hot rows while the scan warps are already on tile i + 1.
+// Warp roles (576 threads): 0-7 scan (TMEM lane quarter = warp & 3, column half = warp >> 2), 8-15 row-tile producers +
+// statistics, 16 MMA issuer + TMEM owner, 17 chunk streamer (one lane).
 // =====================================================================================================================
 namespace vqs {
 
@@ -573,36 +582,43 @@ struct SearchLargeParams {
   long long N;
   int layout, B, D, T, K;
   int nkb, nchunks, ntiles;
-  int debug;            // profiling aid (env VQS_TC_DEBUG): bit 3 skips the score scan, bit 4 the TMEM loads as well
-  float* dbg;           // [2] debug counters: rows settled by the top-2 check / by a full exact scan
+  int debug;            // phase probes of -DVQS_DEBUG builds (env VQS_TC_DEBUG), see L_DBG
+  float* dbg;           // [3] counters: rows settled by the top-2 check / a 64-code group scan / a full exact scan
   FastDiv divD;
 };
 
 namespace {
 
+#ifdef VQS_DEBUG   /* phase probes of profiling builds: bit 3 no score scan, bit 4 no MMAs, bit 5 no chunk loads (WRONG results) */
+#define L_DBG(bit) (p.debug & (bit))
+#else
+#define L_DBG(bit) false
+#endif
 constexpr int L_SCAN_WARPS = 8, L_PROD_WARPS = 8;
 constexpr int L_PROD_THREADS = L_PROD_WARPS * 32;
 constexpr int L_MMA_WARP = L_SCAN_WARPS + L_PROD_WARPS;
-constexpr int L_THREADS = (L_MMA_WARP + 1) * 32;
+constexpr int L_LOAD_WARP = L_MMA_WARP + 1;
+constexpr int L_THREADS = (L_LOAD_WARP + 1) * 32;
 constexpr int CHUNK = 128;    // codes per streamed chunk (UMMA N)
-constexpr int BSTAGES = 2;    // chunk ring depth
-constexpr int TBUF = 2;       // TMEM accumulators (CHUNK columns each)
-#ifndef VQS_LARGE_CLUSTER
-#define VQS_LARGE_CLUSTER 1
+constexpr int BSTAGES = 2;    // chunk ring depth (shared memory)
+#ifndef VQS_LARGE_BBARS
+#define VQS_LARGE_BBARS BSTAGES
 #endif
-constexpr int CLUSTER = VQS_LARGE_CLUSTER;   // CTAs that share every codebook chunk through a multicast bulk copy (L2 reads / CLUSTER)
+// ring depth of the BARRIERS: > BSTAGES only in a probe build run with the chunk loads off (VQS_TC_DEBUG bit 5), where the stages
+// may alias -- "what would a deeper ring buy" without having the shared memory for it
+constexpr int BBARS = VQS_LARGE_BBARS, BBARS_LOG2 = BBARS == 4 ? 2 : 1;
+#ifndef VQS_LARGE_TBUF
+#define VQS_LARGE_TBUF 4
+#endif
+constexpr int TBUF = VQS_LARGE_TBUF;   // TMEM accumulators (CHUNK columns each; 4 x 128 = all 512 columns)
+constexpr int TBUF_LOG2 = TBUF == 4 ? 2 : 1;
+static_assert(TBUF == 2 || TBUF == 4, "accumulator ring of 2 or 4");
+// (Sharing every chunk between the CTAs of a cluster through a multicast bulk copy was built and measured: 2 CTAs 3.76 ms
+// against 3.70 ms alone, 4 CTAs 4.28 ms at N = 2^20 -- the L2 -> SM stream of 74 KB per chunk per SM is not the limit.)
 
-// (cluster_ctarank / cluster_sync_all: tc_common.cuh)
-// tcgen05.commit that arrives on the barrier at the same shared-memory offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-
+constexpr int M3_MAX = 7;     // whole-codebook re-scores per tile done by all producer warps together (more: one warp each)
 struct LShared {
-  uint64_t a_full, b_full[BSTAGES], b_empty[BSTAGES], tmem_full[TBUF], tmem_empty[TBUF];
+  uint64_t a_full, a_empty, b_full[BBARS], b_empty[BBARS], tmem_full[TBUF], tmem_empty[TBUF], idx_ready[2];
   uint32_t tmem_base;
 };
 
@@ -611,11 +627,13 @@ struct LShared {
 // and a single thread can stream it with cp.async.bulk (TMA bulk copy, completion on an mbarrier) -- 4096 16-byte
 // cp.async per chunk gave 10 B/clk/SM.  Also |e_k|^2 (fp32, sequential order = the exact path's) and +inf padding.
 // The |e_k|^2 term of the score rides in the GEMM as ONE EXTRA k-step (round 2): the row tile gets a constant column 1, the chunk a
-// column g_k = -(1 - EPS_SCORE) |e_k|^2 / 2 (split hi + lo like every operand), so the accumulator holds
-// v = x.e_k + g_k and the lower-bound score is just -2 v: the scan warps compare raw accumulator words (2 instructions per score
-// instead of a shared-memory load, two FMAs, a compare and a branch -- the scan, not the tensor pipe, bounded the kernel at 4850
-// cycles per chunk against 1536 of MMA work).  The extra operands are [128 rows x 8 floats] tiles in the un-swizzled K-major
-// canonical layout (8-row x 16-byte core matrices: LBO = 128 B between the two k-halves, SBO = 256 B between row groups).
+// column g_k = -(1 - EPS_LARGE) |e_k|^2 / 2 (split hi + lo like every operand), so the accumulator holds
+// v = x.e_k + g_k and the lower-bound score is just -2 v: the scan warps work on raw accumulator words.  The extra operands are
+// [128 rows x 8 floats] tiles in the un-swizzled K-major canonical layout (8-row x 16-byte core matrices: LBO = 128 B between
+// the two k-halves, SBO = 256 B between row groups).
+// Score tolerance of this kernel: EPS_SCORE plus the 6 mantissa bits the scan overwrites with the column number
+// (|pv - v| < 64 ulp <= 2^-17 |v|, |v| <= |x||e| + |e|^2 / 2 <= |x|^2 + |e|^2, score = -2 v: 2^-16 (|x|^2 + |e|^2)).
+constexpr float EPS_LARGE = EPS_SCORE + 1.53e-5f;
 constexpr int AUG_FLOATS = CHUNK * 8;                 // one copy (hi or lo) of the extra k-step of a chunk
 __host__ __device__ __forceinline__ int aug_off(int row, int k) {   // float index inside such a tile
   return (row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
@@ -648,7 +666,7 @@ __global__ void cb_prep_kernel(const float* __restrict__ cb, int K, int D, int K
   }
   se[k] = (k < K) ? s : INFINITY;
   // extra k-step: column 0 = g_k (padding codes: a huge negative value, never among the best), columns 1..7 = 0
-  const float g = (k < K) ? -0.5f * (s * (1.f - EPS_SCORE)) : -1e30f;
+  const float g = (k < K) ? -0.5f * (s * (1.f - EPS_LARGE)) : -1e30f;
   const float gh = tf32_hi(g);
   float* aug = chunk + 2 * copy_floats;
   for (int j = 0; j < 8; ++j) {
@@ -661,8 +679,8 @@ struct Top3 {
   float b, s, t;
   int kb, ks;
 };
-// Almost every score is NOT among the three smallest seen so far (after 1000 codes fewer than 1 in 300 is), so the common
-// path is one compare and a branch the whole warp skips; the update itself is branch-free selects.
+// Almost every candidate is NOT among the three best seen so far, so the common path is one compare and a branch the whole
+// warp skips; the update itself is branch-free selects.
 __device__ __forceinline__ void top3_push(Top3& a, float sc, int k) {
   if (sc < a.t) {
     const bool lb = sc < a.b, ls = sc < a.s;
@@ -673,7 +691,6 @@ __device__ __forceinline__ void top3_push(Top3& a, float sc, int k) {
     a.kb = lb ? k : a.kb;
   }
 }
-
 // the same for the three LARGEST values (the scan runs on v = x.e + g: largest v = smallest score)
 __device__ __forceinline__ void top3_push_max(Top3& a, float v, int k) {
   if (v > a.t) {
@@ -686,11 +703,90 @@ __device__ __forceinline__ void top3_push_max(Top3& a, float v, int k) {
   }
 }
 
-__device__ __forceinline__ float exact_dist(const uint8_t* xh, const uint8_t* xl, int R, const float* __restrict__ e,
-                                            float sx, float sek, int D) {
-  float dot = 0.f;
-  for (int j = 0; j < D; ++j) dot = fmaf(ld_exact(xh, xl, elem_off(R, j, TROWS)), __ldg(e + j), dot);
-  return __fsub_rn(__fadd_rn(sx, sek), __fmul_rn(2.0f, dot));
+// Element (row, column j) of the row space, from global memory (the settlement paths and the statistics run after the
+// tile's shared-memory copy may already hold the next tile; the rows are L2-hot).  (B, D, T) input is the reference's
+// (D, T, B) row space cut into rows of D (vector_quantizer_ema.py:104-107).
+__device__ __forceinline__ float z_elem(const SearchLargeParams& p, long long row, int j) {
+  const long long f = row * p.D + j;
+  if (p.layout == VQS_LAYOUT_FLAT_ND) return __ldg(p.z + f);
+  const long long P = (long long)p.T * p.B;
+  const long long d = f / P, pp = f - d * P;
+  const long long t = pp / p.B, b = pp - t * p.B;
+  return __ldg(p.z + ((size_t)b * p.D + (size_t)d) * p.T + t);
+}
+// Exact settlement of one row (the rare rows whose tensor-core scores cannot certify the argmin): candidates are re-scored
+// with the fp32 formula AND summation order of the CUDA-core kernel (vq_kernels.cu: |x|^2 as 8 partials over
+// j = 4p + 32 s + e and a butterfly tree, the dot product as one ascending fmaf chain), lowest index on equal distances.
+// The row lives distributed over the lanes of a warp (x[lane], x[lane + 32]) and is broadcast by shuffles; one lane scores
+// one candidate per pass, its code row fetched as 16-byte pieces BEFORE the dependent fmaf chain starts.
+struct RowX {
+  float x0, x1, sx;
+};
+__device__ __noinline__ RowX settle_load_row(const SearchLargeParams& p, long long row, int lane) {
+  const int D = p.D;
+  RowX rx;
+  rx.x0 = z_elem(p, row, lane);
+  rx.x1 = D > 32 ? z_elem(p, row, lane + 32) : 0.f;
+  float part[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float s = 0.f;
+    for (int j = q * 4; j < D; j += 32) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = __shfl_sync(0xffffffffu, (j + e) < 32 ? rx.x0 : rx.x1, (j + e) & 31);
+        s = fmaf(a, a, s);
+      }
+    }
+    part[q] = s;
+  }
+  const float a0 = part[0] + part[1], a1 = part[2] + part[3], a2 = part[4] + part[5], a3 = part[6] + part[7];
+  const float b0 = a0 + a1, b1 = a2 + a3;
+  rx.sx = b0 + b1;
+  return rx;
+}
+// candidates: list == 1: the two codes (ka, kb2); else the n codes from k0 on.  Returns the warp's best (distance, code).
+__device__ __noinline__ void settle_score(const SearchLargeParams& p, const RowX& rx, int list, int ka, int kb2, int k0, int n,
+                                          int lane, float& bd_out, int& bk_out) {
+  const int D = p.D;
+  float bd = INFINITY;
+  int bk = 0x7fffffff;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int c = c0 + lane;
+    const bool ok = c < n;
+    const int k = !ok ? 0 : (list ? (c == 0 ? ka : kb2) : k0 + c);
+    const float4* e = reinterpret_cast<const float4*>(p.cb + (size_t)k * D);
+    float4 ev[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) ev[u] = (u * 4 < D) ? __ldg(e + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (u * 4 < D) {
+        const float xs = u < 8 ? rx.x0 : rx.x1;
+        dot = fmaf(__shfl_sync(0xffffffffu, xs, (u * 4) & 31), ev[u].x, dot);
+        dot = fmaf(__shfl_sync(0xffffffffu, xs, (u * 4 + 1) & 31), ev[u].y, dot);
+        dot = fmaf(__shfl_sync(0xffffffffu, xs, (u * 4 + 2) & 31), ev[u].z, dot);
+        dot = fmaf(__shfl_sync(0xffffffffu, xs, (u * 4 + 3) & 31), ev[u].w, dot);
+      }
+    }
+    const float dd = __fsub_rn(__fadd_rn(rx.sx, __ldg(p.se + k)), __fmul_rn(2.0f, dot));
+    if (ok && (dd < bd || (dd == bd && k < bk))) {
+      bd = dd;
+      bk = k;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+    const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+    if (od < bd || (od == bd && ok < bk)) {
+      bd = od;
+      bk = ok;
+    }
+  }
+  bd_out = bd;
+  bk_out = bk;
 }
 
 __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const SearchLargeParams p) {
@@ -704,320 +800,425 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
   uint8_t* bring = aaug + AUG_FLOATS * 4;             // BSTAGES x [hi | lo | extra k-step hi | lo] chunk images
   const int b_copy = nkb * CHUNK * 128;
   const int b_stage = 2 * b_copy + 2 * AUG_FLOATS * 4;
-  float* mrg = reinterpret_cast<float*>(bring + BSTAGES * b_stage);   // [128][6] merge buffer of the upper column half
-  int* sidx = reinterpret_cast<int*>(mrg + TROWS * 6);           // [128]
-  LShared* sh = reinterpret_cast<LShared*>(sidx + TROWS);
+  float* mrg = reinterpret_cast<float*>(bring + BSTAGES * b_stage);   // [2][128][6] merge buffers of the upper column half
+  int* sidx = reinterpret_cast<int*>(mrg + 2 * TROWS * 6);            // [2][128] indices of a tile (scan -> producers)
+  int* saux = sidx + 2 * TROWS;                                       // [2][128] second-best code | settlement mode << 16
+  int* m3 = saux + 2 * TROWS;                                         // [2][1 + M3_MAX] rows that need a whole-codebook re-score
+  float* red = reinterpret_cast<float*>(m3 + 2 * (1 + M3_MAX));       // [8][2] per-warp partial results of such a re-score
+  LShared* sh = reinterpret_cast<LShared*>(red + 2 * L_PROD_WARPS);
 
   if (tid == 0) {
+    m3[0] = m3[1 + M3_MAX] = 0;
     mbar_init(&sh->a_full, L_PROD_WARPS);
-    for (int s = 0; s < BSTAGES; ++s) {
+    mbar_init(&sh->a_empty, 1 + L_SCAN_WARPS / 2);   // the last MMA of the tile has read it and the |x|^2 readers are done
+    for (int s = 0; s < BBARS; ++s) {
       mbar_init(&sh->b_full[s], 1);
-      mbar_init(&sh->b_empty[s], CLUSTER);          // every CTA of the cluster has consumed the stage
+      mbar_init(&sh->b_empty[s], 1);
     }
     for (int s = 0; s < TBUF; ++s) {
       mbar_init(&sh->tmem_full[s], 1);
       mbar_init(&sh->tmem_empty[s], L_SCAN_WARPS);
     }
+    mbar_init(&sh->idx_ready[0], L_SCAN_WARPS / 2);
+    mbar_init(&sh->idx_ready[1], L_SCAN_WARPS / 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == L_MMA_WARP) tmem_alloc(&sh->tmem_base, TBUF * CHUNK);
-  const float* se_s = p.se;      // |e|^2 (only the settlement of near-ties reads it now: global memory)
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();   // remote CTAs multicast into this CTA's ring and arrive on its barriers: all must be initialised
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
-  const int tile = blockIdx.x;
-  const long long r0 = (long long)tile * TROWS;
-  const long long left = p.N - r0;
-  const int rows = left < 0 ? 0 : (left < TROWS ? (int)left : TROWS);   // padding CTAs of the last cluster own no rows
+  const int ntl = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
   const uint8_t* xh = xa;
-  const uint8_t* xl = xa + a_copy;
 
   if (warp >= L_SCAN_WARPS && warp < L_MMA_WARP) {
-    // ================= producers =================
+    // ================= producers: row tiles in, statistics out =================
     const int ptid = tid - L_SCAN_WARPS * 32;
     const uint32_t xh_a = smem_u32(xa), xl_a = xh_a + (uint32_t)a_copy;
-    // ---- the row tile (once) ----
-    if (ptid < TROWS) {                                                  // extra k-step: (1, 0, ..., 0) per row
+    if (ptid < TROWS) {                                                  // extra k-step: (1, 0, ..., 0) per row, once
       const uint32_t o = smem_u32(aaug) + (uint32_t)((ptid >> 3) * 256 + (ptid & 7) * 16);
       sts_v4(o, make_float4(1.f, 0.f, 0.f, 0.f));
       sts_v4(o + 128, make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    for (int e = ptid; e < (TROWS - rows) * D; e += L_PROD_THREADS) {   // zero tail rows
-      uint32_t r, j;
-      p.divD.divmod((uint32_t)e, r, j);
-      const uint32_t off = elem_off(rows + (int)r, (int)j, TROWS);
-      sts_f32(xh_a + off, 0.f);
-      sts_f32(xl_a + off, 0.f);
-    }
-    if (p.layout == VQS_LAYOUT_FLAT_ND) {
-      const int cpr = D >> 2;
-      const float4* src = reinterpret_cast<const float4*>(p.z + r0 * D);
-      const int total = rows * cpr;
-      for (int c0 = ptid; c0 < total; c0 += L_PROD_THREADS * 4) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = c0 + u * L_PROD_THREADS;
-          v[u] = (c < total) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = c0 + u * L_PROD_THREADS;
-          if (c < total) {
-            const uint32_t row = p.divD.div((uint32_t)c << 2);
-            const int c16 = c - (int)row * cpr;
-            const uint32_t off = (uint32_t)((c16 >> 3) * XT_BYTES + row * 128 + (((c16 & 7) ^ (row & 7)) << 4));
-            const float4 h = make_float4(tf32_hi(v[u].x), tf32_hi(v[u].y), tf32_hi(v[u].z), tf32_hi(v[u].w));
-            sts_v4(xh_a + off, h);
-            sts_v4(xl_a + off, make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w));
-          }
-        }
-      }
-    } else if (rows > 0) {
-      const int B = p.B, T = p.T;
-      const long long P = (long long)T * B;
-      const long long f0 = r0 * D;
-      const long long f1 = f0 + (long long)rows * D;
-      const long long d_first = f0 / P, d_last = (f1 - 1) / P;
-      for (long long d = d_first; d <= d_last; ++d) {
-        const long long base = d * P;
-        const int p0 = (int)((f0 > base ? f0 : base) - base);
-        const int p1 = (int)((f1 < base + P ? f1 : base + P) - base);
-        const int t0 = p0 / B, t1 = (p1 + B - 1) / B;
-        const int span = t1 - t0, count = span * B;
-        const int qs = L_PROD_THREADS / span, rs = L_PROD_THREADS - qs * span;
-        int b = ptid / span, tt = ptid - b * span;
-        const int foff = (int)(base - f0);
-        const float* zd = p.z + (size_t)d * T;
-        for (int e = ptid; e < count; e += L_PROD_THREADS * 8) {
-          float v[8];
-          uint32_t off[8];
-          bool ok[8];
+    const int cpr = D >> 2;                      // 16-byte pieces per row
+    const int cshift = D == 64 ? 4 : 3;          // log2(cpr): D is 32 or 64 (search_large_supported)
+    for (int i = 0; i <= ntl; ++i) {
+      if (i < ntl) {
+        const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TROWS;
+        const long long left = p.N - r0;
+        const int rows = left < TROWS ? (int)left : TROWS;
+        if (p.layout == VQS_LAYOUT_FLAT_ND) {
+          // the whole tile in registers BEFORE the wait: the HBM round trip hides under the previous tile's MMAs
+          const float4* src = reinterpret_cast<const float4*>(p.z + r0 * D);
+          const int total = rows * cpr;
+          float4 v[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int t = t0 + tt;
-            const int pp = t * B + b;
-            ok[u] = (e + u * L_PROD_THREADS < count) && pp >= p0 && pp < p1;
-            v[u] = ok[u] ? __ldg(zd + (size_t)b * D * T + t) : 0.f;
-            uint32_t row, j;
-            p.divD.divmod((uint32_t)(foff + pp), row, j);
-            off[u] = elem_off((int)row, (int)j, TROWS);
-            tt += rs;
-            b += qs;
-            if (tt >= span) {
-              tt -= span;
-              ++b;
-            }
+            const int c = ptid + u * L_PROD_THREADS;
+            v[u] = (c < total) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          if (i > 0) mbar_wait(&sh->a_empty, (uint32_t)(i - 1) & 1u);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            if (ok[u]) {
-              const float h = tf32_hi(v[u]);
-              sts_f32(xh_a + off[u], h);
-              sts_f32(xl_a + off[u], v[u] - h);
+            const int c = ptid + u * L_PROD_THREADS;
+            if (c < TROWS * cpr) {               // rows beyond the input are stored as zeros
+              const uint32_t row = (uint32_t)c >> cshift;
+              const int c16 = c - (int)(row << cshift);
+              const uint32_t off = (uint32_t)((c16 >> 3) * XT_BYTES + row * 128 + (((c16 & 7) ^ (row & 7)) << 4));
+              const float4 h = make_float4(tf32_hi(v[u].x), tf32_hi(v[u].y), tf32_hi(v[u].z), tf32_hi(v[u].w));
+              sts_v4(xh_a + off, h);
+              sts_v4(xl_a + off, make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w));
             }
           }
-        }
-      }
-    }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sh->a_full);
-    // ---- code chunks: one thread streams the pre-built chunk images with TMA bulk copies, two chunks in flight ----
-    if (ptid == 0) {
-      const uint32_t ring_a = smem_u32(bring);
-      const uint32_t chunk_bytes = (uint32_t)b_stage;
-      const uint32_t crank = cluster_ctarank();
-      for (int c = 0; c < p.nchunks; ++c) {
-        const int s = c % BSTAGES;
-        mbar_wait(&sh->b_empty[s], ((uint32_t)(c / BSTAGES) & 1u) ^ 1u);
-        const uint32_t bar = smem_u32(&sh->b_full[s]);
-        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
-                     "r"(chunk_bytes)
-                     : "memory");
-        // this CTA fetches 1/CLUSTER of the chunk and multicasts it to every CTA of the cluster (same smem offset, each
-        // CTA's own b_full barrier at the same offset receives the complete_tx)
-        const uint32_t share = chunk_bytes / CLUSTER;
-        const uint32_t o0 = crank * share;
-        const char* src = reinterpret_cast<const char*>(p.img) + (size_t)c * chunk_bytes + o0;
-        const uint32_t dst = ring_a + (uint32_t)(s * b_stage) + o0;
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-            ::"r"(dst), "l"(src), "r"(share), "r"(bar), "h"((uint16_t)((1u << CLUSTER) - 1))
-            : "memory");
-      }
-    }
-  } else if (warp == L_MMA_WARP) {
-    // ================= MMA issuer: the whole converged warp runs the loop, the MMAs are guarded by elect_one() (bare
-    // UTCHMMA instead of an ELECT / BRA.U.ANY loop per MMA, see gemm_tc.cu::issue_mmas), the chunk ring (BSTAGES = TBUF = 2)
-    // is unrolled so that every descriptor is base + constant =================
-    {
-      static_assert(BSTAGES == 2 && TBUF == 2, "the issue loop is unrolled over a ring of two");
-      constexpr uint32_t idesc = make_idesc_tf32(CHUNK);
-      const bool elected = elect_one();
-      const uint64_t xh_d = make_desc_sw128(smem_u32(xa));
-      const uint64_t xl_d = xh_d + (uint64_t)(a_copy >> 4);
-      const uint64_t ring_d = make_desc_sw128(smem_u32(bring));
-      const uint64_t aug_a = make_desc_kmajor_plain(smem_u32(aaug));
-      const uint64_t aug_b0 = make_desc_kmajor_plain(smem_u32(bring) + (uint32_t)(2 * b_copy));
-      mbar_wait(&sh->a_full, 0);
-      uint32_t par = 0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < p.nchunks; c0 += 2) {
+        } else {
+          if (i > 0) mbar_wait(&sh->a_empty, (uint32_t)(i - 1) & 1u);
+          for (int e = ptid; e < (TROWS - rows) * D; e += L_PROD_THREADS) {   // zero tail rows
+            uint32_t r, j;
+            p.divD.divmod((uint32_t)e, r, j);
+            const uint32_t off = elem_off(rows + (int)r, (int)j, TROWS);
+            sts_f32(xh_a + off, 0.f);
+            sts_f32(xl_a + off, 0.f);
+          }
+          const int B = p.B, T = p.T;
+          const long long P = (long long)T * B;
+          const long long f0 = r0 * D;
+          const long long f1 = f0 + (long long)rows * D;
+          const long long d_first = f0 / P, d_last = (f1 - 1) / P;
+          for (long long d = d_first; d <= d_last; ++d) {
+            const long long base = d * P;
+            const int p0 = (int)((f0 > base ? f0 : base) - base);
+            const int p1 = (int)((f1 < base + P ? f1 : base + P) - base);
+            const int t0 = p0 / B, t1 = (p1 + B - 1) / B;
+            const int span = t1 - t0, count = span * B;
+            const int qs = L_PROD_THREADS / span, rs = L_PROD_THREADS - qs * span;
+            int b = ptid / span, tt = ptid - b * span;
+            const int foff = (int)(base - f0);
+            const float* zd = p.z + (size_t)d * T;
+            for (int e = ptid; e < count; e += L_PROD_THREADS * 8) {
+              float v[8];
+              uint32_t off[8];
+              bool ok[8];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (c0 + s < p.nchunks) {
-            mbar_wait(&sh->b_full[s], par);
-            mbar_wait(&sh->tmem_empty[s], par ^ 1u);
-            tc_fence_after();
-            const uint64_t bh_d = ring_d + (uint64_t)((s * b_stage) >> 4), bl_d = bh_d + (uint64_t)(b_copy >> 4);
-            const uint32_t dst = tmem_base + (uint32_t)(s * CHUNK);
+              for (int u = 0; u < 8; ++u) {
+                const int t = t0 + tt;
+                const int pp = t * B + b;
+                ok[u] = (e + u * L_PROD_THREADS < count) && pp >= p0 && pp < p1;
+                v[u] = ok[u] ? __ldg(zd + (size_t)b * D * T + t) : 0.f;
+                uint32_t row, j;
+                p.divD.divmod((uint32_t)(foff + pp), row, j);
+                off[u] = elem_off((int)row, (int)j, TROWS);
+                tt += rs;
+                b += qs;
+                if (tt >= span) {
+                  tt -= span;
+                  ++b;
+                }
+              }
 #pragma unroll
-            for (int kb = 0; kb < 2; ++kb) {
-              if (kb < nkb) {
-                const uint64_t ao = (uint64_t)((kb * XT_BYTES) >> 4), bo = (uint64_t)((kb * CHUNK * 128) >> 4);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                  if (elected) {
-                    umma_tf32(dst, xl_d + ao + adv, bh_d + bo + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
-                    umma_tf32(dst, xh_d + ao + adv, bl_d + bo + adv, idesc, 1u);
-                    umma_tf32(dst, xh_d + ao + adv, bh_d + bo + adv, idesc, 1u);
-                  }
+              for (int u = 0; u < 8; ++u) {
+                if (ok[u]) {
+                  const float h = tf32_hi(v[u]);
+                  sts_f32(xh_a + off[u], h);
+                  sts_f32(xl_a + off[u], v[u] - h);
                 }
               }
             }
-            if (elected) {
-              // the |e|^2 term: (1, 0, ...) x (g_hi, 0, ...) and (1, 0, ...) x (g_lo, 0, ...)
-              const uint64_t ab = aug_b0 + (uint64_t)((s * b_stage) >> 4);
-              umma_tf32(dst, aug_a, ab, idesc, 1u);
-              umma_tf32(dst, aug_a, ab + (uint64_t)((AUG_FLOATS * 4) >> 4), idesc, 1u);
-            }
-            if (elected) {
-              umma_commit_multicast(&sh->b_empty[s], (uint16_t)((1u << CLUSTER) - 1));   // stage consumed, tell every CTA
-              umma_commit(&sh->tmem_full[s]);
-            }
-            __syncwarp();
           }
         }
-        par ^= 1u;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->a_full);
+      }
+      if (i > 0) {
+        // ---- statistics of tile i - 1: global atomics, values re-read from the (L2-hot) rows ----
+        const int it = i - 1;
+        const long long r0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TROWS;
+        const long long left = p.N - r0;
+        const int rows = left < TROWS ? (int)left : TROWS;
+        mbar_wait(&sh->idx_ready[it & 1], (uint32_t)(it >> 1) & 1u);
+        int* si = sidx + (it & 1) * TROWS;
+        {
+          // near-ties the scan could not certify are settled HERE, by warps that would otherwise idle, so that neither the scan
+          // warps nor (through the accumulators) the MMAs ever wait for an exact re-score; warp w owns rows 16 w .. 16 w + 15.
+          // A whole-codebook re-score (mode 3, a handful per million rows, but ~300 us when one warp did it alone and every
+          // CTA's tile list is fixed) is shared by all eight warps, an eighth of the codes each.
+          const int pw = ptid >> 5;
+          const int R = pw * 16 + (lane & 15);
+          int bk = si[R];
+          const int aux = saux[(it & 1) * TROWS + R];
+          int* m3l = m3 + (it & 1) * (1 + M3_MAX);
+          const int n3 = m3l[0] < M3_MAX ? m3l[0] : M3_MAX;
+          for (int q3 = 0; q3 < n3; ++q3) {
+            const int R3 = m3l[1 + q3];
+            const RowX rx = settle_load_row(p, r0 + R3, lane);
+            const int per = (K + L_PROD_WARPS - 1) / L_PROD_WARPS;
+            const int k0 = pw * per, n = min(per, K - k0);
+            float bd;
+            int bkk;
+            settle_score(p, rx, 0, 0, 0, k0, n, lane, bd, bkk);
+            if (lane == 0) {
+              red[2 * pw] = bd;
+              red[2 * pw + 1] = __int_as_float(bkk);
+              if (pw == 0) atomicAdd(p.dbg + 2, 1.f);
+            }
+            named_bar_sync(2, L_PROD_THREADS);
+            if (pw == (R3 >> 4) && (lane & 15) == (R3 & 15)) {
+              float best = INFINITY;
+              int bb = 0x7fffffff;
+              for (int w = 0; w < L_PROD_WARPS; ++w) {
+                const float od = red[2 * w];
+                const int ok = __float_as_int(red[2 * w + 1]);
+                if (od < best || (od == best && ok < bb)) {
+                  best = od;
+                  bb = ok;
+                }
+              }
+              bk = bb < K ? bb : K - 1;
+            }
+            named_bar_sync(2, L_PROD_THREADS);
+          }
+          // two candidates (mode 1), one 64-code group (mode 2), and whole-codebook rows beyond the shared list: one warp each
+          unsigned mk = __ballot_sync(0xffffffffu, lane < 16 && (aux >> 16) != 0 && ((aux >> 16) != 3 || (aux & 0xffff) >= n3));
+          while (mk) {
+            const int rr = __ffs(mk) - 1;
+            mk &= mk - 1;
+            const int ka = __shfl_sync(0xffffffffu, bk, rr), ax = __shfl_sync(0xffffffffu, aux, rr);
+            const int mode = ax >> 16;
+            if (lane == 0) atomicAdd(p.dbg + mode - 1, 1.f);
+            const RowX rx = settle_load_row(p, r0 + pw * 16 + rr, lane);
+            const int k0 = mode == 3 ? 0 : (ka >> 6) << 6;
+            const int n = mode == 1 ? 2 : (mode == 3 ? K : min(64, K - k0));
+            float bd;
+            int bkk;
+            settle_score(p, rx, mode == 1, ka, ax & 0xffff, k0, n, lane, bd, bkk);
+            if (lane == rr) bk = bkk < K ? bkk : K - 1;
+          }
+          if (lane < 16) {
+            si[R] = bk;
+            if (R < rows) p.idx[r0 + R] = (int64_t)bk;
+          }
+          named_bar_sync(2, L_PROD_THREADS);      // every row's final index is in si[], every warp has read the list
+          if (ptid == 0) m3l[0] = 0;              // the list is free again (next used at the end of tile it + 2)
+        }
+        if (p.layout == VQS_LAYOUT_FLAT_ND) {
+          const float* src = p.z + r0 * D;
+          for (int e = ptid; e < rows * D; e += L_PROD_THREADS) {
+            uint32_t R, j;
+            p.divD.divmod((uint32_t)e, R, j);
+            atomicAdd(p.stats + K + (size_t)si[R] * D + j, __ldg(src + e));
+          }
+        } else {
+          for (int e = ptid; e < rows * D; e += L_PROD_THREADS) {
+            uint32_t R, j;
+            p.divD.divmod((uint32_t)e, R, j);
+            atomicAdd(p.stats + K + (size_t)si[R] * D + j, z_elem(p, r0 + R, (int)j));
+          }
+        }
+        for (int R = ptid; R < rows; R += L_PROD_THREADS) atomicAdd(p.stats + si[R], 1.f);
+      }
+    }
+  } else if (warp == L_LOAD_WARP) {
+    // ================= chunk streamer: one thread, one TMA bulk copy per chunk image, across tile boundaries =================
+    if (lane == 0) {
+      const uint32_t ring_a = smem_u32(bring);
+      const uint32_t chunk_bytes = (uint32_t)b_stage;
+      const int total = ntl * p.nchunks;
+      int c = 0;
+      for (int g = 0; g < total; ++g) {
+        const int s = g & (BBARS - 1);
+        mbar_wait(&sh->b_empty[s], (((uint32_t)g >> BBARS_LOG2) & 1u) ^ 1u);
+        const uint32_t bar = smem_u32(&sh->b_full[s]);
+        if (L_DBG(32)) {
+          mbar_arrive(&sh->b_full[s]);
+        } else {
+          asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
+                       "r"(chunk_bytes)
+                       : "memory");
+          const char* src = reinterpret_cast<const char*>(p.img) + (size_t)c * chunk_bytes;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           ring_a + (uint32_t)((s & (BSTAGES - 1)) * b_stage)),
+                       "l"(src), "r"(chunk_bytes), "r"(bar)
+                       : "memory");
+        }
+        if (++c == p.nchunks) c = 0;
+      }
+    }
+    __syncwarp();
+  } else if (warp == L_MMA_WARP) {
+    // ================= MMA issuer: the whole converged warp runs the loop, the MMAs are guarded by elect_one() (bare
+    // UTCHMMA instead of an ELECT / BRA.U.ANY loop per MMA, see gemm_tc.cu::issue_mmas) =================
+    constexpr uint32_t idesc = make_idesc_tf32(CHUNK);
+    const bool elected = elect_one();
+    const uint64_t xh_d = make_desc_sw128(smem_u32(xa));
+    const uint64_t xl_d = xh_d + (uint64_t)(a_copy >> 4);
+    const uint64_t ring_d = make_desc_sw128(smem_u32(bring));
+    const uint64_t aug_a = make_desc_kmajor_plain(smem_u32(aaug));
+    const uint64_t aug_b0 = make_desc_kmajor_plain(smem_u32(bring) + (uint32_t)(2 * b_copy));
+    uint32_t g = 0;
+#pragma unroll 1
+    for (int i = 0; i < ntl; ++i) {
+      mbar_wait(&sh->a_full, (uint32_t)i & 1u);
+#pragma unroll 1
+      for (int c = 0; c < p.nchunks; ++c, ++g) {
+        const uint32_t sb = g & (uint32_t)(BBARS - 1), par = (g >> BBARS_LOG2) & 1u, s = sb & (uint32_t)(BSTAGES - 1);
+        const uint32_t ta = g & (uint32_t)(TBUF - 1), tpar = (g >> TBUF_LOG2) & 1u;
+        mbar_wait(&sh->b_full[sb], par);
+        mbar_wait(&sh->tmem_empty[ta], tpar ^ 1u);
+        tc_fence_after();
+        const uint64_t bh_d = ring_d + (uint64_t)((s * (uint32_t)b_stage) >> 4), bl_d = bh_d + (uint64_t)(b_copy >> 4);
+        const uint32_t dst = tmem_base + ta * CHUNK;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          if (kb < nkb) {
+            const uint64_t ao = (uint64_t)((kb * XT_BYTES) >> 4), bo = (uint64_t)((kb * CHUNK * 128) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);
+              if (elected && !L_DBG(16)) {
+                umma_tf32(dst, xl_d + ao + adv, bh_d + bo + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+                umma_tf32(dst, xh_d + ao + adv, bl_d + bo + adv, idesc, 1u);
+                umma_tf32(dst, xh_d + ao + adv, bh_d + bo + adv, idesc, 1u);
+              }
+            }
+          }
+        }
+        if (elected && !L_DBG(16)) {
+          // the |e|^2 term: (1, 0, ...) x (g_hi, 0, ...) and (1, 0, ...) x (g_lo, 0, ...)
+          const uint64_t ab = aug_b0 + (uint64_t)((s * (uint32_t)b_stage) >> 4);
+          umma_tf32(dst, aug_a, ab, idesc, 1u);
+          umma_tf32(dst, aug_a, ab + (uint64_t)((AUG_FLOATS * 4) >> 4), idesc, 1u);
+        }
+        if (elected) {
+          umma_commit(&sh->b_empty[sb]);
+          umma_commit(&sh->tmem_full[ta]);
+          if (c == p.nchunks - 1) umma_commit(&sh->a_empty);   // the row tile may be replaced
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
   } else {
-    // ================= scan warps: running top-3 per row over the chunks =================
+    // ================= scan warps: running top-3 per row over the chunks of a tile =================
     const int q = warp & 3, half = warp >> 2;
     const int r = q * 32 + lane;
-    Top3 top;
-    top.b = top.s = top.t = -INFINITY;     // the three largest accumulator words v = x.e - (1 - EPS) |e|^2 / 2
-    top.kb = top.ks = 0;
-    for (int c = 0; c < p.nchunks; ++c) {
-      const int a = c % TBUF;
-      mbar_wait(&sh->tmem_full[a], (uint32_t)(c / TBUF) & 1u);
-      tc_fence_after();
-      // this warp's share of the chunk: lane quarter q, columns [half * CHUNK/2, (half + 1) * CHUNK/2)
-      float v[CHUNK / 2];
-#pragma unroll
-      for (int h2 = 0; h2 < CHUNK / 64; ++h2) {
-        float t[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * CHUNK + half * (CHUNK / 2) + h2 * 32), t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[h2 * 32 + j] = t[j];
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->tmem_empty[a]);      // scores are in registers: the accumulator is free again
-      const int kbase = c * CHUNK + half * (CHUNK / 2);
-#pragma unroll
-      for (int j = 0; j < CHUNK / 2; ++j) top3_push_max(top, v[j], kbase + j);
-    }
-    // back to lower-bound scores (smaller = better): s = (1 - EPS) |e|^2 - 2 x.e = -2 v
-    top.b *= -2.f;
-    top.s *= -2.f;
-    top.t *= -2.f;
-    // ---- merge the two column halves (ties need no care here: equal scores are re-checked exactly) ----
-    if (half == 1) {
-      float* m = mrg + r * 6;
-      m[0] = top.b; m[1] = top.s; m[2] = top.t;
-      m[3] = __int_as_float(top.kb); m[4] = __int_as_float(top.ks);
-    }
-    named_bar_sync(1, L_SCAN_WARPS * 32);
-    if (half == 0) {
-      const float* m = mrg + r * 6;
-      top3_push(top, m[0], __float_as_int(m[3]));
-      top3_push(top, m[1], __float_as_int(m[4]));
-      top3_push(top, m[2], 0);   // only its value matters (third place)
-      // ---- |x|^2 for the bound (hi copy, rotated conflict-free read) ----
+    const int colmask = ~63 | (K >> 30);   // = ~63 (K <= 8192), opaque to the compiler so that it stays in a register
+    uint32_t g = 0;
+    for (int i = 0; i < ntl; ++i) {
+      const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * TROWS;
+      const long long left = p.N - r0;
+      const int rows = left < TROWS ? (int)left : TROWS;
+      // ---- |x|^2 for the bound, from the tile's hi copy (rotated conflict-free read) while it is certainly there ----
       float sx = 0.f;
-      for (int kb = 0; kb < nkb; ++kb) {
+      if (half == 0) {
+        mbar_wait(&sh->a_full, (uint32_t)i & 1u);
+        for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int pc = (r + i) & 7;
-          const float4 h = *reinterpret_cast<const float4*>(xh + kb * XT_BYTES + r * 128 + (pc << 4));
-          sx = fmaf(h.x, h.x, sx);
-          sx = fmaf(h.y, h.y, sx);
-          sx = fmaf(h.z, h.z, sx);
-          sx = fmaf(h.w, h.w, sx);
-        }
-      }
-      sx *= 1.01f;
-      const float tol2 = 2.f * EPS_SCORE * (sx + se_s[top.kb]);
-      int bk = top.kb;
-      const bool close2 = !((top.s - top.b) > tol2);
-      const bool close3 = !((top.t - top.b) > tol2);
-      if (close2 && !close3) {        // exactly two candidates: settle them in fp32 (lowest index on a tie)
-        atomicAdd(p.dbg, 1.f);
-        const float sxr = row_sumsq(xh, xl, r, D);
-        const float d1 = exact_dist(xh, xl, r, p.cb + (size_t)top.kb * D, sxr, se_s[top.kb], D);
-        const float d2 = exact_dist(xh, xl, r, p.cb + (size_t)top.ks * D, sxr, se_s[top.ks], D);
-        if (d2 < d1 || (d2 == d1 && top.ks < top.kb)) bk = top.ks;
-      }
-      // three or more candidates: exact scan over the whole codebook by the warp
-      unsigned mk = __ballot_sync(0xffffffffu, close2 && close3);
-      while (mk) {
-        const int rr = __ffs(mk) - 1;
-        mk &= mk - 1;
-        const int R = q * 32 + rr;
-        if (lane == 0) atomicAdd(p.dbg + 1, 1.f);
-        const float sxr = row_sumsq(xh, xl, R, D);
-        float bd = INFINITY;
-        int bkk = 0x7fffffff;
-        for (int k = lane; k < K; k += 32) {
-          const float dd = exact_dist(xh, xl, R, p.cb + (size_t)k * D, sxr, se_s[k], D);
-          if (dd < bd) {
-            bd = dd;
-            bkk = k;
+          for (int u = 0; u < 8; ++u) {
+            const int pc = (r + u) & 7;
+            const float4 h = *reinterpret_cast<const float4*>(xh + kb * XT_BYTES + r * 128 + (pc << 4));
+            sx = fmaf(h.x, h.x, sx);
+            sx = fmaf(h.y, h.y, sx);
+            sx = fmaf(h.z, h.z, sx);
+            sx = fmaf(h.w, h.w, sx);
           }
         }
+        sx *= 1.01f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->a_empty);
+      }
+      Top3 top;
+      top.b = top.s = top.t = -INFINITY;     // the three largest accumulator words v = x.e - (1 - EPS) |e|^2 / 2
+      top.kb = top.ks = 0;
+      for (int c = 0; c < p.nchunks; ++c, ++g) {
+        const uint32_t a = g & (uint32_t)(TBUF - 1);
+        mbar_wait(&sh->tmem_full[a], (g >> TBUF_LOG2) & 1u);
+        tc_fence_after();
+        // this warp's share of the chunk: lane quarter q, columns [half * CHUNK/2, (half + 1) * CHUNK/2)
+        float v[CHUNK / 2];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-          const int ok = __shfl_xor_sync(0xffffffffu, bkk, o);
-          if (od < bd || (od == bd && ok < bkk)) {
-            bd = od;
-            bkk = ok;
+        for (int h2 = 0; h2 < CHUNK / 64; ++h2) {
+          float t[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (a * CHUNK + (uint32_t)(half * (CHUNK / 2) + h2 * 32)), t);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[h2 * 32 + j] = t[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->tmem_empty[a]);      // scores are in registers: the accumulator is free again
+        const int kbase = c * CHUNK + half * (CHUNK / 2);
+        if (L_DBG(8)) {
+          if (v[0] == 12345.f) top.b = 1.f;
+          continue;
+        }
+        // Branch-free top-2 of this warp's 64 columns: the column number rides in the low 6 mantissa bits of every value
+        // (error <= 2^-17 |v|, part of EPS_LARGE), so a maximum carries its index and one element costs LOP3 + 3 FMNMX in
+        // four independent chains -- a compare-and-branch per element (BSSY / FSETP / BRA / BSYNC, ~20 cycles of control
+        // latency with two warps per scheduler) made the scan, not the tensor pipe, the limiter: 3450 of 3960 cycles per
+        // chunk (profiles/r04b_k4096_phases.txt).
+        float m1[4], m2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) m1[u] = m2[u] = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < CHUNK / 2; ++j) {
+          float pv;   // (v & ~63) | j as ONE LOP3 (mask in a register the compiler cannot fold, column as the immediate)
+          asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=f"(pv) : "f"(v[j]), "r"(colmask), "r"(j));
+          const float lo = fminf(m1[j & 3], pv);
+          m1[j & 3] = fmaxf(m1[j & 3], pv);
+          m2[j & 3] = fmaxf(m2[j & 3], lo);
+        }
+#pragma unroll
+        for (int w = 2; w > 0; w >>= 1) {
+#pragma unroll
+          for (int u = 0; u < w; ++u) {
+            const float lo = fminf(m1[u], m1[u + w]);
+            m1[u] = fmaxf(m1[u], m1[u + w]);
+            m2[u] = fmaxf(lo, fmaxf(m2[u], m2[u + w]));
           }
         }
-        if (lane == rr) bk = bkk < K ? bkk : K - 1;
+        // the chunk's two best enter the running top-3 (rarely, after the first chunks: the whole warp skips the updates)
+        top3_push_max(top, m1[0], kbase + (__float_as_int(m1[0]) & 63));
+        top3_push_max(top, m2[0], kbase + (__float_as_int(m2[0]) & 63));
       }
-      sidx[r] = bk;
-      if (r < rows) p.idx[r0 + r] = (int64_t)bk;
+      // back to lower-bound scores (smaller = better): s = (1 - EPS) |e|^2 - 2 x.e = -2 v
+      top.b *= -2.f;
+      top.s *= -2.f;
+      top.t *= -2.f;
+      // ---- merge the two column halves (ties need no care here: equal scores are re-checked exactly) ----
+      float* m = mrg + ((i & 1) * TROWS + r) * 6;
+      if (half == 1) {
+        m[0] = top.b; m[1] = top.s; m[2] = top.t;
+        m[3] = __int_as_float(top.kb); m[4] = __int_as_float(top.ks);
+      }
+      named_bar_sync(1, L_SCAN_WARPS * 32);
+      if (half == 0) {
+        top3_push(top, m[0], __float_as_int(m[3]));
+        top3_push(top, m[1], __float_as_int(m[4]));
+        top3_push(top, m[2], 0);   // only its value matters (third place)
+        const float tol2 = 2.f * EPS_LARGE * (sx + __ldg(p.se + top.kb));
+        // The scan keeps the two best of every 64-column group, so a value it dropped lies below two kept values of its own
+        // group: with the best and the second in DIFFERENT groups and the third kept value far, nothing else is near (mode 1:
+        // two candidates); with both in the same group and the third kept value far every candidate lies in that group
+        // (mode 2); otherwise the whole codebook is re-scored (mode 3).  Rows beyond the input are zeros: never settled.
+        const bool live = r < rows && !L_DBG(8 | 16 | 32 | 64);   // (bit 6: settlement off)
+        const bool close2 = live && !((top.s - top.b) > tol2);
+        const bool close3 = live && !((top.t - top.b) > tol2);
+        const bool same_group = (top.kb >> 6) == (top.ks >> 6);
+        int mode = !close2 ? 0 : (close3 ? 3 : (same_group ? 2 : 1));
+        if ((L_DBG(128) && mode == 3) || (L_DBG(256) && mode == 1) || (L_DBG(512) && mode == 2)) mode = 0;   // probes
+        int second = top.ks;
+        if (mode == 3) {                        // position in the tile's whole-codebook list (the second-best code is not needed)
+          second = atomicAdd(m3 + (i & 1) * (1 + M3_MAX), 1);
+          if (second < M3_MAX) m3[(i & 1) * (1 + M3_MAX) + 1 + second] = r;
+        }
+        sidx[(i & 1) * TROWS + r] = L_DBG(8 | 16 | 32) ? (r & 63) : top.kb;
+        saux[(i & 1) * TROWS + r] = (second & 0xffff) | (mode << 16);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->idx_ready[i & 1]);   // the producers take the statistics from here
+      }
     }
-    named_bar_sync(1, L_SCAN_WARPS * 32);
-    // ---- statistics: global atomics (low contention at large K) ----
-    const int st = tid;   // 256 scan threads
-    for (int e = st; e < rows * D; e += L_SCAN_WARPS * 32) {
-      uint32_t R, j;
-      p.divD.divmod((uint32_t)e, R, j);
-      atomicAdd(p.stats + K + (size_t)sidx[R] * D + j, ld_exact(xh, xl, elem_off((int)R, (int)j, TROWS)));
-    }
-    for (int R = st; R < rows; R += L_SCAN_WARPS * 32) atomicAdd(p.stats + sidx[R], 1.f);
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();   // no CTA may exit while a sibling can still multicast into it or arrive on its barriers
   if (warp == L_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TBUF * CHUNK);
@@ -1056,11 +1257,12 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
   }
   VQS_CUDA(cudaMemsetAsync(se + (size_t)nchunks * CHUNK, 0, 8 * sizeof(float), st));
   VQS_CUDA(cudaMemsetAsync(stats, 0, (size_t)K * (D + 1) * sizeof(float), st));
+  if (p.ntiles == 0) return 0;
   cb_prep_kernel<<<(nchunks * CHUNK + 127) / 128, 128, 0, st>>>(cb, K, D, nchunks * CHUNK, img, se);
   VQS_LAUNCH_CHECK();
   const int a_copy = p.nkb * XT_BYTES;
   const size_t smem = (size_t)2 * a_copy + AUG_FLOATS * 4 + (size_t)BSTAGES * (2 * p.nkb * CHUNK * 128 + 2 * AUG_FLOATS * 4) +
-                      ((size_t)TROWS * 6 + TROWS) * 4 + sizeof(LShared) + 1024 + 64;
+                      ((size_t)2 * TROWS * 6 + 4 * TROWS + 2 * (1 + M3_MAX) + 2 * L_PROD_WARPS) * 4 + sizeof(LShared) + 1024 + 64;
   if (smem > 226 * 1024) {
     set_error("vq_search_large: codebook of %d codes needs %zu bytes of shared memory", K, smem);
     return VQS_ERR_ARG;
@@ -1068,30 +1270,18 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
   static DevCache configured;
   if (dev_needs(configured, smem))
     VQS_CUDA(cudaFuncSetAttribute(vq_search_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((p.ntiles + CLUSTER - 1) / CLUSTER * CLUSTER));
-    cfg.blockDim = dim3(L_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CLUSTER;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VQS_CUDA(cudaLaunchKernelEx(&cfg, vq_search_large_kernel, p));
-  }
+  const int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
+  vq_search_large_kernel<<<grid, L_THREADS, smem, st>>>(p);
   VQS_LAUNCH_CHECK();
 #ifdef VQS_DEBUG
   {
     const char* dbg = getenv("VQS_TC_DEBUG");
     if (dbg && (atoi(dbg) & 4)) {   // profiling aid: how many rows needed the exact paths (synchronises!)
-      float h[2] = {0.f, 0.f};
+      float h[3] = {0.f, 0.f, 0.f};
       cudaStreamSynchronize(st);
       cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[vq_search_large] N=%lld K=%d: top-2 settlements %.0f, full exact scans %.0f\n", p.N, K, h[0], h[1]);
+      fprintf(stderr, "[vq_search_large] N=%lld K=%d: top-2 settlements %.0f, 64-code group scans %.0f, full exact scans %.0f\n",
+              p.N, K, h[0], h[1], h[2]);
     }
   }
 #endif
