@@ -556,7 +556,7 @@ int launch_assign_tc(const float* z, int layout, int B, int D, int T, const floa
 // Large codebooks (K > what fits shared memory, e.g. the 512 / 4096-code sweep): the distance search is a real GEMM
 // N x 64 . 64 x K.  PERSISTENT kernel, one CTA per SM walking over 128-row tiles: a tile stays in shared memory (hi/lo split)
 // while the codebook is streamed past it in 128-code chunks (pre-built shared-memory images in global memory, one
-// cp.async.bulk per chunk into a 2-stage ring), 24 + 2 tf32 MMAs per chunk into one of two TMEM accumulators; 8 scan warps keep
+// cp.async.bulk per chunk into a 2-stage ring), 24 + 1 tf32 MMAs per chunk into one of four TMEM accumulators; 8 scan warps keep
 // a running top-3 of the scores per row.  Rows whose best and second-best scores are closer than 2*tol are settled exactly
 // in fp32, so indices equal the fp32 search.
 //
@@ -567,8 +567,8 @@ int launch_assign_tc(const float* z, int layout, int B, int D, int T, const floa
 // the tile (a_empty: tcgen05.commit), the chunk ring and the two accumulators run on across tile boundaries, and the
 // statistics of tile i (global atomics, low contention at large K) are issued by the otherwise idle producer warps from
 // the L2-hot rows while the scan warps are already on tile i + 1.
-// Warp roles (576 threads): 0-7 scan (TMEM lane quarter = warp & 3, column half = warp >> 2), 8-15 row-tile producers +
-// statistics, 16 MMA issuer + TMEM owner, 17 chunk streamer (one lane).
+// Warp roles (608 threads): 0-7 scan (TMEM lane quarter = warp & 3, column half = warp >> 2), 8-15 row-tile producers +
+// settlement + statistics, 16-17 MMA issuers (16 owns the TMEM allocation), 18 chunk streamer (one lane).
 // =====================================================================================================================
 namespace vqs {
 
@@ -597,16 +597,16 @@ namespace {
 constexpr int L_SCAN_WARPS = 8, L_PROD_WARPS = 8;
 constexpr int L_PROD_THREADS = L_PROD_WARPS * 32;
 constexpr int L_MMA_WARP = L_SCAN_WARPS + L_PROD_WARPS;
-constexpr int L_LOAD_WARP = L_MMA_WARP + 1;
-constexpr int L_THREADS = (L_LOAD_WARP + 1) * 32;
 constexpr int CHUNK = 128;    // codes per streamed chunk (UMMA N)
-constexpr int BSTAGES = 2;    // chunk ring depth (shared memory)
-#ifndef VQS_LARGE_BBARS
-#define VQS_LARGE_BBARS BSTAGES
+constexpr int BSTAGES = 2;    // chunk ring depth (a probe build with FOUR barrier stages aliasing two buffers, chunk loads off, ran
+                              // no faster: ring depth is not what holds the MMAs back, profiles/r04g_k4096_bbars4.txt)
+#ifndef VQS_LARGE_ISSUERS
+#define VQS_LARGE_ISSUERS 2
 #endif
-// ring depth of the BARRIERS: > BSTAGES only in a probe build run with the chunk loads off (VQS_TC_DEBUG bit 5), where the stages
-// may alias -- "what would a deeper ring buy" without having the shared memory for it
-constexpr int BBARS = VQS_LARGE_BBARS, BBARS_LOG2 = BBARS == 4 ? 2 : 1;
+constexpr int ISSUERS = VQS_LARGE_ISSUERS;   // MMA issuer warps; two take alternate chunks (see the issuer loop)
+static_assert(ISSUERS == 1 || ISSUERS == 2, "one or two issuer warps");
+constexpr int L_LOAD_WARP = L_MMA_WARP + ISSUERS;
+constexpr int L_THREADS = (L_LOAD_WARP + 1) * 32;
 #ifndef VQS_LARGE_TBUF
 #define VQS_LARGE_TBUF 4
 #endif
@@ -618,7 +618,7 @@ static_assert(TBUF == 2 || TBUF == 4, "accumulator ring of 2 or 4");
 
 constexpr int M3_MAX = 7;     // whole-codebook re-scores per tile done by all producer warps together (more: one warp each)
 struct LShared {
-  uint64_t a_full, a_empty, b_full[BBARS], b_empty[BBARS], tmem_full[TBUF], tmem_empty[TBUF], idx_ready[2];
+  uint64_t a_full, a_empty, b_full[BSTAGES], b_empty[BSTAGES], tmem_full[TBUF], tmem_empty[TBUF], idx_ready[2];
   uint32_t tmem_base;
 };
 
@@ -626,15 +626,15 @@ struct LShared {
 // ([hi | lo] x [k-block] x [128 rows x 128 B, SWIZZLE_128B]), so that a chunk is ONE contiguous block in global memory
 // and a single thread can stream it with cp.async.bulk (TMA bulk copy, completion on an mbarrier) -- 4096 16-byte
 // cp.async per chunk gave 10 B/clk/SM.  Also |e_k|^2 (fp32, sequential order = the exact path's) and +inf padding.
-// The |e_k|^2 term of the score rides in the GEMM as ONE EXTRA k-step (round 2): the row tile gets a constant column 1, the chunk a
-// column g_k = -(1 - EPS_LARGE) |e_k|^2 / 2 (split hi + lo like every operand), so the accumulator holds
+// The |e_k|^2 term of the score rides in the GEMM as ONE EXTRA k-step (round 2): the row tile gets two constant columns 1, the chunk
+// the columns hi and lo of g_k = -(1 - EPS_LARGE) |e_k|^2 / 2 (one MMA: 25 per chunk), so the accumulator holds
 // v = x.e_k + g_k and the lower-bound score is just -2 v: the scan warps work on raw accumulator words.  The extra operands are
 // [128 rows x 8 floats] tiles in the un-swizzled K-major canonical layout (8-row x 16-byte core matrices: LBO = 128 B between
 // the two k-halves, SBO = 256 B between row groups).
 // Score tolerance of this kernel: EPS_SCORE plus the 6 mantissa bits the scan overwrites with the column number
 // (|pv - v| < 64 ulp <= 2^-17 |v|, |v| <= |x||e| + |e|^2 / 2 <= |x|^2 + |e|^2, score = -2 v: 2^-16 (|x|^2 + |e|^2)).
 constexpr float EPS_LARGE = EPS_SCORE + 1.53e-5f;
-constexpr int AUG_FLOATS = CHUNK * 8;                 // one copy (hi or lo) of the extra k-step of a chunk
+constexpr int AUG_FLOATS = CHUNK * 8;                 // the extra k-step of a chunk / of the row tile
 __host__ __device__ __forceinline__ int aug_off(int row, int k) {   // float index inside such a tile
   return (row >> 3) * 64 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
 }
@@ -653,7 +653,7 @@ __global__ void cb_prep_kernel(const float* __restrict__ cb, int K, int D, int K
   if (k >= Kpad) return;
   const int nkb = D / 32;
   const int copy_floats = nkb * CHUNK * 32;            // floats per copy of one chunk
-  float* chunk = img + (size_t)(k / CHUNK) * (2 * copy_floats + 2 * AUG_FLOATS);
+  float* chunk = img + (size_t)(k / CHUNK) * (2 * copy_floats + AUG_FLOATS);
   const int row = k % CHUNK;
   float s = 0.f;
   for (int j = 0; j < D; ++j) {
@@ -665,14 +665,11 @@ __global__ void cb_prep_kernel(const float* __restrict__ cb, int K, int D, int K
     s = fmaf(v, v, s);
   }
   se[k] = (k < K) ? s : INFINITY;
-  // extra k-step: column 0 = g_k (padding codes: a huge negative value, never among the best), columns 1..7 = 0
+  // extra k-step: columns 0 / 1 = hi / lo part of g_k (padding codes: a huge negative value, never among the best), 2..7 = 0
   const float g = (k < K) ? -0.5f * (s * (1.f - EPS_LARGE)) : -1e30f;
   const float gh = tf32_hi(g);
   float* aug = chunk + 2 * copy_floats;
-  for (int j = 0; j < 8; ++j) {
-    aug[aug_off(row, j)] = j == 0 ? gh : 0.f;
-    aug[AUG_FLOATS + aug_off(row, j)] = j == 0 ? g - gh : 0.f;
-  }
+  for (int j = 0; j < 8; ++j) aug[aug_off(row, j)] = j == 0 ? gh : (j == 1 ? g - gh : 0.f);
 }
 
 struct Top3 {
@@ -703,6 +700,11 @@ __device__ __forceinline__ void top3_push_max(Top3& a, float v, int k) {
   }
 }
 
+// fire-and-forget fp32 add to GLOBAL memory (atomicAdd on a pointer the compiler cannot prove global also emits the shared-memory
+// CAS loop: 64 unrolled ATOMS.CAST.SPIN blocks in the statistics loop)
+__device__ __forceinline__ void red_add_global(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
 // Element (row, column j) of the row space, from global memory (the settlement paths and the statistics run after the
 // tile's shared-memory copy may already hold the next tile; the rows are L2-hot).  (B, D, T) input is the reference's
 // (D, T, B) row space cut into rows of D (vector_quantizer_ema.py:104-107).
@@ -796,10 +798,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
   const int D = p.D, K = p.K, nkb = p.nkb;
   const int a_copy = nkb * XT_BYTES;                 // one copy (hi or lo) of the row tile / of a code chunk
   uint8_t* xa = smem;                                 // [hi | lo]
-  uint8_t* aaug = smem + 2 * a_copy;                  // the row tile's extra k-step: column 0 = 1 (4 KB, un-swizzled)
-  uint8_t* bring = aaug + AUG_FLOATS * 4;             // BSTAGES x [hi | lo | extra k-step hi | lo] chunk images
+  uint8_t* aaug = smem + 2 * a_copy;                  // the row tile's extra k-step: columns 0, 1 = 1 (4 KB, un-swizzled)
+  uint8_t* bring = aaug + AUG_FLOATS * 4;             // BSTAGES x [hi | lo | extra k-step] chunk images
   const int b_copy = nkb * CHUNK * 128;
-  const int b_stage = 2 * b_copy + 2 * AUG_FLOATS * 4;
+  const int b_stage = 2 * b_copy + AUG_FLOATS * 4;
   float* mrg = reinterpret_cast<float*>(bring + BSTAGES * b_stage);   // [2][128][6] merge buffers of the upper column half
   int* sidx = reinterpret_cast<int*>(mrg + 2 * TROWS * 6);            // [2][128] indices of a tile (scan -> producers)
   int* saux = sidx + 2 * TROWS;                                       // [2][128] second-best code | settlement mode << 16
@@ -810,8 +812,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
   if (tid == 0) {
     m3[0] = m3[1 + M3_MAX] = 0;
     mbar_init(&sh->a_full, L_PROD_WARPS);
-    mbar_init(&sh->a_empty, 1 + L_SCAN_WARPS / 2);   // the last MMA of the tile has read it and the |x|^2 readers are done
-    for (int s = 0; s < BBARS; ++s) {
+    mbar_init(&sh->a_empty, ISSUERS + L_SCAN_WARPS / 2);   // every issuer's last MMA of the tile has read it, the |x|^2 readers are done
+    for (int s = 0; s < BSTAGES; ++s) {
       mbar_init(&sh->b_full[s], 1);
       mbar_init(&sh->b_empty[s], 1);
     }
@@ -835,9 +837,9 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
     // ================= producers: row tiles in, statistics out =================
     const int ptid = tid - L_SCAN_WARPS * 32;
     const uint32_t xh_a = smem_u32(xa), xl_a = xh_a + (uint32_t)a_copy;
-    if (ptid < TROWS) {                                                  // extra k-step: (1, 0, ..., 0) per row, once
+    if (ptid < TROWS) {                                                  // extra k-step: (1, 1, 0, ..., 0) per row, once
       const uint32_t o = smem_u32(aaug) + (uint32_t)((ptid >> 3) * 256 + (ptid & 7) * 16);
-      sts_v4(o, make_float4(1.f, 0.f, 0.f, 0.f));
+      sts_v4(o, make_float4(1.f, 1.f, 0.f, 0.f));
       sts_v4(o + 128, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     const int cpr = D >> 2;                      // 16-byte pieces per row
@@ -959,7 +961,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
             if (lane == 0) {
               red[2 * pw] = bd;
               red[2 * pw + 1] = __int_as_float(bkk);
-              if (pw == 0) atomicAdd(p.dbg + 2, 1.f);
+              if (pw == 0) red_add_global(p.dbg + 2, 1.f);
             }
             named_bar_sync(2, L_PROD_THREADS);
             if (pw == (R3 >> 4) && (lane & 15) == (R3 & 15)) {
@@ -984,7 +986,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
             mk &= mk - 1;
             const int ka = __shfl_sync(0xffffffffu, bk, rr), ax = __shfl_sync(0xffffffffu, aux, rr);
             const int mode = ax >> 16;
-            if (lane == 0) atomicAdd(p.dbg + mode - 1, 1.f);
+            if (lane == 0) red_add_global(p.dbg + mode - 1, 1.f);
             const RowX rx = settle_load_row(p, r0 + pw * 16 + rr, lane);
             const int k0 = mode == 3 ? 0 : (ka >> 6) << 6;
             const int n = mode == 1 ? 2 : (mode == 3 ? K : min(64, K - k0));
@@ -1002,19 +1004,21 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
         }
         if (p.layout == VQS_LAYOUT_FLAT_ND) {
           const float* src = p.z + r0 * D;
+#pragma unroll 4
           for (int e = ptid; e < rows * D; e += L_PROD_THREADS) {
             uint32_t R, j;
             p.divD.divmod((uint32_t)e, R, j);
-            atomicAdd(p.stats + K + (size_t)si[R] * D + j, __ldg(src + e));
+            red_add_global(p.stats + K + (size_t)si[R] * D + j, __ldg(src + e));
           }
         } else {
+#pragma unroll 1
           for (int e = ptid; e < rows * D; e += L_PROD_THREADS) {
             uint32_t R, j;
             p.divD.divmod((uint32_t)e, R, j);
-            atomicAdd(p.stats + K + (size_t)si[R] * D + j, z_elem(p, r0 + R, (int)j));
+            red_add_global(p.stats + K + (size_t)si[R] * D + j, z_elem(p, r0 + R, (int)j));
           }
         }
-        for (int R = ptid; R < rows; R += L_PROD_THREADS) atomicAdd(p.stats + si[R], 1.f);
+        for (int R = ptid; R < rows; R += L_PROD_THREADS) red_add_global(p.stats + si[R], 1.f);
       }
     }
   } else if (warp == L_LOAD_WARP) {
@@ -1025,8 +1029,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
       const int total = ntl * p.nchunks;
       int c = 0;
       for (int g = 0; g < total; ++g) {
-        const int s = g & (BBARS - 1);
-        mbar_wait(&sh->b_empty[s], (((uint32_t)g >> BBARS_LOG2) & 1u) ^ 1u);
+        const int s = g & 1;
+        mbar_wait(&sh->b_empty[s], (((uint32_t)g >> 1) & 1u) ^ 1u);
         const uint32_t bar = smem_u32(&sh->b_full[s]);
         if (L_DBG(32)) {
           mbar_arrive(&sh->b_full[s]);
@@ -1036,7 +1040,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
                        : "memory");
           const char* src = reinterpret_cast<const char*>(p.img) + (size_t)c * chunk_bytes;
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           ring_a + (uint32_t)((s & (BSTAGES - 1)) * b_stage)),
+                           ring_a + (uint32_t)(s * b_stage)),
                        "l"(src), "r"(chunk_bytes), "r"(bar)
                        : "memory");
         }
@@ -1044,9 +1048,14 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
       }
     }
     __syncwarp();
-  } else if (warp == L_MMA_WARP) {
-    // ================= MMA issuer: the whole converged warp runs the loop, the MMAs are guarded by elect_one() (bare
-    // UTCHMMA instead of an ELECT / BRA.U.ANY loop per MMA, see gemm_tc.cu::issue_mmas) =================
+  } else if (warp >= L_MMA_WARP && warp < L_LOAD_WARP) {
+    // ================= MMA issuers: the whole converged warp runs the loop, the MMAs are guarded by elect_one() (bare
+    // UTCHMMA instead of an ELECT / BRA.U.ANY loop per MMA, see gemm_tc.cu::issue_mmas).  TWO issuer warps take alternate
+    // chunks (issuer w: chunk ring stage w, accumulators w and w + 2): between the last MMA of one chunk and the first of its
+    // next the issuing thread runs commits, barrier polls and fences, more than the tensor core's queue covers -- with one
+    // issuer the pipe sat idle for a quarter of every chunk (2190 cycles per chunk of 1664 with nothing else running,
+    // profiles/r04f_k4096_phases.txt). =================
+    const uint32_t w = (uint32_t)(warp - L_MMA_WARP);
     constexpr uint32_t idesc = make_idesc_tf32(CHUNK);
     const bool elected = elect_one();
     const uint64_t xh_d = make_desc_sw128(smem_u32(xa));
@@ -1058,11 +1067,14 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
 #pragma unroll 1
     for (int i = 0; i < ntl; ++i) {
       mbar_wait(&sh->a_full, (uint32_t)i & 1u);
+      bool mine = false;
 #pragma unroll 1
       for (int c = 0; c < p.nchunks; ++c, ++g) {
-        const uint32_t sb = g & (uint32_t)(BBARS - 1), par = (g >> BBARS_LOG2) & 1u, s = sb & (uint32_t)(BSTAGES - 1);
+        if (ISSUERS == 2 && (g & 1u) != w) continue;
+        mine = true;
+        const uint32_t s = g & 1u, par = (g >> 1) & 1u;
         const uint32_t ta = g & (uint32_t)(TBUF - 1), tpar = (g >> TBUF_LOG2) & 1u;
-        mbar_wait(&sh->b_full[sb], par);
+        mbar_wait(&sh->b_full[s], par);
         mbar_wait(&sh->tmem_empty[ta], tpar ^ 1u);
         tc_fence_after();
         const uint64_t bh_d = ring_d + (uint64_t)((s * (uint32_t)b_stage) >> 4), bl_d = bh_d + (uint64_t)(b_copy >> 4);
@@ -1083,18 +1095,20 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
           }
         }
         if (elected && !L_DBG(16)) {
-          // the |e|^2 term: (1, 0, ...) x (g_hi, 0, ...) and (1, 0, ...) x (g_lo, 0, ...)
-          const uint64_t ab = aug_b0 + (uint64_t)((s * (uint32_t)b_stage) >> 4);
-          umma_tf32(dst, aug_a, ab, idesc, 1u);
-          umma_tf32(dst, aug_a, ab + (uint64_t)((AUG_FLOATS * 4) >> 4), idesc, 1u);
+          // the |e|^2 term: (1, 1, 0, ...) x (g_hi, g_lo, 0, ...)
+          umma_tf32(dst, aug_a, aug_b0 + (uint64_t)((s * (uint32_t)b_stage) >> 4), idesc, 1u);
         }
         if (elected) {
-          umma_commit(&sh->b_empty[sb]);
+          umma_commit(&sh->b_empty[s]);
           umma_commit(&sh->tmem_full[ta]);
-          if (c == p.nchunks - 1) umma_commit(&sh->a_empty);   // the row tile may be replaced
         }
         __syncwarp();
       }
+      if (elected) {                                 // the row tile may be replaced once every issuer has said so
+        if (mine) umma_commit(&sh->a_empty);
+        else mbar_arrive(&sh->a_empty);
+      }
+      __syncwarp();
     }
     __syncwarp();
   } else {
@@ -1231,7 +1245,7 @@ bool search_large_supported(int K, int D) { return (D == 32 || D == 64) && K >= 
 
 size_t search_large_workspace_bytes(int K, int D) {
   const int nchunks = (K + CHUNK - 1) / CHUNK;
-  return ((size_t)nchunks * (2 * CHUNK * D + 2 * AUG_FLOATS) + (size_t)nchunks * CHUNK + 8) * sizeof(float);
+  return ((size_t)nchunks * (2 * CHUNK * D + AUG_FLOATS) + (size_t)nchunks * CHUNK + 8) * sizeof(float);
 }
 
 int launch_search_large(const float* z, int layout, int B, int D, int T, const float* cb, int K, int64_t* idx,
@@ -1239,7 +1253,7 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
   SearchLargeParams p;
   const int nchunks = (K + CHUNK - 1) / CHUNK;
   float* img = (float*)workspace;
-  float* se = img + (size_t)nchunks * (2 * CHUNK * D + 2 * AUG_FLOATS);
+  float* se = img + (size_t)nchunks * (2 * CHUNK * D + AUG_FLOATS);
   p.z = z; p.cb = cb; p.img = img; p.se = se; p.idx = idx; p.stats = stats;
   p.N = (long long)B * T;
   p.layout = layout; p.B = B; p.D = D; p.T = T; p.K = K;
@@ -1261,7 +1275,7 @@ int launch_search_large(const float* z, int layout, int B, int D, int T, const f
   cb_prep_kernel<<<(nchunks * CHUNK + 127) / 128, 128, 0, st>>>(cb, K, D, nchunks * CHUNK, img, se);
   VQS_LAUNCH_CHECK();
   const int a_copy = p.nkb * XT_BYTES;
-  const size_t smem = (size_t)2 * a_copy + AUG_FLOATS * 4 + (size_t)BSTAGES * (2 * p.nkb * CHUNK * 128 + 2 * AUG_FLOATS * 4) +
+  const size_t smem = (size_t)2 * a_copy + AUG_FLOATS * 4 + (size_t)BSTAGES * (2 * p.nkb * CHUNK * 128 + AUG_FLOATS * 4) +
                       ((size_t)2 * TROWS * 6 + 4 * TROWS + 2 * (1 + M3_MAX) + 2 * L_PROD_WARPS) * 4 + sizeof(LShared) + 1024 + 64;
   if (smem > 226 * 1024) {
     set_error("vq_search_large: codebook of %d codes needs %zu bytes of shared memory", K, smem);
