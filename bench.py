@@ -336,6 +336,34 @@ def vq_bench(dev, pk, rows, K=44, D=64, iters=20):
     return out
 
 
+def vq_large_bench(dev, K=4096, D=64, N=1 << 20, iters=10):
+    """BASELINE configs[3] (mfcc39-codebook_sizes sweep): the nearest-code search at K = 4096 on the streamed tcgen05 distance GEMM
+    (vq_search_large_kernel: search + index store + statistics), N = 2^20 flat rows.  'mma_tflops' counts what the tensor pipe
+    executes (3 tf32 MMAs per product + the |e|^2 k-step); the ncu tensor-pipe counter is in profiles/r04k_ncu_k4096.txt."""
+    import torch
+    from vq_vae_speech_b200 import ops, LAYOUT_FLAT_ND
+    gen = torch.Generator(device=dev).manual_seed(K)
+    W = torch.randn(K, D, device=dev, generator=gen)
+    z = torch.randn(N, D, device=dev, generator=gen)
+    ws = ops.vq_workspace(K, D, dev)
+    idx = torch.empty(N, dtype=torch.int64, device=dev)
+    st = torch.empty(K * (D + 1), device=dev)
+    for _ in range(3):
+        ops.vq_assign(z, W, LAYOUT_FLAT_ND, ws, idx=idx, stats=st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.vq_assign(z, W, LAYOUT_FLAT_ND, ws, idx=idx, stats=st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    alg = 2.0 * N * D * K
+    return {'K': K, 'D': D, 'rows': N, 'ms': ms, 'rows_per_s': N / (ms * 1e-3), 'algorithmic_tflops': alg / ms / 1e9,
+            'mma_tflops': alg * 3 * (D + 8) / D / ms / 1e9, 'counts_sum_equals_rows': bool(float(st[:K].sum()) == N),
+            'engine': 'persistent tcgen05 3xTF32 search, exact fp32 settlement of near-ties (indices identical to the fp32 search)'}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -485,6 +513,7 @@ def run_b200(args):
     vq = None
     if not args.skip_vq and world == 1:
         vq = vq_bench(dev, pk, args.vq_rows, K=args.codes)
+        vq['k4096'] = vq_large_bench(dev)
     eager = None
     if not args.skip_eager and not args.skip_cpu and world == 1:
         eager = gpu_eager_baseline(cfg, B, T, dev)

@@ -68,11 +68,12 @@ long long vqs_engine_count(int engine);
  * VQS_DP_MAX_WORLD GPUs of one NVSwitch domain. */
 #define VQS_DP_MAX_WORLD 8
 #define VQS_DP_CHANNELS 4        /* independent barrier sequences */
+#define VQS_DP_EPOCH_WORDS 8     /* local words per context: VQS_DP_CHANNELS epoch counters + flags of the fused step kernel */
 #define VQS_DP_PAD_WORD0 256     /* first 32-bit word of the signal pad this library uses (VQS_DP_CHANNELS * VQS_DP_MAX_WORLD words) */
 typedef struct {
   int rank, world;
   void* peer_pads[VQS_DP_MAX_WORLD];   /* peer_pads[r]: rank r's signal pad as mapped into THIS process (r == rank: own pad) */
-  unsigned int* epochs;                /* >= VQS_DP_CHANNELS counters in local device memory, zero-initialised once */
+  unsigned int* epochs;                /* VQS_DP_EPOCH_WORDS words in local device memory, zero-initialised once */
 } vqs_dp_ctx;
 typedef struct {
   const void* p[VQS_DP_MAX_WORLD];     /* p[r]: rank r's copy of a symmetric buffer as mapped into this process */
@@ -91,6 +92,15 @@ int vqs_dp_allreduce_small(const vqs_dp_ctx* ctx, const vqs_dp_ptrs* src, float*
 int vqs_dp_amsgrad_step(const vqs_dp_ctx* ctx, float* mc_p, const float* p_local, const float* mc_g, float* m, float* v,
                         float* vmax, long long n, long long* step, int inc_step, double lr, double beta1, double beta2,
                         double eps, int ch_before, int ch_after, vqs_stream_t stream);
+/* The same step for ONE BUCKET [lo, hi) of the flat buffers (element offsets, multiples of 4), meant for a side stream that
+ * runs BESIDE the backward pass: barrier(ch_before) ("every rank has finished this bucket's gradients"), rank r updates the
+ * r-th W-th of the bucket, barrier(ch_after) unless ch_after < 0.  The kernels are small (128 threads, <= 40 registers, no
+ * shared memory), so their blocks fit next to the 576-thread / ~200 KB tcgen05 GEMM CTAs instead of taking SMs from them.
+ * inc_step: add 1 to *step first (the first bucket of a step).  The optimizer state a rank owns is then the union of its
+ * slices of the buckets (the caller keeps that list for checkpoints). */
+int vqs_dp_amsgrad_range(const vqs_dp_ctx* ctx, float* mc_p, const float* p_local, const float* mc_g, float* m, float* v,
+                         float* vmax, long long lo, long long hi, long long* step, int inc_step, double lr, double beta1,
+                         double beta2, double eps, int ch_before, int ch_after, vqs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* VQ bottleneck                                                                                    */

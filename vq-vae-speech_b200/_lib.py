@@ -51,7 +51,7 @@ class PermuteItem(Structure):
 
 PERMUTE_MAX_ITEMS = 32
 
-DP_MAX_WORLD, DP_CHANNELS, DP_PAD_WORD0 = 8, 4, 256
+DP_MAX_WORLD, DP_CHANNELS, DP_PAD_WORD0, DP_EPOCH_WORDS = 8, 4, 256, 8
 
 
 class DpCtx(Structure):
@@ -109,6 +109,8 @@ PROTOTYPES = {
     'vqs_dp_allreduce_small': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     'vqs_dp_amsgrad_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                     c_void_p, c_int, c_double, c_double, c_double, c_double, c_int, c_int, c_void_p]),
+    'vqs_dp_amsgrad_range': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                     c_longlong, c_void_p, c_int, c_double, c_double, c_double, c_double, c_int, c_int, c_void_p]),
     'vqs_amsgrad_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_int,
                                  c_double, c_double, c_double, c_double, c_double, c_void_p]),
 }

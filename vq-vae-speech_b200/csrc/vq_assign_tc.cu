@@ -567,8 +567,8 @@ int launch_assign_tc(const float* z, int layout, int B, int D, int T, const floa
 // the tile (a_empty: tcgen05.commit), the chunk ring and the two accumulators run on across tile boundaries, and the
 // statistics of tile i (global atomics, low contention at large K) are issued by the otherwise idle producer warps from
 // the L2-hot rows while the scan warps are already on tile i + 1.
-// Warp roles (608 threads): 0-7 scan (TMEM lane quarter = warp & 3, column half = warp >> 2), 8-15 row-tile producers +
-// settlement + statistics, 16-17 MMA issuers (16 owns the TMEM allocation), 18 chunk streamer (one lane).
+// Warp roles (576 threads): 0-7 scan (TMEM lane quarter = warp & 3, column half = warp >> 2), 8-15 row-tile producers +
+// settlement + statistics, 16 MMA issuer (owns the TMEM allocation), 17 chunk streamer (one lane).
 // =====================================================================================================================
 namespace vqs {
 
@@ -601,9 +601,9 @@ constexpr int CHUNK = 128;    // codes per streamed chunk (UMMA N)
 constexpr int BSTAGES = 2;    // chunk ring depth (a probe build with FOUR barrier stages aliasing two buffers, chunk loads off, ran
                               // no faster: ring depth is not what holds the MMAs back, profiles/r04g_k4096_bbars4.txt)
 #ifndef VQS_LARGE_ISSUERS
-#define VQS_LARGE_ISSUERS 2
+#define VQS_LARGE_ISSUERS 1
 #endif
-constexpr int ISSUERS = VQS_LARGE_ISSUERS;   // MMA issuer warps; two take alternate chunks (see the issuer loop)
+constexpr int ISSUERS = VQS_LARGE_ISSUERS;   // MMA issuer warps (see the issuer loop)
 static_assert(ISSUERS == 1 || ISSUERS == 2, "one or two issuer warps");
 constexpr int L_LOAD_WARP = L_MMA_WARP + ISSUERS;
 constexpr int L_THREADS = (L_LOAD_WARP + 1) * 32;
@@ -1049,12 +1049,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) vq_search_large_kernel(const Sea
     }
     __syncwarp();
   } else if (warp >= L_MMA_WARP && warp < L_LOAD_WARP) {
-    // ================= MMA issuers: the whole converged warp runs the loop, the MMAs are guarded by elect_one() (bare
-    // UTCHMMA instead of an ELECT / BRA.U.ANY loop per MMA, see gemm_tc.cu::issue_mmas).  TWO issuer warps take alternate
-    // chunks (issuer w: chunk ring stage w, accumulators w and w + 2): between the last MMA of one chunk and the first of its
-    // next the issuing thread runs commits, barrier polls and fences, more than the tensor core's queue covers -- with one
-    // issuer the pipe sat idle for a quarter of every chunk (2190 cycles per chunk of 1664 with nothing else running,
-    // profiles/r04f_k4096_phases.txt). =================
+    // ================= MMA issuer(s): the whole converged warp runs the loop, the MMAs are guarded by elect_one() (bare
+    // UTCHMMA instead of an ELECT / BRA.U.ANY loop per MMA, see gemm_tc.cu::issue_mmas).  With VQS_LARGE_ISSUERS = 2 two
+    // warps take alternate chunks (issuer w: ring stage w, accumulators w and w + 2).  Measured (profiles/r04j_k4096_issuers.txt):
+    // the empty protocol gets faster (0.81 -> 0.53 ms) but the kernel does not (2.25 vs 2.28 ms): what looked like an issue
+    // bubble (2190 "cycles" per chunk of 1664) was the clock -- under this load the SMs run at 1.66 GHz, not 1.92
+    // (ncu: tensor pipe active 83 % of active cycles).  One issuer is the default. =================
     const uint32_t w = (uint32_t)(warp - L_MMA_WARP);
     constexpr uint32_t idesc = make_idesc_tf32(CHUNK);
     const bool elected = elect_one();

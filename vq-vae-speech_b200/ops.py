@@ -463,6 +463,17 @@ def dp_amsgrad_step(ctx, mc_p, p_local, mc_g, m, v, vmax, step, lr, beta1=0.9, b
                                   float(beta1), float(beta2), float(eps), int(ch_before), int(ch_after)), ctx)
 
 
+def dp_amsgrad_range_on(stream, ctx, mc_p, p_local, mc_g, m, v, vmax, lo, hi, step, lr, beta1=0.9, beta2=0.999, eps=1e-8,
+                        inc_step=False, ch_before=1, ch_after=-1):
+    """The optimizer + exchange of ONE BUCKET [lo, hi) of the flat buffers (vqs_dp_amsgrad_range), issued NOW on `stream` (a
+    torch.cuda.Stream: the side stream that runs beside the backward pass) -- never recorded: callers wrap it in
+    record_callable so that the fork / join with the main stream is part of the same host callable."""
+    fn = getattr(_lib.load(), 'vqs_dp_amsgrad_range')
+    _lib.check(fn(ctypes.byref(ctx), ctypes.c_void_p(int(mc_p)), _p(p_local), ctypes.c_void_p(int(mc_g)), _p(m), _p(v),
+                  _p(vmax), int(lo), int(hi), _p(step, torch.int64), int(inc_step), float(lr), float(beta1), float(beta2),
+                  float(eps), int(ch_before), int(ch_after), stream.cuda_stream))
+
+
 def normalize_features(x64, mean64, std64, out=None):
     """(x - mean) / std in float64 on the device, stored as float32 (the reference normalises in numpy float64 and casts
     with .float()): x64 (..., F) float64, mean64 / std64 (F,) float64."""

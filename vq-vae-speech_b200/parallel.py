@@ -65,7 +65,7 @@ class NvlsExchange(object):
         pad[_lib.DP_PAD_WORD0:_lib.DP_PAD_WORD0 + _lib.DP_CHANNELS * _lib.DP_MAX_WORLD].zero_()
         torch.cuda.synchronize()
         dist.barrier(group=self.pg)
-        self.epochs = torch.zeros(_lib.DP_CHANNELS, dtype=torch.int32, device=self.device)
+        self.epochs = torch.zeros(_lib.DP_EPOCH_WORDS, dtype=torch.int32, device=self.device)
         self.ctx = _lib.DpCtx()
         self.ctx.rank, self.ctx.world = self.rank, self.world
         for r in range(self.world):
@@ -101,11 +101,24 @@ class NvlsExchange(object):
         hi4 = min(lo4 + per, n4)
         return 4 * lo4, 4 * max(hi4, lo4)
 
-    def gather_sharded(self, flat):
-        """Full copy of a rank-sharded flat buffer (AMSGrad moments): every rank contributes its own slice (collective)."""
-        lo, hi = self.slice_bounds(flat.numel())
+    def range_slice(self, lo, hi):
+        """[lo', hi') of bucket [lo, hi) that this rank's optimizer shard owns -- the split of vqs_dp_amsgrad_range."""
+        b4, n4 = lo // 4, (hi - lo) // 4
+        per = (n4 + self.world - 1) // self.world
+        lo4 = b4 + per * self.rank
+        hi4 = min(lo4 + per, b4 + n4)
+        return 4 * lo4, 4 * max(hi4, lo4)
+
+    def gather_sharded(self, flat, buckets=None):
+        """Full copy of a rank-sharded flat buffer (AMSGrad moments): every rank contributes its own slice -- of the whole
+        buffer, or of every bucket in `buckets` ([(lo, hi), ...]) when the step exchanges bucket by bucket (collective)."""
         out = torch.zeros_like(flat)
-        out[lo:hi].copy_(flat[lo:hi])
+        if buckets is None:
+            owned = [self.slice_bounds(flat.numel())]
+        else:
+            owned = [self.range_slice(lo, hi) for lo, hi in buckets if hi > lo]
+        for lo, hi in owned:
+            out[lo:hi].copy_(flat[lo:hi])
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.pg)
         return out
 

@@ -100,6 +100,13 @@ class FusedTrainStep(object):
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         dev = self.dev
         self.nvls = self.comm.nvls if self.world > 1 else None
+        # Bucket-wise exchange BESIDE the backward pass (default): as soon as a bucket's gradients are final on the main stream,
+        # a side stream runs barrier + sharded AMSGrad with the reduce / broadcast through the switch for that bucket
+        # (vqs_dp_amsgrad_range: light kernels that fit next to the GEMM CTAs).  Only the last, small bucket (conv_1 .. conv_3)
+        # and the exit barrier remain after the backward pass.  VQS_DP_OVERLAP=0: the whole exchange after the backward pass,
+        # as one launch (vqs_dp_amsgrad_step).
+        self.dp_overlap = self.nvls is not None and os.environ.get('VQS_DP_OVERLAP', '1') != '0'
+        self.side = torch.cuda.Stream(device=self.dev, priority=-1) if self.dp_overlap else None   # high priority: its small blocks go first
         if self.nvls is not None:
             # symmetric buffers: the optimizer kernel reads the gradient SUM of all GPUs through the NVLS multicast mapping of
             # flat_g and broadcasts the new parameters through the one of flat_p (csrc/dp_nvls.cu)
@@ -152,7 +159,9 @@ class FusedTrainStep(object):
         cut_e = first_of('_encoder._conv_4.', 0)
         cut_3 = min(first_of('_encoder._conv_3.', 0), cut_e)
         cut_2 = min(first_of('_encoder._conv_2.', 0), cut_3)
-        if os.environ.get('VQS_DP_FINE') != '1':         # default: conv_1 .. conv_3 as ONE trailing bucket
+        # (the bucket-wise NVLS exchange wants the fine split: whatever is in the LAST bucket travels after the backward pass)
+        fine = os.environ.get('VQS_DP_FINE', '1' if self.dp_overlap else '0') == '1'
+        if not fine:                                     # NCCL default: conv_1 .. conv_3 as ONE trailing bucket
             cut_3 = cut_2 = cut_e
         self.buckets = {'dec_convT': (cut_t, total), 'dec_rest': (self.bucket_split, cut_t),
                         'enc_hi': (cut_e, self.bucket_split), 'enc_c3': (cut_3, cut_e), 'enc_c2': (cut_2, cut_3),
@@ -282,6 +291,21 @@ class FusedTrainStep(object):
     def _wait_buckets(self):
         self.comm.wait_buckets()
 
+    def _nvls_bucket(self, name, first=False, last=False):
+        """Host callable of the schedule: the gradients of bucket `name` are final on the current (main) stream -> fork to the
+        side stream, which runs barrier + optimizer + exchange of that bucket beside the rest of the backward pass; the last
+        bucket also runs the exit barrier and joins the side stream back.  Capturable (the fork / join become graph edges)."""
+        lo, hi = self.buckets[name]
+        if hi <= lo and not first and not last:
+            return
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        ops.dp_amsgrad_range_on(self.side, self.nvls.ctx, self.mc_p, self.flat_p, self.mc_g, self.flat_m, self.flat_v,
+                                self.flat_vmax, lo, hi, self.opt_step, self.lr, self.betas[0], self.betas[1], self.eps,
+                                inc_step=first, ch_before=1, ch_after=2 if last else -1)
+        if last:
+            main.wait_stream(self.side)
+
     def _emit_step(self):
         m, b, d = self.model, self.buf, self.dims
         B, T, Tq, L2, C, D, K, Fi, Fo = d['B'], d['T'], d['Tq'], d['L2'], d['C'], d['D'], d['K'], d['Fi'], d['Fo']
@@ -405,6 +429,8 @@ class FusedTrainStep(object):
         self._emit_wn_fold(*self.buckets['dec_convT'])
         if self.world > 1 and self.nvls is None:       # the three transposed convs are done: their gradients start travelling now
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_convT']))
+        if self.dp_overlap:
+            ops.record_callable(lambda: self._nvls_bucket('dec_convT', first=True))
         other = self._view('gB2', C, L2)
         R_dec = d['R_dec']
         gh = self._view('gH2', R_dec, L2)
@@ -431,6 +457,8 @@ class FusedTrainStep(object):
         self._emit_wn_fold(*self.buckets['dec_rest'])
         if self.world > 1 and self.nvls is None:       # decoder gradients are complete: allreduce the rest of them under the encoder's backward
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['dec_rest']))
+        if self.dp_overlap:
+            ops.record_callable(lambda: self._nvls_bucket('dec_rest'))
 
         # ---- 6. VQ backward (autograd of ema.py:165-169 / vector_quantizer.py:136-141), upstream d(loss)/d(vq_loss) = 1
         n_local = B * Tq
@@ -478,6 +506,8 @@ class FusedTrainStep(object):
         self._emit_wn_fold(*self.buckets['enc_hi'])
         if self.world > 1 and self.nvls is None:       # conv_4 .. pre_vq (and the codebook gradient) are final
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_hi']))
+        if self.dp_overlap:
+            ops.record_callable(lambda: self._nvls_bucket('enc_hi'))
         # conv_3 (k4 s2 p2): a3 = relu(conv3(h2))
         F.conv1d_wgrad(gp3, b['h2'], G[E + '_conv_3.weight'], 2, 2, ws)
         ops.bias_grad(gp3, G[E + '_conv_3.bias'])
@@ -485,6 +515,8 @@ class FusedTrainStep(object):
         self._emit_wn_fold(*self.buckets['enc_c3'])
         if self.world > 1 and self.nvls is None:
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_c3']))
+        if self.dp_overlap:
+            ops.record_callable(lambda: self._nvls_bucket('enc_c3'))
         cdgrad(gp3, E + '_conv_3.weight', T, 2, 2, out=gh2, out2=gp2, mask2=b['m2'], mask2_kind=MASK_U8)
         # conv_2: h2 = relu(p2) + a1 ; a1 = relu(p1)
         F.conv1d_wgrad(gp2, b['a1'], G[E + '_conv_2.weight'], 1, 1, ws)
@@ -492,6 +524,8 @@ class FusedTrainStep(object):
         self._emit_wn_fold(*self.buckets['enc_c2'])
         if self.world > 1 and self.nvls is None:
             ops.record_callable(lambda: self._allreduce_bucket(*self.buckets['enc_c2']))
+        if self.dp_overlap:
+            ops.record_callable(lambda: self._nvls_bucket('enc_c2'))
         gp1 = self._view('gA2', C, T)
         cdgrad(gp2, E + '_conv_2.weight', T, 1, 1, out=gp1, add_pre=gh2, mask=b['a1'],
                        mask_kind=MASK_FLOAT)
@@ -501,6 +535,9 @@ class FusedTrainStep(object):
         # ---- 8. gradient allreduce (average) + fused AMSGrad over the flat buffers (trainer.py:41-42,68) ----
         g_scale = 1.0
         self._emit_wn_fold(*self.buckets['enc_c1'])
+        if self.dp_overlap:       # the last bucket, the exit barrier, and the join of the side stream
+            ops.record_callable(lambda: self._nvls_bucket('enc_c1', last=True))
+            return
         if self.nvls is not None:
             # the gradient allreduce is folded into the optimizer: barrier, Adam on this rank's slice with
             # g = multimem.ld_reduce(gradients of all GPUs) / W, parameters broadcast by multimem.st, barrier.  Nothing ran
@@ -665,7 +702,8 @@ def optimizer_state_dict(step):
     nstep = int(step.opt_step.item())
     fm, fv, fx = step.flat_m, step.flat_v, step.flat_vmax
     if getattr(step, 'nvls', None) is not None:     # moments are sharded over the ranks: collect them (collective call)
-        fm, fv, fx = (step.nvls.gather_sharded(t) for t in (fm, fv, fx))
+        bk = list(step.buckets.values()) if getattr(step, 'dp_overlap', False) else None
+        fm, fv, fx = (step.nvls.gather_sharded(t, bk) for t in (fm, fv, fx))
     if nstep > 0:
         for name in step.param_names:
             off, p = step.param_offsets[name], params[name]
