@@ -362,7 +362,11 @@ extern "C" int vqs_dp_amsgrad_step(const vqs_dp_ctx* ctx, float* mc_p, const flo
   const long long n4 = n / 4;
   const long long per = (n4 + ctx->world - 1) / ctx->world;
   const long long lo4 = per * ctx->rank, hi4 = lo4 + per < n4 ? lo4 + per : n4;
-  static const bool fused = !(getenv("VQS_DP_FUSED") && atoi(getenv("VQS_DP_FUSED")) == 0);
+  // VQS_DP_FUSED=1: the one-launch kernel.  Measured at 2 GPUs it is no faster than the four launches (0.187 - 0.199 ms against
+  // 0.191 ms per call, profiles/r04o_dp_step_2gpu.txt: the step is bound by what crosses the links -- with NVLS every GPU's own
+  // copy travels to the switch as well, 73 MB in and out per GPU at 8 GPUs at the ~400 GB/s per direction NCCL also reaches
+  // here), so the simpler sequence of launches stays the default.
+  static const bool fused = getenv("VQS_DP_FUSED") && atoi(getenv("VQS_DP_FUSED")) == 1;
   if (fused) {
     // one launch: entry barrier, sharded update with the reduce and the broadcast through the switch, exit barrier.  Every block
     // must be resident at once (the blocks wait for block 0): at most 2 per SM of 256 threads.

@@ -100,12 +100,14 @@ class FusedTrainStep(object):
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         dev = self.dev
         self.nvls = self.comm.nvls if self.world > 1 else None
-        # Bucket-wise exchange BESIDE the backward pass (default): as soon as a bucket's gradients are final on the main stream,
-        # a side stream runs barrier + sharded AMSGrad with the reduce / broadcast through the switch for that bucket
-        # (vqs_dp_amsgrad_range: light kernels that fit next to the GEMM CTAs).  Only the last, small bucket (conv_1 .. conv_3)
-        # and the exit barrier remain after the backward pass.  VQS_DP_OVERLAP=0: the whole exchange after the backward pass,
-        # as one launch (vqs_dp_amsgrad_step).
-        self.dp_overlap = self.nvls is not None and os.environ.get('VQS_DP_OVERLAP', '1') != '0'
+        # Default: the whole exchange after the backward pass (vqs_dp_amsgrad_step).  VQS_DP_OVERLAP=1: bucket-wise exchange
+        # BESIDE the backward pass -- as soon as a bucket's gradients are final on the main stream, a side stream runs barrier +
+        # sharded AMSGrad with the reduce / broadcast through the switch for that bucket (vqs_dp_amsgrad_range: light kernels
+        # that fit next to the GEMM CTAs); only the last, small bucket and the exit barrier remain after the backward pass.
+        # Built, parity-green, and measured SLOWER at 2 GPUs (2.378 ms per step, 2.448 with the max-smem carve-out hint, against
+        # 2.371 for the default and 2.227 for two independent replicas on the same box): what the exchange takes from the
+        # GEMMs it runs beside costs more than hiding it gains.  Kept as an option.
+        self.dp_overlap = self.nvls is not None and os.environ.get('VQS_DP_OVERLAP', '0') == '1'
         self.side = torch.cuda.Stream(device=self.dev, priority=-1) if self.dp_overlap else None   # high priority: its small blocks go first
         if self.nvls is not None:
             # symmetric buffers: the optimizer kernel reads the gradient SUM of all GPUs through the NVLS multicast mapping of
