@@ -200,7 +200,8 @@ int vqs_vq_grad_codebook(const float* stats, const float* codebook, const float*
  * (d1, d0, k) arrangement the other two cases need.  With a_tap_major != 0, A is instead (M, ksz, Cred) -- reduction
  * index j*Cred + c -- the arrangement the tensor-core engines require (vqs_permute_weight modes 1 and 2).  With
  * a_tap_major == 2, A is the pre-split, pre-swizzled tensor-core operand IMAGE of that matrix (vqs_permute_weight
- * modes 3 and 4; Cred % 32 == 0): the GEMM fetches its A tiles with TMA bulk copies.
+ * modes 3 and 4): the GEMM fetches its A tiles with TMA bulk copies.  The image is Cred rounded up to a multiple of 32 wide;
+ * the extra channels are zeros in the image and are read as zeros from X (Cred stays the real channel count here).
  *
  * Epilogue, per output element (b, m, l), out tensors are NCL (B, M, Lout):
  *   v = acc + bias[m]                       (bias may be NULL)
@@ -270,8 +271,9 @@ int vqs_bias_grad(const float* g, int B, int M, int L, float* db, int accumulate
  *   mode 0: out[d1][d0][k]   (swap the channel dims)
  *   mode 1: out[d0][k][d1]   (tap-major, same orientation)
  *   mode 2: out[d1][k][d0]   (tap-major, channel dims swapped)
- *   mode 3 / 4: tensor-core operand image of the mode-1 / mode-2 matrix: ceil(M/128) * (k*Cred/32) blocks of 8192 floats
- *               ([hi | lo] x 128 rows x 32 floats, SWIZZLE_128B), M = d0 / d1, Cred = d1 / d0 */
+ *   mode 3 / 4: tensor-core operand image of the mode-1 / mode-2 matrix: ceil(M/128) * (k*ceil(Cred/32)) blocks of 8192
+ *               floats ([hi | lo] x 128 rows x 32 floats, SWIZZLE_128B), M = d0 / d1, Cred = d1 / d0; rows beyond M and
+ *               channels beyond Cred are zeros */
 int vqs_permute_weight(const float* w, int d0, int d1, int k, int mode, float* out, vqs_stream_t stream);
 
 /* The same re-arrangement for up to VQS_PERMUTE_MAX_ITEMS weights in ONE launch (the training step rebuilds ~25 GEMM

@@ -145,11 +145,13 @@ def test_benchmarked_config_matches_live_reference(B, T):
     ref64 = _Reference(cfg, sd, seed, exact=True)
     model = model.to(dev).train()
     eng = FusedTrainStep(model, B, T, cfg['learning_rate'], use_graph=True, precision='3xtf32')
-    # every conv-like GEMM with Cred % 32 == 0 must run on tcgen05; the 39-channel layers are the only CUDA-core ones
+    # every conv-like GEMM must run on tcgen05, the two 39-channel layers through operand images padded to 64 channels
+    from vq_vae_speech_b200 import functional as F
     conv = [e[2] for e in eng.schedule if e[0] is not None and e[0].__name__ == 'vqs_conv_gemm']
     wgr = [e[2] for e in eng.schedule if e[0] is not None and e[0].__name__ == 'vqs_wgrad_gemm']
-    want_cc = sum(1 for d in conv if d.Cred % 32 != 0)
-    assert want_cc == 2 and len(conv) - want_cc >= 30
+    assert sum(1 for d in conv if d.Cred % 32 != 0) == 2
+    want_cc = sum(1 for d in conv if not F.conv_tc_eligible(d.M, d.Cred, '3xtf32'))
+    assert want_cc == 0 and len(conv) >= 32
     gen = torch.Generator().manual_seed(seed)
     flipped_total = 0
     for s in range(steps):
@@ -248,8 +250,9 @@ def test_eligible_layers_of_the_reference_fixtures_run_on_tcgen05(case):
     g = load_golden(case)
     model, cfg = _build(g, dev)
     eng = FusedTrainStep(model, int(g['B']), int(g['T']), cfg['learning_rate'], use_graph=False, precision='3xtf32')
+    from vq_vae_speech_b200 import functional as F
     conv = [e[2] for e in eng.schedule if e[0] is not None and e[0].__name__ == 'vqs_conv_gemm']
-    eligible = sum(1 for d in conv if d.Cred % 32 == 0)
+    eligible = sum(1 for d in conv if F.conv_tc_eligible(d.M, d.Cred, '3xtf32'))   # (39-channel layers: padded images from M = 128 on)
     assert eligible >= len(conv) - 2 and eligible >= 30
     if cfg['use_jitter']:
         np.random.seed(int(g['seed']))

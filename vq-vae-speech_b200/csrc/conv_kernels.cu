@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
 // Weight re-arrangement through a 32 x 32 x k shared-memory tile: global reads and writes are both contiguous runs
 // (the first version read with stride d1*k in modes 0/2: 13.7 us per 7 MB weight, 8 % of the training step).
 //   w[a][b][j]  ->  mode 0: out[b][a][j]   mode 1: out[a][j][b]   mode 2: out[b][j][a]
-//   modes 3 / 4: tensor-core operand IMAGE of the tap-major matrix A[m][j*Cred + c] (mode 3: m = a, c = b; mode 4: m = b,
-//   c = a): for every (128-row tile mt, 32-wide k-block kb) one contiguous 32 KB block [hi 16 KB | lo 16 KB], each
+//   modes 3 / 4: tensor-core operand IMAGE of the tap-major matrix A[m][j*CredP + c] (mode 3: m = a, c = b; mode 4: m = b,
+//   c = a; CredP = Cred rounded up to a multiple of 32, the extra channels are zeros): for every (128-row tile mt, 32-wide k-block kb) one contiguous 32 KB block [hi 16 KB | lo 16 KB], each
 //   copy laid out exactly as the MMA reads it (128 rows x 128 B, SWIZZLE_128B), values pre-split x = hi + lo.  The GEMM
 //   kernel then fetches its A operand with ONE cp.async.bulk per k-block instead of 512 thread loads + splits.
 template <int KS>
@@ -490,7 +490,9 @@ __device__ __forceinline__ void permute_weight_tile(const float* __restrict__ w,
       if (a < d0 && b < d1) out[((size_t)b * KS + j) * d0 + a] = tile[ar * ROW + br * KS + j];
     }
   } else {                  // operand image: 32 consecutive c of one (m, j) = one swizzled 128-byte row of a k-block
-    const int Cred = (mode == 3) ? d1 : d0;
+    // the image's reduction width is Cred rounded UP to whole 32-wide k-blocks (Cred = 39 -> 64): channels beyond Cred are
+    // never written and stay zero (the host zero-fills padded images), the GEMM's activation loader reads them as zeros
+    const int Cred = ((((mode == 3) ? d1 : d0) + 31) >> 5) << 5;
     const int nkb = KS * Cred / 32;
     // 16 bytes per store: the swizzle permutes whole 16-byte pieces of a row, so 4 consecutive c stay together (the first
     // version stored 4 bytes per thread: 24 store and 12 load instructions per thread and tile, 0.137 ms per training step
@@ -604,16 +606,25 @@ extern "C" int vqs_conv_gemm(const vqs_conv_gemm_desc* d, vqs_stream_t stream) {
   p.Ntot = d->B * d->Lout;
   p.a_vec = (p.Ktot % 4 == 0) && ((reinterpret_cast<uintptr_t>(d->A) & 15) == 0);
   p.divL = FastDiv((uint32_t)d->Lout);
-  p.cpb = d->Cred / 32 > 0 ? d->Cred / 32 : 1;
+  p.cred_real = d->Cred;
+  if (d->a_tap_major == 2 && d->Cred % 32 != 0) {
+    // operand image of a layer whose channel count is not a multiple of the 32-wide k-block (the 39 MFCC channels): the image was
+    // built for Cred rounded up (vqs_permute_weight), the GEMM runs over the padded width and its activation loader reads the
+    // channels that do not exist as zeros (cred_real)
+    p.d.Cred = (d->Cred + 31) / 32 * 32;
+    p.Ktot = p.d.Cred * d->ksz;
+    p.a_vec = (p.Ktot % 4 == 0) && ((reinterpret_cast<uintptr_t>(d->A) & 15) == 0);
+  }
+  p.cpb = p.d.Cred / 32 > 0 ? p.d.Cred / 32 : 1;
   p.divCpb = FastDiv((uint32_t)p.cpb);
-  p.divCred = FastDiv((uint32_t)d->Cred);
+  p.divCred = FastDiv((uint32_t)p.d.Cred);
   p.splits = 1;
   p.kt_per_split = 0;
   p.partial = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (d->a_tap_major == 2) {
     VQS_CHECK_ARG(d->precision != VQS_PREC_FP32 && conv_tc_supported(p),
-                  "vqs_conv_gemm: an operand image (a_tap_major = 2) needs a tensor-core precision and Cred %% 32 == 0");
+                  "vqs_conv_gemm: an operand image (a_tap_major = 2) needs a tensor-core precision");
     count_engine(VQS_ENGINE_CONV_TC);
     return launch_conv_tc(p, d->precision, st);
   }
@@ -719,9 +730,9 @@ extern "C" int vqs_permute_weight(const float* w, int d0, int d1, int k, int mod
                 "vqs_permute_weight: bad arguments (kernel size 1..4, mode 0..4)");
   if (mode >= 3) {
     const int M = mode == 3 ? d0 : d1, Cred = mode == 3 ? d1 : d0;
-    VQS_CHECK_ARG(Cred % 32 == 0, "vqs_permute_weight: operand images need Cred %% 32 == 0 (got %d)", Cred);
-    if (M % 128 != 0)   // rows beyond M stay zero
-      VQS_CUDA(cudaMemsetAsync(out, 0, (size_t)((M + 127) / 128) * (k * Cred / 32) * 8192 * sizeof(float),
+    const int CredP = (Cred + 31) / 32 * 32;
+    if (M % 128 != 0 || Cred != CredP)   // rows beyond M and channels beyond Cred stay zero
+      VQS_CUDA(cudaMemsetAsync(out, 0, (size_t)((M + 127) / 128) * (k * CredP / 32) * 8192 * sizeof(float),
                                (cudaStream_t)stream));
   }
   dim3 grid((d1 + 31) / 32, (d0 + 31) / 32);
@@ -747,9 +758,9 @@ extern "C" int vqs_permute_weights(const vqs_permute_item* items, int n, vqs_str
                   "vqs_permute_weights: bad item %d (kernel size 1..4, mode 0..4)", i);
     if (q.mode >= 3) {
       const int M = q.mode == 3 ? q.d0 : q.d1, Cred = q.mode == 3 ? q.d1 : q.d0;
-      VQS_CHECK_ARG(Cred % 32 == 0, "vqs_permute_weights: operand images need Cred %% 32 == 0 (item %d: %d)", i, Cred);
-      if (M % 128 != 0)   // rows beyond M stay zero
-        VQS_CUDA(cudaMemsetAsync(q.out, 0, (size_t)((M + 127) / 128) * (q.k * Cred / 32) * 8192 * sizeof(float), st));
+      const int CredP = (Cred + 31) / 32 * 32;
+      if (M % 128 != 0 || Cred != CredP)   // rows beyond M and channels beyond Cred stay zero
+        VQS_CUDA(cudaMemsetAsync(q.out, 0, (size_t)((M + 127) / 128) * (q.k * CredP / 32) * 8192 * sizeof(float), st));
     }
     pb.w[i] = q.w; pb.out[i] = q.out; pb.d0[i] = q.d0; pb.d1[i] = q.d1;
     pb.ks[i] = (unsigned char)q.k; pb.mode[i] = (unsigned char)q.mode;

@@ -9,6 +9,7 @@ struct ConvParams {
   int Ktot, Ntot;
   int a_vec;  // A rows are 16-byte aligned and Ktot % 4 == 0
   int cpb;    // 32-wide k-blocks per tap (tap-major A): Cred / 32
+  int cred_real;   // channels that exist in X; d.Cred is the image's padded width when an operand image covers Cred % 32 != 0
   FastDiv divL, divCpb, divCred;
   // split-K (tensor-core engines, few-tile GEMMs with a bias-only epilogue): grid.z CTAs take kt_per_split k-blocks each
   // and write raw accumulators to partial[z][M][Ntot]; conv_splitk_epilogue_kernel sums them and adds the bias

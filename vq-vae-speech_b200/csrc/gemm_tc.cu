@@ -183,8 +183,9 @@ __device__ __forceinline__ void load_conv(const ConvParams& p, int kb, ConvRegs<
   }
   ok = ok && pn < d.Lin;
   const float* ptr = xb + (long long)pn * d.x_sl + (long long)(c0 + bk0 * 4) * d.x_sc;
+  const int cleft = p.cred_real - (c0 + bk0 * 4);     // channels of X from this thread's first one on (padded images: < CH * 4)
 #pragma unroll
-  for (int e = 0; e < ConvRegs<BN>::CH * 4; ++e) rg.b[e] = ok ? __ldg(ptr + (long long)e * d.x_sc) : 0.f;
+  for (int e = 0; e < ConvRegs<BN>::CH * 4; ++e) rg.b[e] = (ok && e < cleft) ? __ldg(ptr + (long long)e * d.x_sc) : 0.f;
 }
 
 // offA = byte offset of this thread's first A chunk, offB[ci] of its B chunks (k-block invariant)
@@ -489,8 +490,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams<M
         }
         ok = ok && pn < d.Lin;
         const float* ptr = xb + (long long)pn * d.x_sl + (long long)c0 * d.x_sc;
+        const int cleft = prm.p.cred_real - (c0 + part * CPT);   // channels of X from this thread's first one on
 #pragma unroll
-        for (int e = 0; e < CPT; ++e) v[e] = ok ? __ldg(ptr + (long long)e * d.x_sc) : 0.f;
+        for (int e = 0; e < CPT; ++e) v[e] = (ok && e < cleft) ? __ldg(ptr + (long long)e * d.x_sc) : 0.f;
       };
       if (g < nkb) load(g);
       for (int i = g; i < nkb; i += S) {

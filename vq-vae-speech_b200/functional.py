@@ -21,8 +21,8 @@ def convT_out_len(Lin, k, pad):
 
 
 # GEMM-ready weight arrangements.  role -> permute mode for (operand image, tap-major matrix, canonical [None = as is]).
-# The tensor-core engines take the pre-split, pre-swizzled operand IMAGE (vqs_permute_weight modes 3 / 4; needs
-# Cred % 32 == 0); everything else runs the canonical arrangement on the exact-fp32 CUDA-core engine.
+# The tensor-core engines take the pre-split, pre-swizzled operand IMAGE (vqs_permute_weight modes 3 / 4; Cred is padded with
+# zero channels to whole 32-wide k-blocks); everything else runs the canonical arrangement on the exact-fp32 CUDA-core engine.
 import collections
 import os
 
@@ -36,14 +36,22 @@ def _role_dims(w_shape, role):
     return (d0, d1, k) if role in ('conv_fwd', 'convT_dgrad') else (d1, d0, k)     # (M, Cred, ksz)
 
 
+def conv_tc_eligible(M, Cred, precision=None):
+    """True when a conv-like GEMM with M output rows and reduction width Cred (channels) runs on tcgen05: a tensor-core
+    precision and either whole 32-wide k-blocks, or more than one of them under at least one full 128-row tile (the 39 MFCC
+    channels of the 768-wide model: an operand image padded to 64 with zero channels; small layers would be mostly padding in
+    both directions and stay on the exact CUDA-core kernel)."""
+    prec = ops.get_precision() if precision is None else precision
+    return prec != 'fp32' and (Cred % 32 == 0 or (Cred > 32 and M >= 128 and not _NO_IMAGE))
+
+
 def gemm_weight_layout(w_shape, role, precision=None):
     """(tap, permute mode or None, number of floats of the GEMM operand buffer) for a weight of shape w_shape."""
-    prec = ops.get_precision() if precision is None else precision
     M, Cred, k = _role_dims(w_shape, role)
-    if prec != 'fp32' and Cred % 32 == 0:
+    if conv_tc_eligible(M, Cred, precision):
         if _NO_IMAGE:     # plain tap-major fp32 matrix [M][ksz][Cred]: the GEMM's producer warps load and split it themselves
             return 1, {3: 1, 4: 2}[_ROLES[role][0]], M * Cred * k
-        return 2, _ROLES[role][0], ((M + 127) // 128) * (k * Cred // 32) * 8192
+        return 2, _ROLES[role][0], ((M + 127) // 128) * (k * ((Cred + 31) // 32)) * 8192
     return 0, _ROLES[role][1], M * Cred * k
 
 

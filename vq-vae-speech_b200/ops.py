@@ -293,7 +293,8 @@ def permute_weight(w, out=None, mode=0):
     d0, d1, k = w.shape
     if out is None:
         shape = {0: (d1, d0, k), 1: (d0, k, d1), 2: (d1, k, d0),
-                 3: (((d0 + 127) // 128) * (k * d1 // 32) * 8192,), 4: (((d1 + 127) // 128) * (k * d0 // 32) * 8192,)}[mode]
+                 3: (((d0 + 127) // 128) * (k * ((d1 + 31) // 32)) * 8192,),
+                 4: (((d1 + 127) // 128) * (k * ((d0 + 31) // 32)) * 8192,)}[mode]
         out = torch.empty(*shape, dtype=torch.float32, device=w.device)
     _call('vqs_permute_weight', (_p(w), d0, d1, k, mode, _p(out)))
     return out
