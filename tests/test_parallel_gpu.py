@@ -137,11 +137,21 @@ def _nccl_worker(rank, world, port, ret):
     os._exit(0)
 
 
-def test_fused_step_data_parallel_nccl_in_cuda_graph():
-    """The path bench.py times under torch.distributed.run: NCCL allreduces captured into the step's CUDA graph, tcgen05
-    3xTF32 GEMMs, two GPUs.  Step 0 (eager) is checked against the per-shard oracle emulation of the contract (SURVEY 8e);
-    steps 1-2 (capture + replay) must keep the replicated state bit-identical on both ranks and finite (bench.py's
-    parity_check additionally asserts on every multi-GPU run that a graph replay equals the eager-NCCL replay bit for bit)."""
+EXCHANGES = {   # environment of the spawned ranks -> which exchange the step runs (parallel.py, trainer.py, csrc/dp_nvls.cu)
+    'nvls': {},                                   # default: own kernels over the NVLS multicast mapping, four launches after backward
+    'nvls_one_launch': {'VQS_DP_FUSED': '1'},     # the same exchange as ONE launch with in-kernel barriers
+    'nvls_beside_backward': {'VQS_DP_OVERLAP': '1'},   # bucket-wise on a side stream (vqs_dp_amsgrad_range)
+    'nccl': {'VQS_DP_NVLS': '0'},                 # NCCL allreduces captured into the graph
+}
+
+
+@pytest.mark.parametrize('exchange', sorted(EXCHANGES))
+def test_fused_step_data_parallel_nccl_in_cuda_graph(exchange):
+    """The path bench.py times under torch.distributed.run: the gradient / statistics exchange (every variant the library has)
+    captured into the step's CUDA graph, tcgen05 3xTF32 GEMMs, two GPUs.  Step 0 (eager) is checked against the per-shard
+    oracle emulation of the contract; steps 1-2 (capture + replay) must keep the replicated state bit-identical on
+    both ranks and finite (bench.py's parity_check additionally asserts on every multi-GPU run that a graph replay equals the
+    eager-NCCL replay bit for bit)."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip('needs two CUDA devices (run with gpurun --gpus 2)')
     from oracle import model_oracle as mo
@@ -168,7 +178,19 @@ def test_fused_step_data_parallel_nccl_in_cuda_graph():
         states.append((out['vq_loss'], c['vq']['idx']))
     avg = {k: sum(gr[k] for gr in grads) / world for k in grads[0]}
     ret = mp.Manager().dict()
-    mp.spawn(_nccl_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    keys = ('VQS_DP_FUSED', 'VQS_DP_OVERLAP', 'VQS_DP_NVLS')
+    saved = dict((k, os.environ.get(k)) for k in keys)
+    for k in keys:
+        os.environ.pop(k, None)
+    os.environ.update(EXCHANGES[exchange])               # the spawned ranks inherit the environment
+    try:
+        mp.spawn(_nccl_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
+    assert ret[0]['nvls'] == (exchange != 'nccl')
     for r in range(world):
         vq_loss, idx = states[r]
         assert np.array_equal(ret[r]['steps'][0]['idx'], idx)
