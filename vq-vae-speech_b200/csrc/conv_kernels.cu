@@ -527,6 +527,10 @@ __device__ __forceinline__ void permute_weight_tile(const float* __restrict__ w,
         *reinterpret_cast<float4*>(out + base + 4096 + off) = l;
       }
     } else {
+      // edge tiles, and tiles that lie wholly in the padding (the grid covers the PADDED image: rows up to the next multiple of
+      // 128, channels up to the next multiple of 32): the tile load put zeros wherever w has no element, so every word of the
+      // image is written by exactly one block and no memset is needed
+      const int Mpad = ((((mode == 3) ? d0 : d1) + 127) >> 7) << 7;
       for (int i = tid; i < 32 * 32 * KS; i += 256) {
         const int cr = i & 31, t = i >> 5;        // cr: position along c (the fast index of the image row)
         const int j = t % KS, mr = t / KS;
@@ -535,12 +539,11 @@ __device__ __forceinline__ void permute_weight_tile(const float* __restrict__ w,
         if (mode == 3) {
           m = a0 + mr; c = b0 + cr;
           v = tile[mr * ROW + cr * KS + j];
-          if (m >= d0 || c >= d1) continue;
         } else {
           m = b0 + mr; c = a0 + cr;
           v = tile[cr * ROW + mr * KS + j];
-          if (m >= d1 || c >= d0) continue;
         }
+        if (m >= Mpad || c >= Cred) continue;
         const int kk = j * Cred + c;
         const int kb = kk >> 5, kcol = kk & 31, r = m & 127, mt = m >> 7;
         const size_t base = ((size_t)mt * nkb + kb) * 8192;   // floats: 2 copies x 4096
@@ -551,6 +554,14 @@ __device__ __forceinline__ void permute_weight_tile(const float* __restrict__ w,
       }
     }
   }
+}
+
+// tile-grid extents of an item: the source (d0, d1) for the plain re-arrangements, the PADDED image for modes 3 / 4
+__host__ __device__ __forceinline__ int permute_ext0(int d0, int mode) {
+  return mode < 3 ? d0 : (mode == 3 ? (d0 + 127) / 128 * 128 : (d0 + 31) / 32 * 32);
+}
+__host__ __device__ __forceinline__ int permute_ext1(int d1, int mode) {
+  return mode < 3 ? d1 : (mode == 3 ? (d1 + 31) / 32 * 32 : (d1 + 127) / 128 * 128);
 }
 
 template <int KS>
@@ -577,7 +588,7 @@ __global__ void __launch_bounds__(256) permute_weights_kernel(const __grid_const
   while (it + 1 < pb.n && (int)blockIdx.x >= pb.first[it + 1]) ++it;
   const int local = blockIdx.x - pb.first[it];
   const int d0 = pb.d0[it], d1 = pb.d1[it], mode = pb.mode[it];
-  const int nbx = (d1 + 31) / 32;
+  const int nbx = (permute_ext1(d1, mode) + 31) / 32;
   const int a0 = (local / nbx) * 32, b0 = (local % nbx) * 32;
   switch (pb.ks[it]) {
     case 1: permute_weight_tile<1>(pb.w[it], d0, d1, mode, pb.out[it], a0, b0, tile); break;
@@ -730,12 +741,10 @@ extern "C" int vqs_permute_weight(const float* w, int d0, int d1, int k, int mod
                 "vqs_permute_weight: bad arguments (kernel size 1..4, mode 0..4)");
   if (mode >= 3) {
     const int M = mode == 3 ? d0 : d1, Cred = mode == 3 ? d1 : d0;
-    const int CredP = (Cred + 31) / 32 * 32;
-    if (M % 128 != 0 || Cred != CredP)   // rows beyond M and channels beyond Cred stay zero
-      VQS_CUDA(cudaMemsetAsync(out, 0, (size_t)((M + 127) / 128) * (k * CredP / 32) * 8192 * sizeof(float),
-                               (cudaStream_t)stream));
+    (void)M;
+    (void)Cred;   // (rows beyond M and channels beyond Cred are written as zeros by the kernel: its grid covers the padded image)
   }
-  dim3 grid((d1 + 31) / 32, (d0 + 31) / 32);
+  dim3 grid((permute_ext1(d1, mode) + 31) / 32, (permute_ext0(d0, mode) + 31) / 32);
   cudaStream_t st = (cudaStream_t)stream;
   switch (k) {
     case 1: permute_weight_kernel<1><<<grid, 256, 0, st>>>(w, d0, d1, mode, out); break;
@@ -758,14 +767,13 @@ extern "C" int vqs_permute_weights(const vqs_permute_item* items, int n, vqs_str
                   "vqs_permute_weights: bad item %d (kernel size 1..4, mode 0..4)", i);
     if (q.mode >= 3) {
       const int M = q.mode == 3 ? q.d0 : q.d1, Cred = q.mode == 3 ? q.d1 : q.d0;
-      const int CredP = (Cred + 31) / 32 * 32;
-      if (M % 128 != 0 || Cred != CredP)   // rows beyond M and channels beyond Cred stay zero
-        VQS_CUDA(cudaMemsetAsync(q.out, 0, (size_t)((M + 127) / 128) * (q.k * CredP / 32) * 8192 * sizeof(float), st));
+      (void)M;
+      (void)Cred;   // (padding is written by the kernel)
     }
     pb.w[i] = q.w; pb.out[i] = q.out; pb.d0[i] = q.d0; pb.d1[i] = q.d1;
     pb.ks[i] = (unsigned char)q.k; pb.mode[i] = (unsigned char)q.mode;
     pb.first[i] = blocks;
-    blocks += ((q.d0 + 31) / 32) * ((q.d1 + 31) / 32);
+    blocks += ((permute_ext0(q.d0, q.mode) + 31) / 32) * ((permute_ext1(q.d1, q.mode) + 31) / 32);
   }
   pb.first[n] = blocks;
   pb.n = n;
