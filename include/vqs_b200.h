@@ -312,6 +312,8 @@ int vqs_mse_fwd_bwd(const float* recon, const float* target, int B, int C, int L
 int vqs_relu_fwd(const float* in, long long n, float* out, vqs_stream_t stream);
 int vqs_relu_bwd(const float* g, const float* act, long long n, float* gin, vqs_stream_t stream);
 int vqs_add(const float* a, const float* b, long long n, float* out, vqs_stream_t stream);
+/* out = x * s[0], s a DEVICE scalar: the upstream gradient of a loss node (autograd of nn.MSELoss on the module path). */
+int vqs_scale(const float* x, const float* s, long long n, float* out, vqs_stream_t stream);
 /* strided (B, L, C) -> NCL (B, C, L) copy: the `.permute(0, 2, 1).contiguous().float()` of convolutional_vq_vae.py:118. */
 int vqs_blc_to_ncl(const float* in, int B, int L, int C, float* out, vqs_stream_t stream);
 /* Speaker conditioning of the decoder input (deconvolutional_decoder.py:108-111; global_conditioning.py:52-57 repeats the

@@ -98,6 +98,7 @@ PROTOTYPES = {
     'vqs_relu_fwd': (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
     'vqs_relu_bwd': (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     'vqs_add': (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
+    'vqs_scale': (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     'vqs_blc_to_ncl': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'vqs_concat_channels': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'vqs_slice_channels': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

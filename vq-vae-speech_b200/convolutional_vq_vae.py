@@ -88,8 +88,8 @@ class DeconvolutionalDecoder(nn.Module):
             emb = nn.Embedding(len(speaker_dic), 40, padding_idx=None)
             emb.weight.data.normal_(0, 0.1)
             emb = emb.to(x.device)
-            gc = emb(speaker_id.to(x.device).view(B, -1).long()).transpose(1, 2)          # (B, 40, 1)
-            x = torch.cat([x, gc.expand(B, -1, T).contiguous()], dim=1)
+            rows = emb.weight.data[speaker_id.to(x.device).view(B).long()]                # (B, 40): a row lookup
+            x = F.concat_channels(x, rows)                                               # vqs_concat_channels
         x = self._conv_1(x)
         x = F.upsample2(x)
         x = self._residual_stack(x)

@@ -107,6 +107,10 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
                            float* __restrict__ out) {
   GRID_STRIDE(i, n) out[i] = a[i] + b[i];
 }
+__global__ void scale_kernel(const float* __restrict__ x, const float* __restrict__ s, long long n, float* __restrict__ out) {
+  const float f = s[0];
+  GRID_STRIDE(i, n) out[i] = x[i] * f;
+}
 // (B, L, C) -> (B, C, L) through a 32x32 smem tile (both sides coalesced)
 __global__ void blc_to_ncl_kernel(const float* __restrict__ in, int B, int L, int C, float* __restrict__ out) {
   __shared__ float tile[32][33];
@@ -382,6 +386,12 @@ extern "C" int vqs_relu_bwd(const float* g, const float* act, long long n, float
 extern "C" int vqs_add(const float* a, const float* b, long long n, float* out, vqs_stream_t stream) {
   VQS_CHECK_ARG(a && b && out && n > 0, "vqs_add: bad arguments");
   add_kernel<<<ew_grid(n), EW_T, 0, (cudaStream_t)stream>>>(a, b, n, out);
+  VQS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int vqs_scale(const float* x, const float* s, long long n, float* out, vqs_stream_t stream) {
+  VQS_CHECK_ARG(x && s && out && n > 0, "vqs_scale: bad arguments");
+  scale_kernel<<<ew_grid(n), EW_T, 0, (cudaStream_t)stream>>>(x, s, n, out);
   VQS_LAUNCH_CHECK();
   return 0;
 }

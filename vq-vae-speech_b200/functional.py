@@ -255,7 +255,50 @@ class MseLossFn(Function):
     @staticmethod
     def backward(ctx, g):
         (grad,) = ctx.saved_tensors
-        return grad * g, None      # g is the scalar upstream gradient (1.0 in the trainer)
+        # g is the scalar upstream gradient (1.0 in the trainer)
+        return ops.scale(grad, g.reshape(1).to(torch.float32).contiguous()), None
+
+
+class WeightNormFn(Function):
+    """w = g v / ||v|| over all dims but 0 (torch._weight_norm, dim = 0) and its gradient: vqs_weight_norm_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, v, g):
+        v, g = v.contiguous(), g.contiguous()
+        w = torch.empty_like(v)
+        norm = torch.empty(v.shape[0], dtype=torch.float32, device=v.device)
+        ops.weight_norm_fwd(v, g, w, norm)
+        ctx.save_for_backward(v, g, norm)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        v, g, norm = ctx.saved_tensors
+        gv, gg = torch.empty_like(v), torch.empty_like(g)
+        ops.weight_norm_bwd(dw.contiguous(), v, g, norm, gv, gg)
+        return gv, gg
+
+
+def weight_norm(v, g):
+    return WeightNormFn.apply(v, g)
+
+
+class ConcatChannelsFn(Function):
+    """(B, Ca, L) ++ (B, Cb) repeated over L (speaker conditioning, deconvolutional_decoder.py:108-111); the features are
+    constants (a fresh embedding per call), so only the first Ca channels pass a gradient."""
+
+    @staticmethod
+    def forward(ctx, a, v):
+        ctx.Ca = a.shape[1]
+        return ops.concat_channels(a.contiguous(), v.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.slice_channels(g.contiguous(), ctx.Ca), None
+
+
+def concat_channels(a, v):
+    return ConcatChannelsFn.apply(a, v)
 
 
 def conv1d(x, w, b, stride=1, pad=0, relu=False):

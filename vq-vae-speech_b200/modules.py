@@ -29,14 +29,36 @@ class ConvTranspose1d(nn.ConvTranspose1d):
         return F.conv_transpose1d(x, self.weight, self.bias, self.padding[0], relu=relu, out_len=out_len)
 
 
+class _WeightNormHook(object):
+    """nn.utils.weight_norm (dim = 0) with the reparametrisation on this library's kernels: same parameters in the same
+    order (`weight` is replaced by `weight_g` = ||weight|| per slice of dim 0, then `weight_v` = weight, both registered after
+    the bias, torch/nn/utils/weight_norm.py), hence the same state_dict keys and optimizer order as the reference; before
+    every forward `weight` is recomputed as g v / ||v|| by vqs_weight_norm_fwd (autograd: vqs_weight_norm_bwd)."""
+
+    def __call__(self, module, inputs):
+        module.weight = F.weight_norm(module.weight_v, module.weight_g)
+
+
+def weight_norm(module):
+    weight = module.weight
+    del module._parameters['weight']
+    module.register_parameter('weight_g', nn.Parameter(torch.norm_except_dim(weight, 2, 0).data))    # (init-time only)
+    module.register_parameter('weight_v', nn.Parameter(weight.data))
+    # a plain tensor until the first forward: the reference's builders run kaiming_normal_ on this recomputed attribute (it
+    # leaves g and v alone but consumes the host RNG, which the parameters created after it depend on)
+    module.weight = weight.data.clone()
+    module.register_forward_pre_hook(_WeightNormHook())
+    return module
+
+
 class Conv1DBuilder(object):
 
     @staticmethod
     def build(in_channels, out_channels, kernel_size, stride=1, padding=0, use_kaiming_normal=False):
         conv = Conv1d(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size, stride=stride,
                       padding=padding)
-        if use_kaiming_normal:   # weight-norm reparametrisation is host-side torch; the conv stays ours
-            conv = nn.utils.weight_norm(conv)
+        if use_kaiming_normal:   # weight-norm reparametrisation (SURVEY 8f N1) on this library's kernels, see weight_norm below
+            conv = weight_norm(conv)
             nn.init.kaiming_normal_(conv.weight)
         return conv
 
@@ -48,7 +70,7 @@ class ConvTranspose1DBuilder(object):
         conv = ConvTranspose1d(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size,
                                stride=stride, padding=padding)
         if use_kaiming_normal:
-            conv = nn.utils.weight_norm(conv)
+            conv = weight_norm(conv)
             nn.init.kaiming_normal_(conv.weight)
         return conv
 
@@ -65,12 +87,12 @@ class Residual(nn.Module):
         conv_1 = Conv1d(in_channels=in_channels, out_channels=num_residual_hiddens, kernel_size=3, stride=1,
                         padding=1, bias=False)
         if use_kaiming_normal:
-            conv_1 = nn.utils.weight_norm(conv_1)
+            conv_1 = weight_norm(conv_1)
             nn.init.kaiming_normal_(conv_1.weight)
         conv_2 = Conv1d(in_channels=num_residual_hiddens, out_channels=num_hiddens, kernel_size=1, stride=1,
                         bias=False)
         if use_kaiming_normal:
-            conv_2 = nn.utils.weight_norm(conv_2)
+            conv_2 = weight_norm(conv_2)
             nn.init.kaiming_normal_(conv_2.weight)
         # same container and indices as the reference so that state_dict keys are `_block.1.weight`, `_block.3.weight`
         self._block = nn.Sequential(nn.ReLU(True), conv_1, nn.ReLU(True), conv_2)

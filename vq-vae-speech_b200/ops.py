@@ -399,6 +399,14 @@ def add(a, b, out=None):
     return out
 
 
+def scale(x, s, out=None):
+    """x * s, s a one-element device tensor (the upstream gradient of a loss)."""
+    if out is None:
+        out = torch.empty_like(x)
+    _call('vqs_scale', (_p(x), _p(s), x.numel(), _p(out)))
+    return out
+
+
 def blc_to_ncl(x, out=None):
     B, L, C = x.shape
     if out is None:
