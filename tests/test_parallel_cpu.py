@@ -136,3 +136,34 @@ def test_shard_rejects_indivisible_batch():
     comm.world = 2
     with pytest.raises(ValueError):
         comm.shard(x)
+
+
+def test_optimizer_shards_cover_every_range_exactly_once():
+    """parallel.shard_bounds (the host mirror of the split inside vqs_dp_amsgrad_step / vqs_dp_amsgrad_range): the ranks' slices
+    of a range are disjoint, 16-byte aligned, in rank order and cover it completely -- also when trailing ranks get nothing."""
+    from vq_vae_speech_b200.parallel import shard_bounds
+    for world in (1, 2, 3, 4, 8):
+        for lo, hi in ((0, 16_400_384), (64, 64), (128, 132), (256, 256 + 4 * 5), (4096, 4096 + 4 * 1001), (0, 4 * world)):
+            cur = lo
+            for rank in range(world):
+                a, b = shard_bounds(lo, hi, world, rank)
+                assert a % 4 == 0 and b % 4 == 0 and a <= b
+                if b > a:                                   # (an empty slice may start beyond the range: never touched)
+                    assert a == cur and b <= hi
+                    cur = b
+            assert cur == hi
+
+
+def test_operand_image_layouts_pad_channels_and_rows():
+    """functional.gemm_weight_layout: operand images are ceil(M / 128) x (k * ceil(Cred / 32)) blocks of 8192 floats; the 39-channel
+    layers of the 768-wide model take padded images (tcgen05), narrow or small layers stay on the exact CUDA-core engine."""
+    from vq_vae_speech_b200 import functional as F
+    assert F.gemm_weight_layout((768, 768, 3), 'conv_fwd', '3xtf32') == (2, 3, 6 * 72 * 8192)
+    assert F.gemm_weight_layout((768, 39, 3), 'conv_fwd', '3xtf32') == (2, 3, 6 * 6 * 8192)        # Cred 39 -> 64
+    assert F.gemm_weight_layout((768, 39, 2), 'convT_dgrad', '3xtf32') == (2, 3, 6 * 4 * 8192)     # M = 768, Cred = 39
+    assert F.gemm_weight_layout((768, 39, 2), 'convT_fwd', '3xtf32') == (2, 4, 1 * 48 * 8192)      # M = 39 (one tile), Cred = 768
+    assert F.gemm_weight_layout((48, 39, 3), 'conv_fwd', '3xtf32')[0] == 0                          # M < 128: CUDA cores
+    assert F.gemm_weight_layout((768, 7, 3), 'conv_fwd', '3xtf32')[0] == 0                          # one partial k-block: CUDA cores
+    assert F.gemm_weight_layout((768, 768, 3), 'conv_fwd', 'fp32')[0] == 0                          # exact engine: canonical weights
+    assert F.conv_tc_eligible(768, 39, '3xtf32') and not F.conv_tc_eligible(64, 39, '3xtf32')
+    assert F.conv_tc_eligible(39, 768, '3xtf32') and not F.conv_tc_eligible(768, 768, 'fp32')

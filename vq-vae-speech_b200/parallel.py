@@ -95,19 +95,11 @@ class NvlsExchange(object):
     def slice_bounds(self, numel):
         """[lo, hi) of the flat buffers (in elements) that this rank's optimizer shard owns -- the split vqs_dp_amsgrad_step
         uses: float4 granules, ceil(n / 4 / W) per rank."""
-        n4 = numel // 4
-        per = (n4 + self.world - 1) // self.world
-        lo4 = per * self.rank
-        hi4 = min(lo4 + per, n4)
-        return 4 * lo4, 4 * max(hi4, lo4)
+        return shard_bounds(0, numel, self.world, self.rank)
 
     def range_slice(self, lo, hi):
         """[lo', hi') of bucket [lo, hi) that this rank's optimizer shard owns -- the split of vqs_dp_amsgrad_range."""
-        b4, n4 = lo // 4, (hi - lo) // 4
-        per = (n4 + self.world - 1) // self.world
-        lo4 = b4 + per * self.rank
-        hi4 = min(lo4 + per, b4 + n4)
-        return 4 * lo4, 4 * max(hi4, lo4)
+        return shard_bounds(lo, hi, self.world, self.rank)
 
     def gather_sharded(self, flat, buckets=None):
         """Full copy of a rank-sharded flat buffer (AMSGrad moments): every rank contributes its own slice -- of the whole
@@ -128,6 +120,17 @@ class NvlsExchange(object):
             if t.data_ptr() == tensor.data_ptr():
                 return hdl.get_buffer(rank, (numel if numel is not None else tensor.numel(),), torch.float32)
         raise KeyError('not a symmetric tensor of this exchange')
+
+
+def shard_bounds(lo, hi, world, rank):
+    """[lo', hi') of the element range [lo, hi) (multiples of 4) that rank `rank` of `world` owns in the sharded optimizer step:
+    float4 granules, ceil(n / 4 / W) per rank, trailing ranks possibly empty -- exactly the split of vqs_dp_amsgrad_step
+    (lo = 0, hi = n) and vqs_dp_amsgrad_range (csrc/dp_nvls.cu)."""
+    b4, n4 = lo // 4, (hi - lo) // 4
+    per = (n4 + world - 1) // world
+    lo4 = b4 + per * rank
+    hi4 = min(lo4 + per, b4 + n4)
+    return 4 * lo4, 4 * max(hi4, lo4)
 
 
 def nvls_available(process_group=None):
