@@ -130,8 +130,9 @@ int vqs_vq_assign(const float* z, int layout, int B, int D, int T, const float* 
  *       operands + exact fp32 settlement of every row the filter cannot decide): flat rows arrive by TMA, the reference's
  *       (B, 64, T) rows with B % 64 == 0 by a cp.async gather (2^22 rows: 0.42 / 0.58 ms against 1.23 / 3.7 ms on CUDA
  *       cores); the exact-fp32 CUDA-core search for every other shape with a shared-memory resident codebook; the streamed
- *       tcgen05 distance GEMM (3xTF32 scores + exact fp32 settlement of near-ties) for large codebooks (D = 32/64;
- *       K = 512: 1.9x, K = 4096: 4x faster than the CUDA-core search);
+ *       tcgen05 distance GEMM (persistent kernel, 3xTF32 scores + exact fp32 settlement of near-ties) for large codebooks
+ *       (D = 32/64, K <= 8192; K = 512: 4x, K = 4096: 9x faster than the CUDA-core search, 254 TFLOP/s at 2^20 rows; the
+ *       statistics of this engine are accumulated with fp32 atomics: counts exact, dw to rounding, order not fixed);
  *   0 = tensor cores wherever a tensor-core kernel exists (also the resident-codebook one);
  *   2 = CUDA cores only. */
 int vqs_vq_set_engine(int engine);
