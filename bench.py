@@ -474,6 +474,14 @@ def run_b200(args):
                 'note': {'fp32': 'exact-fp32 CUDA-core implicit GEMM', '3xtf32': 'tcgen05 kind::tf32, 3 MMAs per product '
                          '(fp32-accurate split, 1e-5 parity)', 'tf32': 'tcgen05 kind::tf32 single pass'}[args.precision]
                 + '; achieved counts ALGORITHMIC FLOPs = 2*M*Cred*k*B*L per launch (the split\'s extra MMAs are not counted)'}
+    if args.precision == '3xtf32':
+        # context for the fraction above (not part of the contract): what the tensor pipe executes is three kind::tf32 MMAs per
+        # product, and kind::tf32 runs at half the bf16 rate; the ncu counters of the same binary are in profiles/
+        roofline['context'] = {
+            'executed_tf32_tflops': 3.0 * achieved, 'tf32_peak_tflops': pk['tensor'] / 2.0,
+            'executed_frac_of_tf32_peak': 3.0 * achieved / (pk['tensor'] / 2.0),
+            'ncu': 'profiles/r04r_ncu_gemm_family.txt: sm__pipe_tensor_cycles_active 75 % (768x768x3 conv) / 52 % (wgrad) of the '
+                   'active cycles, SM clock 1.68-1.77 GHz under this load (power cap)'}
     breakdown = dict((k, {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[2] // args.steps,
                           'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[1] else None}) for k, v in fam.items())
     gemm_launches = []
