@@ -502,7 +502,7 @@ def run_b200(args):
     last = None
     for i in range(args.steps):
         eng.step(host[i % 8])          # H2D copy from pinned memory + the step
-        last = eng.losses()            # 16-byte D2H + stream sync
+        last = eng.losses()            # 32-byte D2H + stream sync
     e1.record()
     barrier()
     ems = e0.elapsed_time(e1)
@@ -511,7 +511,7 @@ def run_b200(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ems = float(tms.item())
     e2e = {'value': B * world * args.steps / (ems * 1e-3), 'unit': 'utterances/s',
-           'h2d_bytes_per_step': B * T * 39 * 4, 'd2h_bytes_per_step': 16, 'ms_per_step': ems / args.steps,
+           'h2d_bytes_per_step': B * T * 39 * 4, 'd2h_bytes_per_step': 32, 'ms_per_step': ems / args.steps,
            'last_losses': last}
 
     parity = dp_parity_check(eng, devb, world) if world > 1 else None

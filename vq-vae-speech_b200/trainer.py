@@ -244,7 +244,8 @@ class FusedTrainStep(object):
         self.dims['Lt2'] = Lt2
         b['s'], b['t1'], b['t2'] = f(B, C, L2), f(B, C, L2), f(B, C, Lt2)
         b['recon'], b['g_recon'] = f(B, Fo, T), f(B, Fo, T)
-        b['recon_loss'] = torch.zeros(1, dtype=torch.float32, device=dev)
+        # slot 5 of the VQ scalars (its kernels write [0, 5)): all losses of a step sit in ONE 32-byte vector, read back by one copy
+        b['recon_loss'] = b['vq_scalars'][5:6]
         b['one'] = torch.ones(1, dtype=torch.float32, device=dev)
         # backward scratch: two ping-pong gradient buffers per resolution + hidden-gradient buffers
         b['gA2'], b['gB2'] = f(B, C, L2 + 2), f(B, C, L2 + 2)
@@ -274,8 +275,7 @@ class FusedTrainStep(object):
         self.ws_wgrad = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         self.ws_vq = ops.vq_workspace(K, D, dev)
         self.ws_mse = ops.mse_workspace(dev)
-        self.host_scalars = torch.zeros(4, dtype=torch.float32).pin_memory()
-        self.dev_scalars = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.host_scalars = torch.zeros(8, dtype=torch.float32).pin_memory()
 
     # ------------------------------------------------------------------------------------------------
     # the step, emitted once through the recorder
@@ -646,15 +646,12 @@ class FusedTrainStep(object):
         self.graph = g
 
     def losses(self):
-        """{'loss', 'reconstruction_loss', 'vq_loss', 'perplexity'} of the last step: one packed 16-byte D2H copy + sync
-        (the reference does three .item() syncs per step, trainer.py:57,58,70)."""
-        sc = self.buf['vq_scalars']
-        self.dev_scalars[0:1].copy_(self.buf['recon_loss'])
-        self.dev_scalars[1:2].copy_(sc[3:4] if self.is_ema else sc[4:5])
-        self.dev_scalars[2:3].copy_(sc[2:3])
-        self.host_scalars.copy_(self.dev_scalars, non_blocking=True)
+        """{'loss', 'reconstruction_loss', 'vq_loss', 'perplexity'} of the last step: ONE 32-byte D2H copy of the scalar vector the
+        step's kernels wrote + sync (the reference does three .item() syncs per step, trainer.py:57,58,70)."""
+        self.host_scalars.copy_(self.buf['vq_scalars'], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        r, v, p = (float(self.host_scalars[i]) for i in range(3))
+        h = self.host_scalars
+        r, v, p = float(h[5]), float(h[3] if self.is_ema else h[4]), float(h[2])
         return {'loss': r + v, 'reconstruction_loss': r, 'vq_loss': v, 'perplexity': p}
 
     def encoding_indices(self):
