@@ -58,7 +58,8 @@ struct TcCfg {
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > STAGES_MAX ? STAGES_MAX : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers, row table*/;
   static constexpr int NACC = (PASSES == 3) ? 4 : 1;                // TMEM accumulators of BN columns each
-  static constexpr int TMEM_COLS = NACC * BN;
+  static constexpr int TMEM_USED = NACC * BN;                        // accumulator a lives at columns [a * BN, a * BN + BN)
+  static constexpr int TMEM_COLS = TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512));   // allocations are powers of two
   static constexpr int N_ISSUERS = (PASSES == 3) ? 2 : 1;           // threads that issue tcgen05.mma (see issue_mmas)
   static_assert(STAGES >= 2, "need at least a double buffer");
 };
@@ -1007,8 +1008,17 @@ int launch_tc_k(const TcParams<MODE>& prm, int ksz, dim3 grid, cudaStream_t st) 
 
 template <int MODE>
 int launch_tc(const TcParams<MODE>& prm, int ksz, int bn, int precision, dim3 grid, cudaStream_t st) {
-  bool pair = bn == 128 && grid.y % 2 == 0 && pair_enabled();
+  bool pair = (bn == 128 || bn == 96) && grid.y % 2 == 0 && pair_enabled();
   if constexpr (MODE == 0) pair = pair && prm.p.d.a_tap_major != 0;     // an image or the tap-major matrix (conv_tc_supported)
+  if constexpr (MODE == 1) {
+    if (bn == 96) {        // 96-column tiles (launch_wgrad_tc): pairs, 3xTF32 only
+      if (!pair || precision != 2) {
+        set_error("tcgen05 wgrad: 96-column tiles need the pair kernel and the 3xTF32 engine");
+        return VQS_ERR_ARG;
+      }
+      return launch_tc_k<MODE, 96, 3, 1>(prm, ksz, grid, st);
+    }
+  }
   if (precision == 2) {
     if (pair) return launch_tc_k<MODE, 128, 3, 1>(prm, ksz, grid, st);
     if (bn == 128) return launch_tc_k<MODE, 128, 3, 0>(prm, ksz, grid, st);
@@ -1188,7 +1198,18 @@ int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
 int launch_wgrad_tc(const WgradParams& p, int precision, cudaStream_t st) {
   TcParams<1> prm;
   prm.p = p;
-  const int bn = 128;
+  int bn = 128;
+  // 96-column tiles when 128-column tiles leave SMs without a tile although the kernel is paced by its producers, whose work
+  // per k-block is proportional to the rows a CTA stages (128 of A + BN / 2 of B): 768 x 2304 = 108 tiles of 128 columns on 148
+  // SMs, or 144 of 96 (each CTA stages 176 instead of 192 rows per k-block)
+  {
+    const int mt = (p.d.M + BM - 1) / BM;
+    const int t128 = ((p.Nw + 127) / 128) * mt, t96 = ((p.Nw + 95) / 96) * mt;
+    static const bool off = getenv("VQS_WGRAD_BN96") && atoi(getenv("VQS_WGRAD_BN96")) == 0;
+    if (!off && precision == 2 && p.splits == 1 && mt % 2 == 0 && pair_enabled() && p.Nw % 96 == 0 && t96 <= num_sms() &&
+        t128 < t96)
+      bn = 96;
+  }
   dim3 grid((p.Nw + bn - 1) / bn, (p.d.M + BM - 1) / BM, p.splits);
   return launch_tc<1>(prm, p.d.ksz, bn, precision, grid, st);
 }
