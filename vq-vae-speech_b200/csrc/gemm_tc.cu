@@ -1006,10 +1006,27 @@ int launch_tc_k(const TcParams<MODE>& prm, int ksz, dim3 grid, cudaStream_t st) 
   }
 }
 
+// Half-wave conv GEMMs with few k-blocks (the 1 x 1 layers at T_q = 24: 72 tiles of 128 columns, 24 k-blocks) as ONE wave of CTA
+// pairs with 64-column tiles (VQS_CONV_BN64_PAIR=0: single 128 x 64 CTAs as before; read once)
+bool conv_bn64_pair_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("VQS_CONV_BN64_PAIR");
+    cached = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  return cached == 1;
+}
+
 template <int MODE>
 int launch_tc(const TcParams<MODE>& prm, int ksz, int bn, int precision, dim3 grid, cudaStream_t st) {
   bool pair = (bn == 128 || bn == 96) && grid.y % 2 == 0 && pair_enabled();
   if constexpr (MODE == 0) pair = pair && prm.p.d.a_tap_major != 0;     // an image or the tap-major matrix (conv_tc_supported)
+  if constexpr (MODE == 0) {
+    if (bn == 64 && grid.z == 1 && grid.y % 2 == 0 && pair_enabled() && conv_bn64_pair_enabled() && prm.p.d.a_tap_major != 0) {
+      if (precision == 2) return launch_tc_k<MODE, 64, 3, 1>(prm, ksz, grid, st);
+      return launch_tc_k<MODE, 64, 1, 1>(prm, ksz, grid, st);
+    }
+  }
   if constexpr (MODE == 1) {
     if (bn == 96) {        // 96-column tiles (launch_wgrad_tc): pairs, 3xTF32 only
       if (!pair || precision != 2) {
@@ -1151,7 +1168,13 @@ int launch_conv_tc(const ConvParams& p, int precision, cudaStream_t st) {
   const int nkb = (p.Ktot + BKF - 1) / BKF;
   prm.p.splits = 1;
   prm.p.partial = nullptr;
-  if (d.splitk_ws != nullptr && nkb >= 8) {
+  // half a wave of 128-column tiles, an even number of 128-row tiles and too few k-blocks for the split below (the 1 x 1 layers at
+  // T_q = 24): one wave of 64-column CTA PAIRS instead of single 128 x 64 CTAs (0.029 -> 0.024 ms).  With 72 k-blocks the two
+  // split-K halves of 128-column tiles stay faster (0.034 against 0.039 ms measured for 64-column pairs without a split).
+  const bool half_wave_pairs = conv_bn64_pair_enabled() && pair_enabled() && mt % 2 == 0 && d.a_tap_major != 0 &&
+                               t128 * 2 <= sms && t128 * 3 > sms && t64 <= sms && nkb < 48;
+  if (half_wave_pairs) bn = 64;
+  if (!half_wave_pairs && d.splitk_ws != nullptr && nkb >= 8) {
     int s = 0, sbn = 0;
     if (t64 * 3 <= sms) {
       sbn = 64;
