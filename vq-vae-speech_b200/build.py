@@ -15,7 +15,7 @@ LIB = os.path.join(CSRC, 'libvqs_b200.so')
 STAMP = os.path.join(CSRC, '.libvqs_b200.stamp')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
-FLAGS = ['-O3', '-std=c++17', '-lineinfo'] + os.environ.get('VQS_EXTRA_NVCC_FLAGS', '').split()   # e.g. -DVQS_LARGE_CLUSTER=2
+FLAGS = ['-O3', '-std=c++17', '-lineinfo'] + os.environ.get('VQS_EXTRA_NVCC_FLAGS', '').split()   # e.g. -DVQS_DEBUG, -DVQS_LARGE_TBUF=2 (profiles/build_variant.py builds such variants next to the shipped library)
 
 
 def sources():
